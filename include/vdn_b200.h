@@ -1,0 +1,137 @@
+/* vdn_b200.h -- C ABI of libvdn_b200.so, the sm_100a kernels behind the VDN-NeRF neural-SDF
+ * volume-rendering hot path.
+ *
+ * The reference (BoifZ/VDN-NeRF) is pure Python/PyTorch and has no FFI layer; its
+ * boundary is the Python class surface of dpt_models/{embedder,fields,renderer}.py.  This library is what the
+ * host-side mirror of those classes (vdn_nerf_b200/*.py) binds with ctypes; each entry point names the
+ * reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data owned by the caller (torch tensors) unless noted
+ *     "host"; the library never allocates device memory and never synchronises;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - return value: 0 on success, otherwise a cudaError_t value (invalid arguments -> cudaErrorInvalidValue);
+ *   - N, B are counts of points / rays; row-major everywhere; "ld" = leading dimension in floats.
+ *
+ * Packed parameters.  A network's effective weights live in one fp32 buffer laid out by vdn_mlp_layout():
+ * per layer W[out_ld,in_ld], W^T[in_ld,out_ld], bias[out_ld] with in_ld/out_ld rounded up to 16 and zero
+ * padding.  A packed gradient buffer has the same layout (W and bias regions are accumulated into).
+ */
+#ifndef VDN_B200_H
+#define VDN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+/* ABI version of this header; bumped on any signature change. */
+int vdn_abi_version(void);
+/* Number of this library's kernel launches enqueued by the calling process so far (for bench.py's
+ * gpu_launches claim). */
+long long vdn_launch_count(void);
+
+/* ---- packed parameters (weight_norm: fields.py:65-66, 141-142; nn.Linear: fields.py:303-318) ------------ */
+long long vdn_mlp_layout(int L, const int* in_dims /*host*/, const int* out_dims /*host*/, long long* off_w /*host*/,
+                         long long* off_wt /*host*/, long long* off_b /*host*/);
+/* v/g/b/rows are host arrays of 2*L entries: each packed layer stacks up to two parameter sets by rows
+ * (second entry null / 0 rows when unused).  g == null means a plain (not weight-normed) weight. */
+int vdn_mlp_pack(int L, const int* in_dims, const int* out_dims, const float* const* v, const float* const* g,
+                 const float* const* b, const int* rows, float* packed, void* stream);
+/* Weight-norm backward + un-padding: packed gradient -> d weight_v, d weight_g, d bias (overwritten). */
+int vdn_mlp_unpack_grads(int L, const int* in_dims, const int* out_dims, const float* const* v,
+                         const float* const* g, const int* rows, const float* dpacked, float* const* dv,
+                         float* const* dg, float* const* db, void* stream);
+
+/* ---- SDFNetwork (fields.py:9-108).  cfg (host) = {d_in, multires, d_hidden, n_layers, d_out, skip_layer|-1} */
+int vdn_sdf_layer_dims(const int* cfg, int* in_dims, int* out_dims); /* returns number of linear layers */
+long long vdn_sdf_blob_floats(const int* cfg, long long N, int save);
+long long vdn_sdf_blobg_floats(const int* cfg, long long N);
+long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N);
+/* SDFNetwork.forward / .sdf (fields.py:72-92): sdf[N] and, when feat != null, feat[N, d_out-1] (ld ldf).
+ * blob: scratch of vdn_sdf_blob_floats(cfg, N, save) floats; save=1 keeps every pre-activation for
+ * vdn_sdf_normals / vdn_sdf_backward. */
+int vdn_sdf_forward(const int* cfg, float scale, const float* packed, const float* x, long long N, float* sdf,
+                    float* feat, int ldf, float* blob, int save, void* stream);
+/* SDFNetwork.gradient (fields.py:97-108) without autograd: normals[N, d_in] = d sdf / d x.
+ * blob: the save=1 blob of the forward on the same x; blobg: vdn_sdf_blobg_floats floats (kept for backward). */
+int vdn_sdf_normals(const int* cfg, float scale, const float* packed, const float* x, long long N, const float* blob,
+                    float* blobg, float* normals, void* stream);
+/* Backward of (sdf, feat, normals) w.r.t. the packed parameters (accumulated into dpacked) and, when
+ * d_x != null, the points (overwritten).  Replaces autograd's double backward through fields.py:97-108.
+ * Cotangents may be null.  ws: vdn_sdf_bwd_ws_floats floats. */
+int vdn_sdf_backward(const int* cfg, float scale, const float* packed, const float* x, long long N, const float* blob,
+                     const float* blobg, const float* d_sdf, const float* d_feat, int ldf, const float* d_normals,
+                     float* dpacked, float* d_x, float* ws, void* stream);
+/* extract_fields (renderer.py:10-30) for the x-slab [i0, i1): u_slab[(i-i0), j, k] = out_mul * sdf(xs[i], ys[j],
+ * zs[k]).  pts: (i1-i0)*ny*nz*3 floats scratch; blob: save=0 blob for that many points. */
+int vdn_grid_sdf(const int* cfg, float scale, const float* packed, const float* xs, const float* ys, const float* zs,
+                 int ny, int nz, int i0, int i1, float out_mul, float* u_slab, float* pts, float* blob, void* stream);
+
+/* ---- RenderingNetwork (fields.py:112-176).
+ * cfg (host) = {d_feature, mode(0 idr,1 no_view_dir,2 no_normal), d_out, d_hidden, n_layers, multires_view,
+ *               squeeze_out} */
+int vdn_rendernet_layer_dims(const int* cfg, int* in_dims, int* out_dims);
+long long vdn_rendernet_blob_floats(const int* cfg, long long N);
+long long vdn_rendernet_bwd_ws_floats(const int* cfg, long long N);
+int vdn_rendernet_forward(const int* cfg, const float* packed, const float* points, const float* normals,
+                          const float* view_dirs, const float* feats, int ldf, long long N, float* out, float* blob,
+                          void* stream);
+/* d_cin (nullable): [N, round_up(in0,16)] cotangent of the concatenated input row of fields.py:154. */
+int vdn_rendernet_backward(const int* cfg, const float* packed, long long N, const float* blob, const float* out,
+                           const float* d_out, float* dpacked, float* d_cin, float* ws, void* stream);
+
+/* ---- NeRF background field (fields.py:264-355).
+ * cfg (host) = {D, W, d_in, d_in_view, multires, multires_view, skip|-1, rgb_dims, dpt_dim(0 = no depth head)}
+ * Packed layers: pts_linears[0..D-1], [alpha_linear;feature_linear], views_linears[0], [rgb_linear;dpt_linear]. */
+int vdn_nerf_layer_dims(const int* cfg, int* in_dims, int* out_dims);
+long long vdn_nerf_blob_floats(const int* cfg, long long N);
+long long vdn_nerf_bwd_ws_floats(const int* cfg, long long N);
+int vdn_nerf_forward(const int* cfg, const float* packed, const float* pts, const float* views, long long N,
+                     float* sigma, float* rgb, float* dpt, float* blob, void* stream);
+int vdn_nerf_backward(const int* cfg, const float* packed, const float* pts, const float* views, long long N,
+                      const float* blob, const float* d_sigma, const float* d_rgb, const float* d_dpt, float* dpacked,
+                      float* d_pts, float* d_views, float* ws, void* stream);
+
+/* ---- embedder (embedder.py:11-36) -------------------------------------------------------------------- */
+int vdn_embed_fwd(const float* x, long long N, int d, int multires, float* out /*[N, d*(1+2*multires)]*/,
+                  void* stream);
+int vdn_embed_bwd(const float* x, long long N, int d, int multires, const float* d_out, float* d_x, void* stream);
+
+/* ---- per-ray kernels (renderer.py) ------------------------------------------------------------------- */
+/* pts[b,k,:] = o[b] + d[b] * z[b,k]   (renderer.py:150, 196, 369) */
+int vdn_ray_points(const float* o, const float* d, const float* z, long long B, int n, float* pts, void* stream);
+/* One iteration of the up-sampling loop (renderer.py:372-384): gathers the merged sdf of the previous
+ * iteration (perm_prev/sdf_new null on the first), runs up_sample + sample_pdf(det=True) (renderer.py:44-74,
+ * 147-191) and the cat+sort of cat_z_vals (193-198).  Outputs: z_out[B,n+n_imp] sorted, sdf_out[B,n] (nullable),
+ * perm_out[B,n+n_imp] (source index of each sorted sample; >= n means new sample), new_z[B,n_imp],
+ * new_pts[B*n_imp,3] (nullable), inds_out[B,n_imp] (int64 searchsorted result, nullable). */
+int vdn_upsample_step(const float* o, const float* d, const float* z_in, int n, const float* sdf_prev, int n_prev,
+                      const float* sdf_new, int n_new_prev, const unsigned char* perm_prev, float inv_s, int n_imp,
+                      long long B, float* z_out, float* sdf_out, unsigned char* perm_out, float* new_z, float* new_pts,
+                      long long* inds_out, void* stream);
+/* Section lengths, mid points and fine sample points (renderer.py:228-237). */
+int vdn_fine_prep(const float* o, const float* d, const float* z, float sample_dist, long long B, int S, float* dists,
+                  float* mid_z, float* pts, void* stream);
+/* Merge fine and outside samples (renderer.py:389-391) and build the inverted-sphere inputs (102-120). */
+int vdn_bg_prep(const float* o, const float* d, const float* z_fine, int S, const float* z_outside, int NO,
+                float sample_dist, long long B, float* dists, float* mid_z, float* pts4, void* stream);
+/* Sigmoid-CDF alpha, background blend, transmittance scan, compositing and Eikonal sums (renderer.py:262-315).
+ * NB = 0 (no background) or the merged sample count (>= S); F = feature width (0 = none). */
+int vdn_composite_fwd(long long B, int S, int NB, int F, const float* o, const float* d, const float* mid_z,
+                      const float* dists, const float* sdf, const float* nrm, const float* col, const float* feat,
+                      const float* sigma_bg, const float* rgb_bg, const float* feat_bg, const float* dists_bg,
+                      const float* variance, const float* bg_rgb, float cos_anneal, float* weights, float* cdf,
+                      float* inside, float* color, float* dfeat, float* eik_num, float* eik_den, void* stream);
+int vdn_composite_bwd(long long B, int S, int NB, int F, const float* o, const float* d, const float* mid_z,
+                      const float* dists, const float* sdf, const float* nrm, const float* col, const float* feat,
+                      const float* sigma_bg, const float* rgb_bg, const float* feat_bg, const float* dists_bg,
+                      const float* variance, const float* bg_rgb, float cos_anneal, const float* d_color,
+                      const float* d_weights, const float* d_cdf, const float* d_dfeat, const float* d_eik_num,
+                      float* d_sdf, float* d_nrm, float* d_col, float* d_feat, float* d_sigma_bg, float* d_rgb_bg,
+                      float* d_feat_bg, float* d_dists_bg, float* d_var_partial, float* d_dirs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDN_B200_H */

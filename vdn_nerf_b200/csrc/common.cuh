@@ -1,0 +1,68 @@
+// Shared device helpers for the vdn_nerf_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <atomic>
+
+#define VDN_CHECK(expr)                                   \
+  do {                                                    \
+    cudaError_t _e = (expr);                              \
+    if (_e != cudaSuccess) return (int)_e;                \
+  } while (0)
+
+#define VDN_LAUNCH_CHECK()                                \
+  do {                                                    \
+    cudaError_t _e = cudaGetLastError();                  \
+    if (_e != cudaSuccess) return (int)_e;                \
+  } while (0)
+
+namespace vdn {
+
+extern std::atomic<long long> g_launches;  // defined in api.cu; read through vdn_launch_count()
+
+// Every kernel launch of the library goes through this macro so the launch count is exact.
+#define VDN_LAUNCH(kernel, grid, block, smem, stream, ...)         \
+  do {                                                             \
+    ++::vdn::g_launches;                                           \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+  } while (0)
+
+constexpr float kInvSqrt2 = 0.70710678118654752440f;
+constexpr float kSoftplusBeta = 100.0f;
+constexpr float kSoftplusThreshold = 20.0f;
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// softplus(beta=100, threshold=20) as nn.Softplus computes it (reference fields.py:70).
+__device__ __forceinline__ float softplus100(float z) {
+  float t = z * kSoftplusBeta;
+  return t > kSoftplusThreshold ? z : log1pf(expf(t)) * (1.0f / kSoftplusBeta);
+}
+// d softplus / dz  (= sigmoid(100 z) below the threshold, 1 above it)
+__device__ __forceinline__ float softplus100_d1(float z) {
+  float t = z * kSoftplusBeta;
+  return t > kSoftplusThreshold ? 1.0f : 1.0f / (1.0f + expf(-t));
+}
+// d^2 softplus / dz^2 (= 100 s (1-s) below the threshold, 0 above it)
+__device__ __forceinline__ float softplus100_d2(float z) {
+  float t = z * kSoftplusBeta;
+  if (t > kSoftplusThreshold) return 0.0f;
+  float s = 1.0f / (1.0f + expf(-t));
+  return kSoftplusBeta * s * (1.0f - s);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace vdn

@@ -1,0 +1,421 @@
+// ReLU MLPs of the path, exact-fp32 layer-wise mode:
+//   * RenderingNetwork (colour head d_out=3, depth-feature head d_out=96)   reference fields.py:112-176
+//   * NeRF++ background field                                             reference fields.py:264-355
+// Post-activation tensors H_l are stored (ReLU backward only needs the sign), heads that share an input are
+// packed as one stacked weight so they run as one GEMM with a splitting epilogue.
+#include "gemm_simt.cuh"
+#include "mlp_layout.cuh"
+#include "pointwise.cuh"
+#include "../../include/vdn_b200.h"
+
+namespace vdn {
+
+// ------------------------------------------------------------------------------------------------
+// RenderingNetwork
+// ------------------------------------------------------------------------------------------------
+struct RnCfg {
+  int d_feature, mode, d_out, d_hidden, n_layers, multires_view, squeeze_out;
+  int L, in0, ldIn, ldH;
+  MlpLayout ly;
+};
+
+static int parse_rn_cfg(const int* cfg, RnCfg* c) {
+  c->d_feature = cfg[0]; c->mode = cfg[1]; c->d_out = cfg[2]; c->d_hidden = cfg[3]; c->n_layers = cfg[4];
+  c->multires_view = cfg[5]; c->squeeze_out = cfg[6];
+  c->L = c->n_layers + 1;
+  if (c->L < 2 || c->L > VDN_MAX_LAYERS || c->mode < 0 || c->mode > 2 || c->multires_view < 0) return 1;
+  int nview = (c->mode != 1) ? 3 * (1 + 2 * c->multires_view) : 0;
+  int nnrm = (c->mode != 2) ? 3 : 0;
+  c->in0 = 3 + nview + nnrm + c->d_feature;
+  int in_dims[VDN_MAX_LAYERS], out_dims[VDN_MAX_LAYERS];
+  for (int l = 0; l < c->L; ++l) {
+    in_dims[l] = l == 0 ? c->in0 : c->d_hidden;
+    out_dims[l] = l == c->L - 1 ? c->d_out : c->d_hidden;
+  }
+  c->ldIn = round_up(c->in0, 16);
+  c->ldH = round_up(c->d_hidden, 16);
+  return make_layout(c->L, in_dims, out_dims, &c->ly);
+}
+
+}  // namespace vdn
+using namespace vdn;
+
+extern "C" int vdn_rendernet_layer_dims(const int* cfg, int* in_dims, int* out_dims) {
+  RnCfg c;
+  if (parse_rn_cfg(cfg, &c)) return -1;
+  for (int l = 0; l < c.L; ++l) { in_dims[l] = c.ly.in_dim[l]; out_dims[l] = c.ly.out_dim[l]; }
+  return c.L;
+}
+
+// saved blob: CIN [N, ldIn] | H_0 .. H_{L-2} [N, ldH]
+extern "C" long long vdn_rendernet_blob_floats(const int* cfg, long long N) {
+  RnCfg c;
+  if (parse_rn_cfg(cfg, &c)) return -1;
+  return N * c.ldIn + (long long)(c.L - 1) * N * c.ldH;
+}
+
+extern "C" int vdn_rendernet_forward(const int* cfg, const float* packed, const float* points, const float* normals,
+                                     const float* view_dirs, const float* feats, int ldf, long long N, float* out,
+                                     float* blob, void* stream) {
+  RnCfg c;
+  if (parse_rn_cfg(cfg, &c)) return (int)cudaErrorInvalidValue;
+  if (N <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* CIN = blob;
+  float* H = blob + N * c.ldIn;
+  long long threads = N * 32;
+  VDN_LAUNCH(rendernet_input_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, points, normals, view_dirs, feats, ldf,
+                                                                           c.d_feature, c.multires_view, c.mode, N,
+                                                                           CIN, c.ldIn);
+  int e = (int)cudaGetLastError();
+  if (e) return e;
+  for (int l = 0; l < c.L; ++l) {
+    Operand A = (l == 0) ? make_operand(CIN, c.ldIn, c.ldIn, c.in0)
+                         : make_operand(H + (long long)(l - 1) * N * c.ldH, c.ldH, c.ly.in_ld[l], c.ly.in_dim[l]);
+    Epilogue E;
+    if (l == c.L - 1)
+      E = make_epilogue(c.squeeze_out ? EPI_SIGMOID : EPI_RELU, packed + c.ly.off_b[l], out, c.d_out);
+    else
+      E = make_epilogue(EPI_RELU, packed + c.ly.off_b[l], H + (long long)l * N * c.ldH, c.ldH);
+    e = launch_gemm_nt((int)N, c.ly.out_dim[l], c.ly.in_ld[l], A, packed + c.ly.off_w[l], c.ly.in_ld[l], E, st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+extern "C" long long vdn_rendernet_bwd_ws_floats(const int* cfg, long long N) {
+  RnCfg c;
+  if (parse_rn_cfg(cfg, &c)) return -1;
+  long long S = wgrad_splits((int)N);
+  long long maxw = 0, maxo = 0;
+  for (int l = 0; l < c.L; ++l) {
+    long long w = (long long)c.ly.out_dim[l] * c.ly.in_dim[l];
+    if (w > maxw) maxw = w;
+    if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
+  }
+  return 2 * N * c.ldH + N * c.ly.out_ld[c.L - 1] + S * maxw + S * maxo + 64;
+}
+
+// d_out: [N, d_out] contiguous cotangent of the network output; `out` is the forward output.
+// d_cin (nullable): [N, ldIn] cotangent of the assembled input row (caller slices points/normals/feature/view).
+extern "C" int vdn_rendernet_backward(const int* cfg, const float* packed, long long N, const float* blob,
+                                      const float* out, const float* d_out, float* dpacked, float* d_cin, float* ws,
+                                      void* stream) {
+  RnCfg c;
+  if (parse_rn_cfg(cfg, &c)) return (int)cudaErrorInvalidValue;
+  if (N <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const MlpLayout& ly = c.ly;
+  const int L = c.L, M = (int)N;
+  const float* CIN = blob;
+  const float* H = blob + N * c.ldIn;
+  float* ZB[2] = {ws, ws + N * c.ldH};
+  float* ZL = ws + 2 * N * c.ldH;
+  float* partials = ZL + N * ly.out_ld[L - 1];
+  // zbar_last = d_out * act'(out), padded to out_ld
+  {
+    long long tot = N * ly.out_ld[L - 1];
+    VDN_LAUNCH(act_backward_pad_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, d_out, out, c.d_out, N, ZL,
+                                                                          ly.out_ld[L - 1], c.squeeze_out ? 0 : 1);
+    int e = (int)cudaGetLastError();
+    if (e) return e;
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    Operand zbar = (l == L - 1) ? make_operand(ZL, ly.out_ld[l], ly.out_ld[l], ly.out_dim[l])
+                                : make_operand(ZB[l & 1], c.ldH, ly.out_ld[l], ly.out_dim[l]);
+    Operand u = (l == 0) ? make_operand(CIN, c.ldIn, c.ldIn, c.in0)
+                         : make_operand(H + (long long)(l - 1) * N * c.ldH, c.ldH, ly.in_ld[l], ly.in_dim[l]);
+    int e = launch_wgrad(M, ly.out_dim[l], ly.in_dim[l], zbar, u, nullptr, nullptr, partials, dpacked + ly.off_w[l],
+                         ly.in_ld[l], 1, st);
+    if (e) return e;
+    e = launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);
+    if (e) return e;
+    const float* WT = packed + ly.off_wt[l];
+    if (l > 0) {
+      Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(l - 1) & 1], c.ldH);
+      E.aux = H + (long long)(l - 1) * N * c.ldH; E.ldaux = c.ldH; E.split = 0;
+      e = launch_gemm_nt(M, ly.in_dim[l], ly.out_ld[l], zbar, WT, ly.out_ld[l], E, st);
+      if (e) return e;
+    } else if (d_cin) {
+      Epilogue E = make_epilogue(EPI_STORE, nullptr, d_cin, c.ldIn);
+      e = launch_gemm_nt(M, c.in0, ly.out_ld[0], zbar, WT, ly.out_ld[0], E, st);
+      if (e) return e;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NeRF++ background field.  Packed layer list:
+//   0..D-1 : pts_linears          D   : [alpha_linear ; feature_linear] stacked (1 + W rows)
+//   D+1    : views_linears.0      D+2 : [rgb_linear ; dpt_linear] stacked (3 [+ dpt_dim] rows)
+// ------------------------------------------------------------------------------------------------
+namespace vdn {
+struct NerfCfg {
+  int D, W, d_in, d_in_view, multires, multires_view, skip, rgb_dims, dpt_dim;
+  int L, d_e, d_ev, ldE, ldH, ldU, ldV, ldHV, vin;
+  MlpLayout ly;
+};
+
+static int parse_nerf_cfg(const int* cfg, NerfCfg* c) {
+  c->D = cfg[0]; c->W = cfg[1]; c->d_in = cfg[2]; c->d_in_view = cfg[3]; c->multires = cfg[4];
+  c->multires_view = cfg[5]; c->skip = cfg[6]; c->rgb_dims = cfg[7]; c->dpt_dim = cfg[8];
+  c->L = c->D + 3;
+  if (c->D < 2 || c->L > VDN_MAX_LAYERS || c->d_in < 1 || c->d_in > 4 || c->d_in_view != 3) return 1;
+  if (c->skip >= 0 && (c->skip < 0 || c->skip > c->D - 2)) return 1;
+  c->d_e = c->d_in * (1 + 2 * c->multires);
+  c->d_ev = c->d_in_view * (1 + 2 * c->multires_view);
+  int in_dims[VDN_MAX_LAYERS], out_dims[VDN_MAX_LAYERS];
+  for (int i = 0; i < c->D; ++i) {
+    in_dims[i] = (i == 0) ? c->d_e : (i - 1 == c->skip ? c->W + c->d_e : c->W);
+    out_dims[i] = c->W;
+  }
+  in_dims[c->D] = c->W; out_dims[c->D] = 1 + c->W;
+  c->vin = c->W + c->d_ev;
+  in_dims[c->D + 1] = c->vin; out_dims[c->D + 1] = c->W / 2;
+  in_dims[c->D + 2] = c->W / 2; out_dims[c->D + 2] = c->rgb_dims + c->dpt_dim;
+  c->ldE = round_up(c->d_e, 16);
+  c->ldH = round_up(c->W, 16);
+  c->ldU = round_up(c->W + c->d_e, 16);
+  c->ldV = round_up(c->vin, 16);
+  c->ldHV = round_up(c->W / 2, 16);
+  return make_layout(c->L, in_dims, out_dims, &c->ly);
+}
+
+// saved blob: E [N,ldE] | VIN [N,ldV] | U [N,ldU] (skip only) | H_0..H_{D-1} [N,ldH] | HV [N,ldHV]
+struct NerfBlob {
+  float* E; float* VIN; float* U; float* H[VDN_MAX_LAYERS]; float* HV;
+};
+static long long nerf_blob_floats(const NerfCfg& c, long long N) {
+  return N * c.ldE + N * c.ldV + (c.skip >= 0 ? N * c.ldU : 0) + (long long)c.D * N * c.ldH + N * c.ldHV;
+}
+static void carve_nerf(const NerfCfg& c, long long N, float* p, NerfBlob* b) {
+  b->E = p; p += N * c.ldE;
+  b->VIN = p; p += N * c.ldV;
+  b->U = nullptr;
+  if (c.skip >= 0) { b->U = p; p += N * c.ldU; }
+  for (int i = 0; i < c.D; ++i) { b->H[i] = p; p += N * c.ldH; }
+  b->HV = p;
+}
+// The input operand of pts layer i and where its post-ReLU output lives (buffer, ld, column offset).
+static Operand nerf_input(const NerfCfg& c, const NerfBlob& b, int i) {
+  if (i == 0) return make_operand(b.E, c.ldE, c.ldE, c.d_e);
+  if (i - 1 == c.skip) return make_operand(b.U, c.ldU, c.ldU, c.W + c.d_e);
+  return make_operand(b.H[i - 1], c.ldH, c.ly.in_ld[i], c.W);
+}
+}  // namespace vdn
+
+extern "C" int vdn_nerf_layer_dims(const int* cfg, int* in_dims, int* out_dims) {
+  NerfCfg c;
+  if (parse_nerf_cfg(cfg, &c)) return -1;
+  for (int l = 0; l < c.L; ++l) { in_dims[l] = c.ly.in_dim[l]; out_dims[l] = c.ly.out_dim[l]; }
+  return c.L;
+}
+
+extern "C" long long vdn_nerf_blob_floats(const int* cfg, long long N) {
+  NerfCfg c;
+  if (parse_nerf_cfg(cfg, &c)) return -1;
+  return nerf_blob_floats(c, N);
+}
+
+extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float* pts, const float* views,
+                                long long N, float* sigma, float* rgb, float* dpt, float* blob, void* stream) {
+  NerfCfg c;
+  if (parse_nerf_cfg(cfg, &c)) return (int)cudaErrorInvalidValue;
+  if (N <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const MlpLayout& ly = c.ly;
+  NerfBlob b;
+  carve_nerf(c, N, blob, &b);
+  const int M = (int)N, D = c.D;
+  unsigned blocks = (unsigned)((N + 127) / 128);
+  // pts embedding -> E and the head of the skip buffer U (reference fields.py:334-335: cat[input_pts, h])
+  VDN_LAUNCH(embed_rows_kernel, blocks, 128, 0, st, pts, c.d_in, N, c.d_in, c.multires, 1.0f, b.E, c.ldE, b.U, c.ldU, 0, 1.0f,
+                                            c.d_e);
+  // view embedding -> tail of VIN (reference fields.py:340: cat[feature, input_views])
+  VDN_LAUNCH(embed_rows_kernel, blocks, 128, 0, st, views, c.d_in_view, N, c.d_in_view, c.multires_view, 1.0f, nullptr, 0,
+                                            b.VIN, c.ldV, c.W, 1.0f, c.ldV);
+  int e = (int)cudaGetLastError();
+  if (e) return e;
+  for (int i = 0; i < D; ++i) {
+    Operand A = nerf_input(c, b, i);
+    Epilogue E = make_epilogue(EPI_RELU, packed + ly.off_b[i], b.H[i], c.ldH);
+    if (i == c.skip) { E.c = b.U; E.ldc = c.ldU; E.coff = c.d_e; }
+    e = launch_gemm_nt(M, c.W, ly.in_ld[i], A, packed + ly.off_w[i], ly.in_ld[i], E, st);
+    if (e) return e;
+    if (i == c.skip) {  // zero the padding columns of U once per call
+      long long tot = N * (c.ldU - (c.W + c.d_e));
+      if (tot > 0)
+        VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, nullptr, 0, 0, N, b.U, c.ldU,
+                                                                           c.W + c.d_e, c.ldU, 0.0f);
+    }
+  }
+  // heads on h_{D-1}: sigma (row 0) and the feature (rows 1..W) into VIN[:, :W]
+  {
+    Operand A = nerf_input(c, b, D);
+    Epilogue E = make_epilogue(EPI_SPLIT, packed + ly.off_b[D], b.VIN, c.ldV);
+    E.c2 = sigma; E.ldc2 = 1; E.split = 1; E.scale = 1.0f;
+    e = launch_gemm_nt(M, 1 + c.W, ly.in_ld[D], A, packed + ly.off_w[D], ly.in_ld[D], E, st);
+    if (e) return e;
+  }
+  {
+    Operand A = make_operand(b.VIN, c.ldV, c.ldV, c.vin);
+    Epilogue E = make_epilogue(EPI_RELU, packed + ly.off_b[D + 1], b.HV, c.ldHV);
+    e = launch_gemm_nt(M, c.W / 2, ly.in_ld[D + 1], A, packed + ly.off_w[D + 1], ly.in_ld[D + 1], E, st);
+    if (e) return e;
+  }
+  {
+    Operand A = make_operand(b.HV, c.ldHV, c.ldHV, c.W / 2);
+    Epilogue E = make_epilogue(EPI_SPLIT, packed + ly.off_b[D + 2], dpt, c.dpt_dim);
+    E.c2 = rgb; E.ldc2 = c.rgb_dims; E.split = c.rgb_dims; E.scale = 1.0f;
+    e = launch_gemm_nt(M, c.rgb_dims + c.dpt_dim, ly.in_ld[D + 2], A, packed + ly.off_w[D + 2], ly.in_ld[D + 2], E,
+                       st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+extern "C" long long vdn_nerf_bwd_ws_floats(const int* cfg, long long N) {
+  NerfCfg c;
+  if (parse_nerf_cfg(cfg, &c)) return -1;
+  long long S = wgrad_splits((int)N);
+  long long maxw = 0, maxo = 0;
+  for (int l = 0; l < c.L; ++l) {
+    long long w = (long long)c.ly.out_dim[l] * c.ly.in_dim[l];
+    if (w > maxw) maxw = w;
+    if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
+  }
+  return 2 * N * c.ldH + N * c.ly.out_ld[c.D] + N * c.ldHV + N * c.ly.out_ld[c.D + 2] + N * c.ldV +
+         2 * N * c.ldE + S * maxw + S * maxo + 64;
+}
+
+// d_pts (nullable): [N, d_in]; d_views (nullable): [N, 3].
+extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const float* pts, const float* views,
+                                 long long N, const float* blob, const float* d_sigma, const float* d_rgb,
+                                 const float* d_dpt, float* dpacked, float* d_pts, float* d_views, float* ws,
+                                 void* stream) {
+  NerfCfg c;
+  if (parse_nerf_cfg(cfg, &c)) return (int)cudaErrorInvalidValue;
+  if (N <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const MlpLayout& ly = c.ly;
+  NerfBlob b;
+  carve_nerf(c, N, const_cast<float*>(blob), &b);
+  const int M = (int)N, D = c.D;
+  float* p = ws;
+  float* ZB[2] = {p, p + N * c.ldH}; p += 2 * N * c.ldH;
+  float* ZHEAD = p; p += N * ly.out_ld[D];        // [d_sigma | d_feature]
+  float* ZV = p; p += N * c.ldHV;                  // zbar of the view layer
+  float* ZO = p; p += N * ly.out_ld[D + 2];        // [d_rgb | d_dpt]
+  float* DVIN = p; p += N * c.ldV;                 // cotangent of the view-embedding tail (only for d_views)
+  float* EE0 = p; p += N * c.ldE;
+  float* EE1 = p; p += N * c.ldE;
+  float* partials = p;
+  int e;
+  auto wg = [&](int l, const Operand& zbar, const Operand& u) -> int {
+    int r = launch_wgrad(M, ly.out_dim[l], ly.in_dim[l], zbar, u, nullptr, nullptr, partials, dpacked + ly.off_w[l],
+                         ly.in_ld[l], 1, st);
+    if (r) return r;
+    return launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);
+  };
+  // output heads
+  {
+    int ldo = ly.out_ld[D + 2];
+    long long tot = N * ldo;
+    VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, nullptr, 0, 0, N, ZO, ldo, 0, ldo, 0.0f);
+    if (d_rgb) {
+      long long t = N * c.rgb_dims;
+      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((t + 255) / 256), 256, 0, st, d_rgb, c.rgb_dims, c.rgb_dims, N, ZO, ldo, 0,
+                                                                       c.rgb_dims, 1.0f);
+    }
+    if (d_dpt && c.dpt_dim > 0) {
+      long long t = N * c.dpt_dim;
+      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((t + 255) / 256), 256, 0, st, d_dpt, c.dpt_dim, c.dpt_dim, N, ZO, ldo,
+                                                                       c.rgb_dims, c.rgb_dims + c.dpt_dim, 1.0f);
+    }
+    e = (int)cudaGetLastError();
+    if (e) return e;
+    Operand zo = make_operand(ZO, ldo, ldo, ly.out_dim[D + 2]);
+    Operand hv = make_operand(b.HV, c.ldHV, c.ldHV, c.W / 2);
+    e = wg(D + 2, zo, hv);
+    if (e) return e;
+    Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZV, c.ldHV);
+    E.aux = b.HV; E.ldaux = c.ldHV;
+    e = launch_gemm_nt(M, c.W / 2, ldo, zo, packed + ly.off_wt[D + 2], ldo, E, st);
+    if (e) return e;
+  }
+  // view layer
+  {
+    Operand zv = make_operand(ZV, c.ldHV, c.ldHV, c.W / 2);
+    Operand vin = make_operand(b.VIN, c.ldV, c.ldV, c.vin);
+    e = wg(D + 1, zv, vin);
+    if (e) return e;
+    // cotangent of the feature -> columns 1..W of ZHEAD; column 0 = d_sigma
+    int ldh = ly.out_ld[D];
+    long long tot = N * ldh;
+    VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, nullptr, 0, 0, N, ZHEAD, ldh, 0, ldh, 0.0f);
+    if (d_sigma)
+      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((N + 255) / 256), 256, 0, st, d_sigma, 1, 1, N, ZHEAD, ldh, 0, 1, 1.0f);
+    e = (int)cudaGetLastError();
+    if (e) return e;
+    Epilogue E = make_epilogue(EPI_STORE, nullptr, ZHEAD, ldh);
+    E.coff = 1;
+    e = launch_gemm_nt(M, c.W, c.ldHV, zv, packed + ly.off_wt[D + 1], ly.out_ld[D + 1], E, st);
+    if (e) return e;
+    if (d_views) {
+      Epilogue E2 = make_epilogue(EPI_STORE, nullptr, DVIN, c.ldV);
+      e = launch_gemm_nt(M, c.d_ev, c.ldHV, zv, packed + ly.off_wt[D + 1] + (long long)c.W * ly.out_ld[D + 1],
+                         ly.out_ld[D + 1], E2, st);
+      if (e) return e;
+    }
+  }
+  // stacked alpha / feature head -> zbar_{D-1}
+  {
+    int ldh = ly.out_ld[D];
+    Operand zh = make_operand(ZHEAD, ldh, ldh, ly.out_dim[D]);
+    e = wg(D, zh, nerf_input(c, b, D));
+    if (e) return e;
+    Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(D - 1) & 1], c.ldH);
+    E.aux = b.H[D - 1]; E.ldaux = c.ldH;
+    e = launch_gemm_nt(M, c.W, ldh, zh, packed + ly.off_wt[D], ldh, E, st);
+    if (e) return e;
+  }
+  for (int i = D - 1; i >= 0; --i) {
+    Operand zbar = make_operand(ZB[i & 1], c.ldH, c.ldH, c.W);
+    e = wg(i, zbar, nerf_input(c, b, i));
+    if (e) return e;
+    const float* WT = packed + ly.off_wt[i];
+    const int ldwt = ly.out_ld[i];
+    if (i > 0) {
+      // hidden part of the input cotangent, masked by the sign of h_{i-1}
+      const bool after_skip = (i - 1 == c.skip);
+      Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(i - 1) & 1], c.ldH);
+      if (after_skip) { E.aux = b.U; E.ldaux = c.ldU; E.split = c.d_e; }
+      else { E.aux = b.H[i - 1]; E.ldaux = c.ldH; E.split = 0; }
+      e = launch_gemm_nt(M, c.W, c.ldH, zbar, WT + (after_skip ? (long long)c.d_e * ldwt : 0), ldwt, E, st);
+      if (e) return e;
+      if (after_skip && d_pts) {
+        Epilogue E2 = make_epilogue(EPI_STORE, nullptr, EE1, c.ldE);
+        e = launch_gemm_nt(M, c.d_e, c.ldH, zbar, WT, ldwt, E2, st);
+        if (e) return e;
+      }
+    } else if (d_pts) {
+      Epilogue E2 = make_epilogue(EPI_STORE, nullptr, EE0, c.ldE);
+      e = launch_gemm_nt(M, c.d_e, c.ldH, zbar, WT, ldwt, E2, st);
+      if (e) return e;
+    }
+  }
+  if (d_pts) {
+    long long tot = N * c.d_in;
+    VDN_LAUNCH(embed_vjp_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, pts, c.d_in, N, c.d_in, c.multires, 1.0f, EE0,
+                                                                   c.ldE, c.skip >= 0 ? EE1 : nullptr, c.ldE, 1.0f,
+                                                                   1.0f, d_pts, c.d_in, 0);
+  }
+  if (d_views) {
+    long long tot = N * c.d_in_view;
+    VDN_LAUNCH(embed_vjp_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, views, c.d_in_view, N, c.d_in_view,
+                                                                   c.multires_view, 1.0f, DVIN, c.ldV, nullptr, 0,
+                                                                   0.0f, 1.0f, d_views, c.d_in_view, 0);
+  }
+  return (int)cudaGetLastError();
+}
