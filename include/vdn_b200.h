@@ -30,6 +30,8 @@ int vdn_abi_version(void);
 /* Number of this library's kernel launches enqueued by the calling process so far (for bench.py's
  * gpu_launches claim). */
 long long vdn_launch_count(void);
+/* cudaGetErrorString for the codes this library returns. */
+const char* vdn_error_string(int code);
 
 /* ---- packed parameters (weight_norm: fields.py:65-66, 141-142; nn.Linear: fields.py:303-318) ------------ */
 long long vdn_mlp_layout(int L, const int* in_dims /*host*/, const int* out_dims /*host*/, long long* off_w /*host*/,
@@ -48,11 +50,12 @@ int vdn_sdf_layer_dims(const int* cfg, int* in_dims, int* out_dims); /* returns 
 long long vdn_sdf_blob_floats(const int* cfg, long long N, int save);
 long long vdn_sdf_blobg_floats(const int* cfg, long long N);
 long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N);
-/* SDFNetwork.forward / .sdf (fields.py:72-92): sdf[N] and, when feat != null, feat[N, d_out-1] (ld ldf).
+/* SDFNetwork.forward / .sdf (fields.py:72-92): sdf[N] (stride lds) and, when feat != null, feat[N, d_out-1]
+ * (ld ldf).
  * blob: scratch of vdn_sdf_blob_floats(cfg, N, save) floats; save=1 keeps every pre-activation for
  * vdn_sdf_normals / vdn_sdf_backward. */
 int vdn_sdf_forward(const int* cfg, float scale, const float* packed, const float* x, long long N, float* sdf,
-                    float* feat, int ldf, float* blob, int save, void* stream);
+                    int lds, float* feat, int ldf, float* blob, int save, void* stream);
 /* SDFNetwork.gradient (fields.py:97-108) without autograd: normals[N, d_in] = d sdf / d x.
  * blob: the save=1 blob of the forward on the same x; blobg: vdn_sdf_blobg_floats floats (kept for backward). */
 int vdn_sdf_normals(const int* cfg, float scale, const float* packed, const float* x, long long N, const float* blob,
@@ -61,8 +64,8 @@ int vdn_sdf_normals(const int* cfg, float scale, const float* packed, const floa
  * d_x != null, the points (overwritten).  Replaces autograd's double backward through fields.py:97-108.
  * Cotangents may be null.  ws: vdn_sdf_bwd_ws_floats floats. */
 int vdn_sdf_backward(const int* cfg, float scale, const float* packed, const float* x, long long N, const float* blob,
-                     const float* blobg, const float* d_sdf, const float* d_feat, int ldf, const float* d_normals,
-                     float* dpacked, float* d_x, float* ws, void* stream);
+                     const float* blobg, const float* d_sdf, int lds, const float* d_feat, int ldf,
+                     const float* d_normals, float* dpacked, float* d_x, float* ws, void* stream);
 /* extract_fields (renderer.py:10-30) for the x-slab [i0, i1): u_slab[(i-i0), j, k] = out_mul * sdf(xs[i], ys[j],
  * zs[k]).  pts: (i1-i0)*ny*nz*3 floats scratch; blob: save=0 blob for that many points. */
 int vdn_grid_sdf(const int* cfg, float scale, const float* packed, const float* xs, const float* ys, const float* zs,
@@ -110,6 +113,10 @@ int vdn_upsample_step(const float* o, const float* d, const float* z_in, int n, 
                       const float* sdf_new, int n_new_prev, const unsigned char* perm_prev, float inv_s, int n_imp,
                       long long B, float* z_out, float* sdf_out, unsigned char* perm_out, float* new_z, float* new_pts,
                       long long* inds_out, void* stream);
+/* cat + sort of cat_z_vals (renderer.py:197-198) as a stable merge: za[B,n] sorted, zb[B,m] arbitrary;
+ * perm[B,n+m] = source index of each output sample (< n from za, >= n from zb). */
+int vdn_merge_sorted(const float* za, int n, const float* zb, int m, long long B, float* z_out, unsigned char* perm,
+                     void* stream);
 /* Section lengths, mid points and fine sample points (renderer.py:228-237). */
 int vdn_fine_prep(const float* o, const float* d, const float* z, float sample_dist, long long B, int S, float* dists,
                   float* mid_z, float* pts, void* stream);

@@ -50,7 +50,9 @@ def effective_weight(p: Params, name: str) -> torch.Tensor:
     if name + ".weight_v" in p:
         v = p[name + ".weight_v"]
         g = p[name + ".weight_g"]
-        return v * (g / v.norm(dim=1, keepdim=True))
+        # the ATen op nn.utils.weight_norm's hook calls (its fused CPU kernel rounds the row norm differently
+        # from v.norm(dim=1), so the composite formula would not be bit-identical to the reference)
+        return torch._weight_norm(v, g, 0)
     return p[name + ".weight"]
 
 
@@ -191,6 +193,38 @@ class Nets:
             if d is not None:
                 out += [(f"{name}.{k}", v) for k, v in d.items()]
         return out
+
+
+def nets_from_modules(nerf, sdf, variance_net, color, depth, conf, detach=True, dtype=None) -> "Nets":
+    """Build the oracle's parameter dictionaries from constructed modules (this package's or the reference's:
+    both expose the same named_parameters) and a conf dict of vdn_nerf_b200.configs."""
+    def grab(m):
+        if m is None:
+            return None
+        d = {}
+        for k, v in m.named_parameters():
+            t = v.detach().cpu().clone() if detach else v
+            if dtype is not None:
+                t = t.to(dtype)
+            d[k] = t
+        return d
+    sc, rc, nc, rr = conf["sdf_network"], conf["rendering_network"], conf["nerf"], conf["neus_renderer"]
+    dc = conf.get("depth_extract_network") or rc
+    var = variance_net.variance.detach().cpu().clone() if detach else variance_net.variance
+    if dtype is not None:
+        var = var.to(dtype)
+    return Nets(
+        sdf=grab(sdf), color=grab(color), variance=var, nerf=grab(nerf), depth=grab(depth),
+        sdf_spec=SDFSpec(n_lin=sc["n_layers"] + 1, skip_in=tuple(sc["skip_in"]), multires=sc["multires"],
+                         scale=sc["scale"]),
+        color_spec=RenderNetSpec(n_lin=rc["n_layers"] + 1, mode=rc["mode"], multires_view=rc["multires_view"],
+                                 squeeze_out=rc["squeeze_out"]),
+        depth_spec=RenderNetSpec(n_lin=dc["n_layers"] + 1, mode=dc["mode"], multires_view=dc["multires_view"],
+                                 squeeze_out=dc["squeeze_out"]),
+        nerf_spec=NeRFSpec(D=nc["D"], skips=tuple(nc["skips"]), multires=nc["multires"],
+                           multires_view=nc["multires_view"], gen_depth_feats=nc.get("gen_depth_feats", False)),
+        n_samples=rr["n_samples"], n_importance=rr["n_importance"], n_outside=rr["n_outside"],
+        up_sample_steps=rr["up_sample_steps"], perturb=rr["perturb"])
 
 
 def excl_cumprod_weights(alpha: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,107 @@
+"""Host-side contract tests that need no GPU: the drop-in boundary (constructor kwargs, state_dict keys,
+parameter counts), the C-ABI surface (header == binding == exported symbols), packed-weight layout, sharding
+helpers, and the "fail loudly" rule."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from tests import util
+from vdn_nerf_b200 import _lib, configs, dist as vdist, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "vdn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vdn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_abi_header_binding_and_library_agree():
+    hdr = header_symbols()
+    assert hdr == sorted(_lib.SIGNATURES.keys())
+    lib = _lib.load()                      # loads without a GPU; raises if a symbol is missing
+    assert lib.vdn_abi_version() == _lib.ABI_VERSION
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (vdn_[a-z0-9_]+)", out)))
+    assert exported == hdr
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_state_dict_keys_and_param_counts():
+    (nerf, sdf, var, col, dep), conf = util.build("womsk_white_wdepth")
+    count = lambda m: sum(p.numel() for p in m.parameters())
+    assert count(sdf) == 529076 and count(col) == 273414 and count(dep) == 297408 and count(nerf) == 618980
+    assert count(var) == 1
+    keys = list(sdf.state_dict().keys())
+    assert keys[:3] == ["lin0.bias", "lin0.weight_g", "lin0.weight_v"] and len(keys) == 27
+    assert tuple(sdf.lin3.weight_v.shape) == (217, 256) and tuple(sdf.lin8.weight_v.shape) == (257, 256)
+    assert tuple(col.lin0.weight_v.shape) == (256, 289)
+    nk = list(nerf.state_dict().keys())
+    for k in ("pts_linears.5.weight", "views_linears.0.weight", "feature_linear.bias", "alpha_linear.weight",
+              "rgb_linear.weight", "dpt_linear.weight"):
+        assert k in nk
+    assert tuple(nerf.pts_linears[5].weight.shape) == (256, 340)
+    assert list(var.state_dict().keys()) == ["variance"]
+    (nerf2, *_), _ = util.build("womsk_white")
+    assert count(nerf2) == 606596
+    # state_dict round trip (checkpoint compatibility, dpt_runner.py:350-381)
+    sd = {k: v.clone() for k, v in sdf.state_dict().items()}
+    (_, sdf_b, *_), _ = util.build("womsk_white_wdepth", seed=1)
+    sdf_b.load_state_dict(sd)
+    assert all(torch.equal(a, b) for a, b in zip(sdf.state_dict().values(), sdf_b.state_dict().values()))
+
+
+def test_layer_dims_and_layout_from_the_library():
+    (nerf, sdf, var, col, dep), conf = util.build("womsk_white_wdepth")
+    h = sdf.handle()
+    assert h.mlp.in_dims == [39] + [256] * 8
+    assert h.mlp.out_dims == [256, 256, 256, 217, 256, 256, 256, 256, 257]
+    assert col.handle().mlp.in_dims == [289, 256, 256, 256, 256] and dep.handle().mlp.out_dims[-1] == 96
+    nh = nerf.handle()
+    assert nh.mlp.in_dims == [84, 256, 256, 256, 256, 340, 256, 256, 256, 283, 128]
+    assert nh.mlp.out_dims == [256] * 8 + [257, 128, 99]
+    # offsets are contiguous, 16-float aligned, W | W^T | b per layer
+    m = h.mlp
+    off = 0
+    for l in range(m.L):
+        ild, old = (m.in_dims[l] + 15) // 16 * 16, (m.out_dims[l] + 15) // 16 * 16
+        assert (m.off_w[l], m.off_wt[l], m.off_b[l]) == (off, off + old * ild, off + 2 * old * ild)
+        off += 2 * old * ild + old
+    assert m.total == off
+    assert len(m.params) == 27 and len(nh.mlp.params) == 26
+
+
+def test_no_cpu_fallback():
+    (nerf, sdf, var, col, dep), conf = util.build("womsk_white")
+    with pytest.raises(_lib.VdnLibraryError):
+        sdf(torch.zeros(4, 3))
+    with pytest.raises(_lib.VdnLibraryError):
+        ops.ray_points(torch.zeros(2, 3), torch.zeros(2, 3), torch.zeros(2, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vdn_nerf_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# ", ""), fn
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 512, 513):
+        for ws in (1, 2, 3, 8):
+            spans = [vdist.shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1

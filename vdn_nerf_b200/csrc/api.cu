@@ -9,6 +9,7 @@ using namespace vdn;
 
 extern "C" int vdn_abi_version(void) { return 1; }
 extern "C" long long vdn_launch_count(void) { return g_launches.load(); }
+extern "C" const char* vdn_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
 extern "C" int vdn_embed_fwd(const float* x, long long N, int d, int multires, float* out, void* stream) {
   if (N <= 0) return 0;

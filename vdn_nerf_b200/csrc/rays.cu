@@ -157,6 +157,42 @@ upsample_kernel(const float* __restrict__ o, const float* __restrict__ d, const 
   }
 }
 
+// Stable merge of sorted za[B,n] with zb[B,m] (cat + sort of renderer.py:197-198): z_out[B,n+m] and the source
+// index of every output sample (< n: from za, >= n: from zb).
+__global__ void __launch_bounds__(RAY_WARPS * 32)
+merge_sorted_kernel(const float* __restrict__ za, int n, const float* __restrict__ zb, int m, long long B,
+                    float* __restrict__ z_out, unsigned char* __restrict__ perm) {
+  __shared__ float sa[RAY_WARPS][RAY_MAXN], sb[RAY_WARPS][RAY_MAXN];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * RAY_WARPS + wid;
+  if (b >= B) return;
+  float* a = sa[wid];
+  float* c = sb[wid];
+  for (int k = lane; k < n; k += 32) a[k] = za[b * n + k];
+  for (int j = lane; j < m; j += 32) c[j] = zb[b * m + j];
+  __syncwarp();
+  const int nt = n + m;
+  for (int k = lane; k < n; k += 32) {
+    const float v = a[k];
+    int cnt = 0;
+    for (int j = 0; j < m; ++j) cnt += (c[j] < v) ? 1 : 0;
+    z_out[b * nt + k + cnt] = v;
+    perm[b * nt + k + cnt] = (unsigned char)k;
+  }
+  for (int j = lane; j < m; j += 32) {
+    const float v = c[j];
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (a[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    int cnt = lo;
+    for (int j2 = 0; j2 < m; ++j2) cnt += (c[j2] < v || (c[j2] == v && j2 < j)) ? 1 : 0;
+    z_out[b * nt + cnt] = v;
+    perm[b * nt + cnt] = (unsigned char)(n + j);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Sample placement for render_core / render_core_outside
 // ------------------------------------------------------------------------------------------------
@@ -272,6 +308,13 @@ __device__ __forceinline__ FineEval eval_fine(const CompArgs& a, long long b, in
 
 __device__ __forceinline__ float softplus1(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 
+// Background alpha: 1 - exp(-softplus(sigma) * dist) (renderer.py:124), or sigma_bg taken as an already
+// computed alpha when no section lengths are given (the stand-alone render_core API of renderer.py:209).
+__device__ __forceinline__ float bg_alpha(const CompArgs& a, long long j) {
+  if (!a.dists_bg) return a.sigma_bg[j];
+  return 1.0f - expf(-softplus1(a.sigma_bg[j]) * a.dists_bg[j]);
+}
+
 // blocked exclusive product scan over NW values held in shared memory: T[k] = prod_{j<k} (1 - alpha[j] + 1e-7)
 __device__ __forceinline__ void transmittance_scan(const float* alpha, float* T, int NW, int lane) {
   const int per = (NW + 31) / 32;
@@ -327,11 +370,11 @@ composite_fwd_kernel(CompArgs a, float* __restrict__ weights, float* __restrict_
       en += f.relax * ge;
       ed += f.relax;
       if (NB > 0) {
-        const float abg = 1.0f - expf(-softplus1(a.sigma_bg[b * NB + k]) * a.dists_bg[b * NB + k]);
+        const float abg = bg_alpha(a, b * NB + k);
         al = al * in + abg * (1.0f - in);
       }
     } else {
-      al = 1.0f - expf(-softplus1(a.sigma_bg[b * NB + k]) * a.dists_bg[b * NB + k]);
+      al = bg_alpha(a, b * NB + k);
     }
     alpha[k] = al;
     ins[k] = in;
@@ -425,11 +468,11 @@ composite_bwd_kernel(CompArgs a, CompGrads g) {
       al = f.alpha;
       in = f.inside;
       if (NB > 0) {
-        const float abg = 1.0f - expf(-softplus1(a.sigma_bg[b * NB + k]) * a.dists_bg[b * NB + k]);
+        const float abg = bg_alpha(a, b * NB + k);
         al = al * in + abg * (1.0f - in);
       }
     } else {
-      al = 1.0f - expf(-softplus1(a.sigma_bg[b * NB + k]) * a.dists_bg[b * NB + k]);
+      al = bg_alpha(a, b * NB + k);
     }
     alpha[k] = al;
     ins[k] = in;
@@ -567,12 +610,16 @@ composite_bwd_kernel(CompArgs a, CompGrads g) {
     }
     if (NB > 0) {
       const long long j = b * NB + k;
-      const float sg = a.sigma_bg[j], dist = a.dists_bg[j];
-      const float sp = softplus1(sg);
-      const float ex = expf(-sp * dist);
-      const float dsp = sg > 20.0f ? 1.0f : sigmoidf_(sg);
-      g.d_sigma_bg[j] = abar_bg * ex * dist * dsp;
-      if (g.d_dists_bg) g.d_dists_bg[j] = abar_bg * ex * sp;
+      if (!a.dists_bg) {
+        g.d_sigma_bg[j] = abar_bg;
+      } else {
+        const float sg = a.sigma_bg[j], dist = a.dists_bg[j];
+        const float sp = softplus1(sg);
+        const float ex = expf(-sp * dist);
+        const float dsp = sg > 20.0f ? 1.0f : sigmoidf_(sg);
+        g.d_sigma_bg[j] = abar_bg * ex * dist * dsp;
+        if (g.d_dists_bg) g.d_dists_bg[j] = abar_bg * ex * sp;
+      }
     }
   }
   dvar = warp_sum(dvar);
@@ -610,6 +657,15 @@ extern "C" int vdn_upsample_step(const float* o, const float* d, const float* z_
   VDN_LAUNCH(upsample_kernel, blocks, RAY_WARPS * 32, 0, (cudaStream_t)stream, o, d, z_in, n, sdf_prev, n_prev, sdf_new,
                                                                       n_new_prev, perm_prev, inv_s, n_imp, B, z_out,
                                                                       sdf_out, perm_out, new_z, new_pts, inds_out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int vdn_merge_sorted(const float* za, int n, const float* zb, int m, long long B, float* z_out,
+                                unsigned char* perm, void* stream) {
+  if (B <= 0) return 0;
+  if (n < 0 || m < 0 || n + m > RAY_MAXN || n + m < 1) return (int)cudaErrorInvalidValue;
+  unsigned blocks = (unsigned)((B + RAY_WARPS - 1) / RAY_WARPS);
+  VDN_LAUNCH(merge_sorted_kernel, blocks, RAY_WARPS * 32, 0, (cudaStream_t)stream, za, n, zb, m, B, z_out, perm);
   return (int)cudaGetLastError();
 }
 

@@ -140,7 +140,7 @@ extern "C" long long vdn_sdf_blobg_floats(const int* cfg, long long N) {
   return sdf_blobg_floats(c, N);
 }
 
-static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x, long long N, float* sdf,
+static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x, long long N, float* sdf, int lds,
                             float* feat, int ldf, float* blob, int save, float out_mul, cudaStream_t st) {
   if (N <= 0) return 0;
   if (N > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
@@ -156,7 +156,7 @@ static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x
     int ngemm = c.ly.out_dim[l];
     if (l == c.L - 1) {
       E = make_epilogue(EPI_SPLIT, bias, feat, ldf);
-      E.c2 = sdf; E.ldc2 = 1; E.split = 1; E.scale = out_mul / c.scale;
+      E.c2 = sdf; E.ldc2 = lds; E.split = 1; E.scale = out_mul / c.scale;
       if (!feat) ngemm = 1;
     } else if (l + 1 == c.skip) {
       E = make_epilogue(EPI_SDF_SKIP, bias, b.Z[l], c.ldH);
@@ -171,10 +171,10 @@ static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x
 }
 
 extern "C" int vdn_sdf_forward(const int* cfg, float scale, const float* packed, const float* x, long long N,
-                               float* sdf, float* feat, int ldf, float* blob, int save, void* stream) {
+                               float* sdf, int lds, float* feat, int ldf, float* blob, int save, void* stream) {
   SdfCfg c;
   if (parse_sdf_cfg(cfg, scale, &c)) return (int)cudaErrorInvalidValue;
-  return sdf_forward_impl(c, packed, x, N, sdf, feat, ldf, blob, save, 1.0f, (cudaStream_t)stream);
+  return sdf_forward_impl(c, packed, x, N, sdf, lds, feat, ldf, blob, save, 1.0f, (cudaStream_t)stream);
 }
 
 namespace vdn {
@@ -208,7 +208,7 @@ extern "C" int vdn_grid_sdf(const int* cfg, float scale, const float* packed, co
   VDN_LAUNCH(grid_points_kernel, (unsigned)((count + 255) / 256), 256, 0, st, xs, ys, zs, i0, ny, nz, count, pts);
   int e = (int)cudaGetLastError();
   if (e) return e;
-  return sdf_forward_impl(c, packed, pts, count, u_slab, nullptr, 0, blob, 0, out_mul, st);
+  return sdf_forward_impl(c, packed, pts, count, u_slab, 1, nullptr, 0, blob, 0, out_mul, st);
 }
 
 extern "C" int vdn_sdf_normals(const int* cfg, float scale, const float* packed, const float* x, long long N,
@@ -259,8 +259,9 @@ extern "C" long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N) {
 }
 
 extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed, const float* x, long long N,
-                                const float* blob, const float* blobg, const float* d_sdf, const float* d_feat,
-                                int ldf, const float* d_normals, float* dpacked, float* d_x, float* ws,
+                                const float* blob, const float* blobg, const float* d_sdf, int lds,
+                                const float* d_feat, int ldf, const float* d_normals, float* dpacked, float* d_x,
+                                float* ws,
                                 void* stream) {
   SdfCfg c;
   if (parse_sdf_cfg(cfg, scale, &c)) return (int)cudaErrorInvalidValue;
@@ -328,7 +329,7 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
     VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, nullptr, 0, 0, N, ZL, ly.out_ld[L - 1], 0,
                                                                        ly.out_ld[L - 1], 0.0f);
     if (d_sdf) {
-      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((N + 255) / 256), 256, 0, st, d_sdf, 1, 1, N, ZL, ly.out_ld[L - 1], 0, 1,
+      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((N + 255) / 256), 256, 0, st, d_sdf, lds, 1, N, ZL, ly.out_ld[L - 1], 0, 1,
                                                                        1.0f / c.scale);
     }
     if (d_feat) {

@@ -1,0 +1,63 @@
+"""One optimiser-ready training step of the path, as ``dpt_runner.py:214-253`` forms it.
+
+The reference driver stays the caller of ``NeuSRenderer.render``; this module restates only its loss
+(dpt_runner.py:228-243) so that tests and ``bench.py`` can run the measured unit of work - render forward,
+loss, backward, gradient all-reduce - without the driver's dataset / logging machinery.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import dist as vdist
+
+
+def driver_loss(render_out, true_rgb, mask=None, igr_weight=0.1, mask_weight=0.0, gt_feats=None, depth_weight=1.0,
+                global_batch: Optional[int] = None, data_parallel: bool = False):
+    """color L1 / mask_sum + igr * eikonal + mask_weight * BCE [+ depth-feature L1 / mask_sum].
+
+    With `data_parallel` the two batch-global normalisers (mask_sum and the Eikonal denominator) are formed
+    over all ranks, so the sum over ranks of the returned losses - and hence the all-reduced gradient - equals
+    the single-GPU value on the concatenated batch.
+    """
+    color = render_out["color_fine"]
+    if mask is None:
+        mask = torch.ones_like(render_out["weight_sum"])
+    if data_parallel and global_batch is not None:
+        mask_sum = mask.new_tensor(float(global_batch)) + 1e-5      # use_mask=False: mask == 1 (dpt_runner.py:209)
+    else:
+        mask_sum = mask.sum() + 1e-5
+    color_error = (color - true_rgb) * mask
+    loss = F.l1_loss(color_error, torch.zeros_like(color_error), reduction="sum") / mask_sum
+    if data_parallel:
+        eik = vdist.global_eikonal(render_out["_eik_num"], render_out["_eik_den"])
+    else:
+        eik = render_out["gradient_error"]
+    loss = loss + eik * igr_weight
+    if mask_weight != 0.0:
+        bce = F.binary_cross_entropy(render_out["weight_sum"].clip(1e-3, 1.0 - 1e-3), mask,
+                                     reduction="sum" if data_parallel else "mean")
+        if data_parallel:
+            bce = bce / float(global_batch if global_batch is not None else mask.numel())
+        loss = loss + bce * mask_weight
+    if gt_feats is not None and render_out.get("render_feats") is not None:
+        err = (render_out["render_feats"] - gt_feats) * mask
+        loss = loss + F.l1_loss(err, torch.zeros_like(err), reduction="sum") / mask_sum * depth_weight
+    return loss
+
+
+def train_step(renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None,
+               cos_anneal_ratio=1.0, perturb_overwrite=-1, igr_weight=0.1, grad_sync=None, global_batch=None):
+    """render + loss + backward (+ gradient all-reduce): the unit `train rays/s` counts.  Returns the loss."""
+    for p in params:
+        p.grad = None
+    out = renderer.render(rays_o, rays_d, near, far, perturb_overwrite=perturb_overwrite,
+                          background_rgb=background_rgb, cos_anneal_ratio=cos_anneal_ratio)
+    loss = driver_loss(out, true_rgb, igr_weight=igr_weight, gt_feats=gt_feats, global_batch=global_batch,
+                       data_parallel=grad_sync is not None)
+    loss.backward()
+    if grad_sync is not None:
+        grad_sync()
+    return loss.detach(), out
