@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the neural-SDF volume-rendering hot path (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's kernels
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU implementation (oracle port)
+
+Workloads (BASELINE.json configs):
+  train (default)  configs[1]: womsk_white.conf training step, 512 rays/batch/GPU, 64 coarse + 64 importance + 32
+                   outside samples, render forward + driver loss + backward (+ NCCL gradient all-reduce for N > 1);
+                   metric = train rays/s, whole job.  Weak scaling: every rank renders its own 512 rays.
+  grid             configs[3]: extract_fields SDF query on the 512^3 grid, x-slabs sharded over the ranks;
+                   metric = SDF pts/s.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic MAC / point (reverse-mode accounting, dense)
+F_SDF, F_SDF1, G_SDF, F_COL, F_DEP, F_NERF, F_NERF_D = 524544, 459008, 458752, 271360, 295168, 604160, 616448
+
+
+def alg_flops_per_ray(depth: bool) -> float:
+    f_dep = F_DEP if depth else 0
+    f_nerf = F_NERF_D if depth else F_NERF
+    fwd = 112 * F_SDF1 + 128 * (F_SDF + G_SDF + F_COL + f_dep) + 160 * f_nerf
+    bwd = 2 * (128 * (F_SDF + G_SDF + F_COL + f_dep) + 160 * f_nerf)
+    return 2.0 * (fwd + bwd)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def setup_dist(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world, dev):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def timed_steps(fn, steps, warmup, world, dev, flush, lib):
+    """W untimed + K timed calls of fn(i); every timed call is bracketed by CUDA events on the current stream,
+    an L2 flush (a 256 MiB write) runs untimed between calls.  Returns total milliseconds (max over ranks)."""
+    for i in range(warmup):
+        fn(i)
+    barrier(world)
+    evs = []
+    l0 = lib.vdn_launch_count()
+    for i in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(warmup + i)
+        b.record()
+        evs.append((a, b))
+    barrier(world)
+    total = sum(a.elapsed_time(b) for a, b in evs)
+    return max_over_ranks(total, world, dev), int(lib.vdn_launch_count() - l0)
+
+
+def cpu_reference_step(n_rays, depth, reps, warm=1):
+    """The reference algorithm (oracle port, PyTorch CPU, all host threads) on a bounded sample: rays/s."""
+    from oracle import vdn_oracle as vo
+    from vdn_nerf_b200 import configs, fields
+    conf = configs.CONFIGS["womsk_white_wdepth" if depth else "womsk_white"]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    mods = configs.build_networks(conf, fields, seed=0)
+    nets = vo.nets_from_modules(*mods, conf)
+    for _, t in nets.leaves():
+        t.requires_grad_(True)
+    o, d, near, far = vo.synthetic_rays(n_rays)
+    rgb = torch.full((n_rays, 3), 0.5)
+    times = []
+    for i in range(warm + reps):
+        torch.manual_seed(2)
+        t0 = time.perf_counter()
+        out = vo.render(nets, o, d, near, far, background_rgb=torch.ones(1, 3), cos_anneal_ratio=1.0)
+        gt = torch.full_like(out["render_feats"], 0.5) if out["render_feats"] is not None else None
+        loss = vo.driver_loss(out, rgb, gt_feats=gt)
+        torch.autograd.grad(loss, [t for _, t in nets.leaves()], allow_unused=True)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return n_rays * len(times) / sum(times), threads, times
+
+
+def cpu_reference_grid(n_points, reps):
+    from oracle import vdn_oracle as vo
+    from vdn_nerf_b200 import configs, fields
+    conf = configs.CONFIGS["womsk_white"]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    mods = configs.build_networks(conf, fields, seed=0)
+    nets = vo.nets_from_modules(*mods, conf)
+    pts = torch.rand(n_points, 3) * 2.02 - 1.01
+    times = []
+    with torch.no_grad():
+        for i in range(1 + reps):
+            t0 = time.perf_counter()
+            vo.sdf_value(nets.sdf, pts, nets.sdf_spec)
+            if i:
+                times.append(time.perf_counter() - t0)
+    return n_points * len(times) / sum(times), threads, times
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    depth = args.workload == "train_wdepth"
+    if args.workload == "grid":
+        sample = 1 << 17
+        vals = []
+        v, threads, times = cpu_reference_grid(sample, args.warmup + args.steps)
+        value, unit, metric, ms = v, "pts/s", "sdf_grid_pts_per_s", 1e3 * sum(times) / len(times)
+        cfg = {"workload": "extract_fields 512^3 SDF grid query (womsk_white SDF net)", "resolution": 512}
+        sample_s = f"{sample} lattice-like points per step, PyTorch CPU fp32"
+    else:
+        sample = 64
+        v, threads, times = cpu_reference_step(sample, depth, args.steps, warm=args.warmup)
+        value, unit, metric, ms = v, "rays/s", "train_rays_per_s", 1e3 * sum(times) / len(times)
+        cfg = {"workload": "womsk_white%s training step: render fwd + loss + bwd, 64+64 samples + 32 outside"
+                           % ("_wdepth" if depth else ""), "rays_per_step_per_gpu": args.rays}
+        sample_s = f"{sample} rays per step (bounded sample of the {args.rays}-ray batch), PyTorch CPU fp32, autograd"
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample_s},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference cannot travel to the GPU box; this is oracle/vdn_oracle.py, the restatement that "
+                    "oracle/make_golden.py pinned bit-exact against the live reference"}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    from oracle import vdn_oracle as vo          # synthetic-ray protocol + cpu_baseline leg only
+    from vdn_nerf_b200 import _lib, configs, dist as vdist, fields, ops
+    from vdn_nerf_b200.renderer import NeuSRenderer, extract_fields_sdf
+    from vdn_nerf_b200.training import train_step
+    rank, world, local = setup_dist(args.gpus)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    pk = peaks()
+    depth = args.workload == "train_wdepth"
+    conf = configs.CONFIGS["womsk_white_wdepth" if depth else "womsk_white"]
+    mods = configs.build_networks(conf, fields, seed=0, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    line = {}
+
+    if args.workload == "grid":
+        res = args.resolution
+        lo, hi = vdist.shard_range(res, rank, world)
+        u = torch.empty(hi - lo, res, res, device=dev)
+        bmin, bmax = [-1.01] * 3, [1.01] * 3
+
+        def fn(i):
+            extract_fields_sdf(mods[1], bmin, bmax, res, x_range=(lo, hi), out=u)
+        with ClockSampler(local) as cs:
+            ms, launches = timed_steps(fn, args.steps, args.warmup, world, dev, flush, lib)
+        pts = float(res) ** 3
+        value = pts * args.steps / (ms * 1e-3)
+        # end to end: bounds from host, field back on the host (the reference's extract_fields returns numpy)
+        host_u = torch.empty(hi - lo, res, res, pin_memory=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(max(1, args.steps // 2)):
+            fn(i)
+            host_u.copy_(u, non_blocking=False)
+        torch.cuda.synchronize()
+        e2e_t = (time.perf_counter() - t0) / max(1, args.steps // 2)
+        e2e_t = max_over_ranks(e2e_t, world, dev)
+        lib.vdn_prof_enable(1)
+        fn(0)
+        import ctypes
+        msn, sp, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        lib.vdn_prof_read(0, ctypes.byref(msn), ctypes.byref(sp), ctypes.byref(fl))
+        lib.vdn_prof_enable(0)
+        local_pts = float(hi - lo) * res * res
+        ach = 2.0 * F_SDF1 * local_pts / (msn.value * 1e-3) / 1e12
+        line.update({"metric": "sdf_grid_pts_per_s", "unit": "pts/s", "value": value, "ms_per_step": ms / args.steps,
+                     "config": {"workload": "extract_fields SDF grid query, womsk_white SDF net, x-slabs per rank",
+                                "resolution": res, "l2": "256 MiB flush between timed iterations", "mode": "fp32"},
+                     "e2e": {"value": pts / e2e_t, "unit": "pts/s", "h2d_bytes_per_step": 3 * res * 4,
+                             "d2h_bytes_per_step": int(local_pts * 4)},
+                     "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (9 launches per slab)",
+                                  "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                                  "frac": ach / pk["bf16_sustained"], "traffic": None,
+                                  "peak_source": pk["source"] + " bf16 sustained; the kernel is exact-fp32 FFMA",
+                                  "launch_ms": msn.value / max(1, sp.value)}})
+        cpu_kind = "grid"
+    else:
+        B = args.rays
+        rend = NeuSRenderer(*mods, **conf["neus_renderer"])
+        params = [p for m in mods if m is not None for p in m.parameters()]
+        o, d, near, far = (t.to(dev) for t in vo.synthetic_rays(B, seed=1234 + rank))
+        rgb = torch.full((B, 3), 0.5, device=dev)
+        gt = torch.full((B, 96), 0.5, device=dev) if depth else None
+        bg = torch.ones(1, 3, device=dev)
+        sync = vdist.FlatGradAllReduce(params) if world > 1 else None
+
+        def fn(i):
+            torch.manual_seed(2 + i)
+            train_step(rend, params, o, d, near, far, rgb, gt_feats=gt, background_rgb=bg, cos_anneal_ratio=1.0,
+                       grad_sync=sync, global_batch=B * world)
+        with ClockSampler(local) as cs:
+            ms, launches = timed_steps(fn, args.steps, args.warmup, world, dev, flush, lib)
+        value = B * world * args.steps / (ms * 1e-3)
+        # end to end through the public API with HOST buffers: pinned rays in, loss value out, every step
+        host = [t.cpu().pin_memory() for t in (o, d, near, far, rgb)]
+        dbuf = [torch.empty_like(t, device=dev) for t in host]
+        barrier(world)
+        t0 = time.perf_counter()
+        n_e2e = max(2, args.steps // 2)
+        for i in range(n_e2e):
+            for h, g_ in zip(host, dbuf):
+                g_.copy_(h, non_blocking=True)
+            torch.manual_seed(2 + i)
+            loss, _ = train_step(rend, params, dbuf[0], dbuf[1], dbuf[2], dbuf[3], dbuf[4], gt_feats=gt,
+                                 background_rgb=bg, cos_anneal_ratio=1.0, grad_sync=sync, global_batch=B * world)
+            float(loss)                                   # device -> host read of the step's result
+        barrier(world)
+        e2e_t = max_over_ranks((time.perf_counter() - t0) / n_e2e, world, dev)
+        # per-family device time of one extra step (CUDA events on the launching stream)
+        import ctypes
+        lib.vdn_prof_enable(1)
+        fn(0)
+        fam = {}
+        for f, nm in ((0, "gemm_nt"), (1, "wgrad")):
+            msn, sp, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+            lib.vdn_prof_read(f, ctypes.byref(msn), ctypes.byref(sp), ctypes.byref(fl))
+            fam[nm] = (msn.value, sp.value, fl.value)
+        lib.vdn_prof_enable(0)
+        gemm_ms = fam["gemm_nt"][0] + fam["wgrad"][0]
+        alg = alg_flops_per_ray(depth) * B
+        ach = alg / (gemm_ms * 1e-3) / 1e12
+        line.update({"metric": "train_rays_per_s", "unit": "rays/s", "value": value, "ms_per_step": ms / args.steps,
+                     "config": {"workload": "womsk_white%s training step (BASELINE configs[%d]): render fwd + driver "
+                                            "loss + bwd%s" % ("_wdepth" if depth else "", 2 if depth else 1,
+                                                              " + NCCL grad all-reduce" if world > 1 else ""),
+                                "rays_per_step_per_gpu": B, "global_batch": B * world, "n_samples": 64,
+                                "n_importance": 64, "n_outside": 32, "mode": "fp32",
+                                "l2": "256 MiB flush between timed iterations"},
+                     "e2e": {"value": B * world / e2e_t, "unit": "rays/s",
+                             "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)), "d2h_bytes_per_step": 4},
+                     "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel + gemm_tn_kernel (all MLP contractions "
+                                  "of one step: %d + %d launches)" % (fam["gemm_nt"][1], fam["wgrad"][1]),
+                                  "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                                  "frac": ach / pk["bf16_sustained"], "traffic": None,
+                                  "algorithmic_flops_per_step": alg,
+                                  "executed_flops_per_step": fam["gemm_nt"][2] + fam["wgrad"][2],
+                                  "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps),
+                                  "peak_source": pk["source"] + " bf16 sustained; the kernels are exact-fp32 FFMA"}})
+        cpu_kind = "train"
+
+    clocks = cs.summary()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            if cpu_kind == "grid":
+                v, threads, times = cpu_reference_grid(1 << 17, 3)
+                cb = {"value": v, "unit": "pts/s", "cores": threads, "kind": "port",
+                      "sample": "131072 points x 3 reps of SDFNetwork.sdf, PyTorch CPU fp32 (oracle port)"}
+            else:
+                v, threads, times = cpu_reference_step(128, depth, 2)
+                cb = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                      "sample": "128 rays x 2 timed steps (1 warm-up) of render+loss+backward, PyTorch CPU fp32 "
+                                "autograd (oracle port of the reference)"}
+            line["cpu_baseline"] = cb
+        line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                     "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                     "gpu_launches": int(launches), "clocks": clocks})
+        order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"]
+        print(json.dumps({k: line[k] for k in order if k in line}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "train_wdepth", "grid"])
+    ap.add_argument("--rays", type=int, default=512, help="rays per step per GPU")
+    ap.add_argument("--resolution", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

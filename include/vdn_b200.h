@@ -33,6 +33,12 @@ long long vdn_launch_count(void);
 /* cudaGetErrorString for the codes this library returns. */
 const char* vdn_error_string(int code);
 
+/* Measurement aid for bench.py: when enabled, CUDA events bracket every launch of a kernel family on its
+ * stream (0 = gemm_nt, 1 = weight-gradient gemm_tn + reduce, 2 = tcgen05 chain kernels); vdn_prof_read sums the
+ * recorded durations (ms), the number of spans and the executed FLOPs.  Enabling/disabling clears the record. */
+int vdn_prof_enable(int on);
+int vdn_prof_read(int family, double* ms /*host*/, long long* spans /*host*/, double* flops /*host*/);
+
 /* ---- packed parameters (weight_norm: fields.py:65-66, 141-142; nn.Linear: fields.py:303-318) ------------ */
 long long vdn_mlp_layout(int L, const int* in_dims /*host*/, const int* out_dims /*host*/, long long* off_w /*host*/,
                          long long* off_wt /*host*/, long long* off_b /*host*/);

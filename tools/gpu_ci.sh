@@ -1,0 +1,34 @@
+#!/bin/bash
+# One GPU-box session: tcgen05 probe, the -m gpu parity suite (one pytest process per group so that a faulting
+# kernel cannot poison the CUDA context of the others), smoke(), bench lines and an ncu launch list.
+# Usage (from the repo root, under gpurun):  bash tools/gpu_ci.sh [quick]
+set -u
+mkdir -p gpurun_out
+OUT=gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
+echo "== probe_tc" ; timeout 120 ./build/probe_tc > $OUT/probe.log 2>&1; echo "probe exit $?"; tail -14 $OUT/probe.log
+
+GROUPS=("embedder or packed" "sdf_forward" "backward_vs_fp64 or depth_head" "nerf" "upsample or cat_z"
+        "render_core or composite" "full_render or without_background" "extract_fields" "full_size")
+: > $OUT/pytest.log
+i=0
+for g in "${GROUPS[@]}"; do
+  i=$((i+1))
+  echo "== pytest group $i: $g" | tee -a $OUT/pytest.log
+  timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "$g" >> $OUT/pytest.log 2>&1
+  echo "group $i exit $?" | tee -a $OUT/pytest.log
+  tail -3 $OUT/pytest.log
+done
+grep -E "passed|failed|error" $OUT/pytest.log | tail -12
+
+echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke exit $?"; tail -3 $OUT/smoke.log
+if [ "${1:-}" != "quick" ]; then
+  echo "== bench train"; timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "exit $?"; tail -c 1800 $OUT/bench_train.json; tail -3 $OUT/bench_train.err
+  echo "== bench grid"; timeout 900 python bench.py --workload grid --steps 2 --warmup 3 > $OUT/bench_grid.json 2> $OUT/bench_grid.err; echo "exit $?"; tail -c 1500 $OUT/bench_grid.json; tail -3 $OUT/bench_grid.err
+  echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "exit $?"; tail -c 900 $OUT/bench_ref.json
+  echo "== ncu launch list"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_train.csv \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_train.log 2>&1; echo "ncu exit $?"
+  wc -l $OUT/launches_train.csv
+fi
+echo "== done"

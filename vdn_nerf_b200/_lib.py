@@ -21,6 +21,8 @@ SIGNATURES = {
     "vdn_abi_version": (I, []),
     "vdn_launch_count": (L, []),
     "vdn_error_string": (c_char_p, [I]),
+    "vdn_prof_enable": (I, [I]),
+    "vdn_prof_read": (I, [I, P, P, P]),
     "vdn_mlp_layout": (L, [I, P, P, P, P, P]),
     "vdn_mlp_pack": (I, [I, P, P, P, P, P, P, P, P]),
     "vdn_mlp_unpack_grads": (I, [I, P, P, P, P, P, P, P, P, P, P]),

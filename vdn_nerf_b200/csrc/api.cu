@@ -2,14 +2,66 @@
 #include "pointwise.cuh"
 #include "../../include/vdn_b200.h"
 
+#include <vector>
+#include "gemm_simt.cuh"
+
 namespace vdn {
 std::atomic<long long> g_launches{0};
+
+// ---- optional profiling: CUDA events around kernel families, summed on read ----------------------------
+static bool g_prof_on = false;
+struct ProfSpan { cudaEvent_t a, b; };
+static std::vector<ProfSpan> g_spans[PROF_FAMILIES];
+static double g_flops[PROF_FAMILIES];
+static cudaEvent_t g_open[PROF_FAMILIES];
+
+void prof_begin(int family, cudaStream_t st, double flops) {
+  if (!g_prof_on) return;
+  cudaEvent_t a;
+  cudaEventCreate(&a);
+  cudaEventRecord(a, st);
+  g_open[family] = a;
+  g_flops[family] += flops;
 }
+void prof_end(int family, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEvent_t b;
+  cudaEventCreate(&b);
+  cudaEventRecord(b, st);
+  g_spans[family].push_back({g_open[family], b});
+}
+}  // namespace vdn
 using namespace vdn;
 
 extern "C" int vdn_abi_version(void) { return 1; }
 extern "C" long long vdn_launch_count(void) { return g_launches.load(); }
 extern "C" const char* vdn_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
+
+extern "C" int vdn_prof_enable(int on) {
+  g_prof_on = on != 0;
+  for (int f = 0; f < PROF_FAMILIES; ++f) {
+    for (auto& s : g_spans[f]) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    g_spans[f].clear();
+    g_flops[f] = 0.0;
+  }
+  return 0;
+}
+
+extern "C" int vdn_prof_read(int family, double* ms, long long* spans, double* flops) {
+  if (family < 0 || family >= PROF_FAMILIES) return (int)cudaErrorInvalidValue;
+  double total = 0.0;
+  for (auto& s : g_spans[family]) {
+    cudaError_t e = cudaEventSynchronize(s.b);
+    if (e != cudaSuccess) return (int)e;
+    float t = 0.f;
+    cudaEventElapsedTime(&t, s.a, s.b);
+    total += t;
+  }
+  *ms = total;
+  *spans = (long long)g_spans[family].size();
+  *flops = g_flops[family];
+  return 0;
+}
 
 extern "C" int vdn_embed_fwd(const float* x, long long N, int d, int multires, float* out, void* stream) {
   if (N <= 0) return 0;

@@ -368,12 +368,19 @@ inline bool operand_ok(const Operand& o) {
   return true;
 }
 
+// Optional per-family timing (vdn_prof_enable): CUDA events around the GEMM launches on the launching stream.
+void prof_begin(int family, cudaStream_t st, double flops);
+void prof_end(int family, cudaStream_t st);
+enum { PROF_GEMM_NT = 0, PROF_WGRAD = 1, PROF_TC = 2, PROF_FAMILIES = 3 };
+
 inline int launch_gemm_nt(int M, int N, int K, const Operand& A, const float* B, int ldb, const Epilogue& E,
                           cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   if (K % GEMM_BK != 0 || !operand_ok(A) || ((uintptr_t)B & 15) || (ldb & 3)) return (int)cudaErrorInvalidValue;
   dim3 grid((M + GEMM_BM - 1) / GEMM_BM, (N + GEMM_BN - 1) / GEMM_BN);
+  prof_begin(PROF_GEMM_NT, st, 2.0 * M * N * K);
   VDN_LAUNCH(gemm_nt_kernel, grid, GEMM_THREADS, 0, st, M, N, K, A, B, ldb, E);
+  prof_end(PROF_GEMM_NT, st);
   return (int)cudaGetLastError();
 }
 
@@ -396,12 +403,14 @@ inline int launch_wgrad(int M, int N, int K, const Operand& A0, const Operand& X
   const int rows_per_split = (rows + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
   const int ldp = K;
   dim3 grid((K + GEMM_BN - 1) / GEMM_BN, (N + GEMM_BM - 1) / GEMM_BM, S);
+  prof_begin(PROF_WGRAD, st, 2.0 * M * N * K * (A1 ? 2 : 1));
   VDN_LAUNCH(gemm_tn_kernel, grid, GEMM_THREADS, 0, st, M, N, K, A0, X0, A1 ? *A1 : A0, X1 ? *X1 : X0, A1 ? 2 : 1,
                                                 partials, ldp, rows_per_split);
   int e = (int)cudaGetLastError();
   if (e) return e;
   int total = N * K;
   VDN_LAUNCH(reduce_partials_kernel, (total + 255) / 256, 256, 0, st, partials, S, N, K, ldp, dW, ldd, accumulate);
+  prof_end(PROF_WGRAD, st);
   return (int)cudaGetLastError();
 }
 
