@@ -234,6 +234,7 @@ def run_ours(args):
     rank, world, local = setup_dist(args.gpus)
     dev = torch.device("cuda", local)
     lib = _lib.load()
+    ops.set_precision(args.precision)
     pk = peaks()
     depth = args.workload == "train_wdepth"
     conf = configs.CONFIGS["womsk_white_wdepth" if depth else "womsk_white"]
@@ -266,21 +267,26 @@ def run_ours(args):
         lib.vdn_prof_enable(1)
         fn(0)
         import ctypes
-        msn, sp, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
-        lib.vdn_prof_read(0, ctypes.byref(msn), ctypes.byref(sp), ctypes.byref(fl))
+        fam_ms, fam_n = 0.0, 0
+        for f in (0, 2):
+            msn, sp, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+            lib.vdn_prof_read(f, ctypes.byref(msn), ctypes.byref(sp), ctypes.byref(fl))
+            fam_ms += msn.value
+            fam_n += sp.value
         lib.vdn_prof_enable(0)
         local_pts = float(hi - lo) * res * res
-        ach = 2.0 * F_SDF1 * local_pts / (msn.value * 1e-3) / 1e12
+        ach = 2.0 * F_SDF1 * local_pts / (fam_ms * 1e-3) / 1e12
+        kname = "gemm_nt_tc_kernel (tcgen05 kind::tf32)" if args.precision == "tf32" else "gemm_nt_kernel (FFMA)"
         line.update({"metric": "sdf_grid_pts_per_s", "unit": "pts/s", "value": value, "ms_per_step": ms / args.steps,
                      "config": {"workload": "extract_fields SDF grid query, womsk_white SDF net, x-slabs per rank",
-                                "resolution": res, "l2": "256 MiB flush between timed iterations", "mode": "fp32"},
+                                "resolution": res, "l2": "256 MiB flush between timed iterations", "mode": args.precision},
                      "e2e": {"value": pts / e2e_t, "unit": "pts/s", "h2d_bytes_per_step": 3 * res * 4,
                              "d2h_bytes_per_step": int(local_pts * 4)},
-                     "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (9 launches per slab)",
+                     "roofline": {"bound": "tensor", "kernel": kname + ", 9 launches per slab",
                                   "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                                   "frac": ach / pk["bf16_sustained"], "traffic": None,
-                                  "peak_source": pk["source"] + " bf16 sustained; the kernel is exact-fp32 FFMA",
-                                  "launch_ms": msn.value / max(1, sp.value)}})
+                                  "peak_source": pk["source"] + " bf16 sustained (dense tf32 peak is half of it)",
+                                  "launch_ms": fam_ms / max(1, fam_n)}})
         cpu_kind = "grid"
     else:
         B = args.rays
@@ -319,12 +325,12 @@ def run_ours(args):
         lib.vdn_prof_enable(1)
         fn(0)
         fam = {}
-        for f, nm in ((0, "gemm_nt"), (1, "wgrad")):
+        for f, nm in ((0, "gemm_nt"), (1, "wgrad"), (2, "tc")):
             msn, sp, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
             lib.vdn_prof_read(f, ctypes.byref(msn), ctypes.byref(sp), ctypes.byref(fl))
             fam[nm] = (msn.value, sp.value, fl.value)
         lib.vdn_prof_enable(0)
-        gemm_ms = fam["gemm_nt"][0] + fam["wgrad"][0]
+        gemm_ms = fam["gemm_nt"][0] + fam["wgrad"][0] + fam["tc"][0]
         alg = alg_flops_per_ray(depth) * B
         ach = alg / (gemm_ms * 1e-3) / 1e12
         line.update({"metric": "train_rays_per_s", "unit": "rays/s", "value": value, "ms_per_step": ms / args.steps,
@@ -332,18 +338,20 @@ def run_ours(args):
                                             "loss + bwd%s" % ("_wdepth" if depth else "", 2 if depth else 1,
                                                               " + NCCL grad all-reduce" if world > 1 else ""),
                                 "rays_per_step_per_gpu": B, "global_batch": B * world, "n_samples": 64,
-                                "n_importance": 64, "n_outside": 32, "mode": "fp32",
+                                "n_importance": 64, "n_outside": 32, "mode": args.precision,
                                 "l2": "256 MiB flush between timed iterations"},
                      "e2e": {"value": B * world / e2e_t, "unit": "rays/s",
                              "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)), "d2h_bytes_per_step": 4},
-                     "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel + gemm_tn_kernel (all MLP contractions "
-                                  "of one step: %d + %d launches)" % (fam["gemm_nt"][1], fam["wgrad"][1]),
+                     "roofline": {"bound": "tensor", "kernel": "all MLP contractions of one step: gemm_nt_tc_kernel (tcgen05) x%d, "
+                                  "gemm_nt_kernel (FFMA) x%d, gemm_tn_kernel (wgrad) x%d"
+                                  % (fam["tc"][1], fam["gemm_nt"][1], fam["wgrad"][1]),
                                   "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                                   "frac": ach / pk["bf16_sustained"], "traffic": None,
                                   "algorithmic_flops_per_step": alg,
-                                  "executed_flops_per_step": fam["gemm_nt"][2] + fam["wgrad"][2],
+                                  "executed_flops_per_step": fam["gemm_nt"][2] + fam["wgrad"][2] + fam["tc"][2],
+                                  "ms_by_family": {k: v[0] for k, v in fam.items()},
                                   "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps),
-                                  "peak_source": pk["source"] + " bf16 sustained; the kernels are exact-fp32 FFMA"}})
+                                  "peak_source": pk["source"] + " bf16 sustained (dense tf32 peak is half of it)"}})
         cpu_kind = "train"
 
     clocks = cs.summary()
@@ -360,8 +368,8 @@ def run_ours(args):
                                 "autograd (oracle port of the reference)"}
             line["cpu_baseline"] = cb
         line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-                     "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                     "gpu_launches": int(launches), "clocks": clocks})
+                     "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32",
+                     "data": "synthetic", "gpu_launches": int(launches), "clocks": clocks})
         order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"]
         print(json.dumps({k: line[k] for k in order if k in line}))
@@ -380,6 +388,8 @@ def main():
     ap.add_argument("--rays", type=int, default=512, help="rays per step per GPU")
     ap.add_argument("--resolution", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="fp32: exact FFMA kernels; tf32: tcgen05 tensor-core kernels (fp32 accumulate)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

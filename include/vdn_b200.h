@@ -15,7 +15,7 @@
  *
  * Packed parameters.  A network's effective weights live in one fp32 buffer laid out by vdn_mlp_layout():
  * per layer W[out_ld,in_ld], W^T[in_ld,out_ld], bias[out_ld] with in_ld/out_ld rounded up to 16 and zero
- * padding.  A packed gradient buffer has the same layout (W and bias regions are accumulated into).
+ * padding, followed by tf32 SWIZZLE_128B tile images of W and W^T for the tcgen05 kernels (csrc/mlp_layout.cuh).  A packed gradient buffer has the same layout (W and bias regions are accumulated into).
  */
 #ifndef VDN_B200_H
 #define VDN_B200_H
@@ -33,6 +33,14 @@ long long vdn_launch_count(void);
 /* cudaGetErrorString for the codes this library returns. */
 const char* vdn_error_string(int code);
 
+/* Arithmetic mode of the MLP contractions: 0 = exact fp32 (FFMA kernels; parity <= 1e-5), 1 = tf32 tensor cores
+ * (tcgen05.mma kind::tf32 with fp32 accumulation in TMEM; parity <= 2e-3 on colour and normals).  Process-wide.
+ * Mode 1 allocates one 4-byte device flag that a tcgen05 kernel raises if one of its bounded barrier waits times
+ * out; vdn_tc_fault() reads it (synchronising). */
+int vdn_set_mode(int mode);
+int vdn_get_mode(void);
+int vdn_tc_fault(void);
+
 /* Measurement aid for bench.py: when enabled, CUDA events bracket every launch of a kernel family on its
  * stream (0 = gemm_nt, 1 = weight-gradient gemm_tn + reduce, 2 = tcgen05 chain kernels); vdn_prof_read sums the
  * recorded durations (ms), the number of spans and the executed FLOPs.  Enabling/disabling clears the record. */
@@ -45,11 +53,12 @@ long long vdn_mlp_layout(int L, const int* in_dims /*host*/, const int* out_dims
 /* v/g/b/rows are host arrays of 2*L entries: each packed layer stacks up to two parameter sets by rows
  * (second entry null / 0 rows when unused).  g == null means a plain (not weight-normed) weight. */
 int vdn_mlp_pack(int L, const int* in_dims, const int* out_dims, const float* const* v, const float* const* g,
-                 const float* const* b, const int* rows, float* packed, void* stream);
+                 const float* const* b, const int* rows, const int* rot /*host, nullable: per-layer input-column
+                 rotation*/, float* packed, void* stream);
 /* Weight-norm backward + un-padding: packed gradient -> d weight_v, d weight_g, d bias (overwritten). */
 int vdn_mlp_unpack_grads(int L, const int* in_dims, const int* out_dims, const float* const* v,
-                         const float* const* g, const int* rows, const float* dpacked, float* const* dv,
-                         float* const* dg, float* const* db, void* stream);
+                         const float* const* g, const int* rows, const int* rot, const float* dpacked,
+                         float* const* dv, float* const* dg, float* const* db, void* stream);
 
 /* ---- SDFNetwork (fields.py:9-108).  cfg (host) = {d_in, multires, d_hidden, n_layers, d_out, skip_layer|-1} */
 int vdn_sdf_layer_dims(const int* cfg, int* in_dims, int* out_dims); /* returns number of linear layers */

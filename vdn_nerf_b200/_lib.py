@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdn_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 
@@ -24,8 +24,11 @@ SIGNATURES = {
     "vdn_prof_enable": (I, [I]),
     "vdn_prof_read": (I, [I, P, P, P]),
     "vdn_mlp_layout": (L, [I, P, P, P, P, P]),
-    "vdn_mlp_pack": (I, [I, P, P, P, P, P, P, P, P]),
-    "vdn_mlp_unpack_grads": (I, [I, P, P, P, P, P, P, P, P, P, P]),
+    "vdn_mlp_pack": (I, [I, P, P, P, P, P, P, P, P, P]),
+    "vdn_mlp_unpack_grads": (I, [I, P, P, P, P, P, P, P, P, P, P, P]),
+    "vdn_set_mode": (I, [I]),
+    "vdn_get_mode": (I, []),
+    "vdn_tc_fault": (I, []),
     "vdn_sdf_layer_dims": (I, [P, P, P]),
     "vdn_sdf_blob_floats": (L, [P, L, I]),
     "vdn_sdf_blobg_floats": (L, [P, L]),

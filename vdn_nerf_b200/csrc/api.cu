@@ -3,10 +3,12 @@
 #include "../../include/vdn_b200.h"
 
 #include <vector>
-#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace vdn {
 std::atomic<long long> g_launches{0};
+int g_mode = 0;
+int* g_tc_fault = nullptr;
 
 // ---- optional profiling: CUDA events around kernel families, summed on read ----------------------------
 static bool g_prof_on = false;
@@ -33,9 +35,28 @@ void prof_end(int family, cudaStream_t st) {
 }  // namespace vdn
 using namespace vdn;
 
-extern "C" int vdn_abi_version(void) { return 1; }
+extern "C" int vdn_abi_version(void) { return 2; }
 extern "C" long long vdn_launch_count(void) { return g_launches.load(); }
 extern "C" const char* vdn_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
+
+extern "C" int vdn_set_mode(int mode) {
+  if (mode != 0 && mode != 1) return (int)cudaErrorInvalidValue;
+  if (mode == 1 && !g_tc_fault) {  // 4-byte device flag raised by a timed-out barrier wait in a tcgen05 kernel
+    cudaError_t e = cudaMalloc(&g_tc_fault, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(g_tc_fault, 0, sizeof(int));
+    if (e != cudaSuccess) return (int)e;
+  }
+  g_mode = mode;
+  return 0;
+}
+extern "C" int vdn_get_mode(void) { return g_mode; }
+extern "C" int vdn_tc_fault(void) {
+  if (!g_tc_fault) return 0;
+  int h = 0;
+  if (cudaMemcpy(&h, g_tc_fault, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return h;
+}
 
 extern "C" int vdn_prof_enable(int on) {
   g_prof_on = on != 0;

@@ -373,7 +373,7 @@ void prof_begin(int family, cudaStream_t st, double flops);
 void prof_end(int family, cudaStream_t st);
 enum { PROF_GEMM_NT = 0, PROF_WGRAD = 1, PROF_TC = 2, PROF_FAMILIES = 3 };
 
-inline int launch_gemm_nt(int M, int N, int K, const Operand& A, const float* B, int ldb, const Epilogue& E,
+inline int launch_gemm_nt_simt(int M, int N, int K, const Operand& A, const float* B, int ldb, const Epilogue& E,
                           cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   if (K % GEMM_BK != 0 || !operand_ok(A) || ((uintptr_t)B & 15) || (ldb & 3)) return (int)cudaErrorInvalidValue;

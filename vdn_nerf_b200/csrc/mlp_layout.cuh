@@ -1,11 +1,16 @@
 // Packed parameter layout shared by every MLP kernel family.
 //
 // One contiguous fp32 buffer per network and per optimiser step holds, for every linear layer l:
-//   W_l   [out_ld, in_ld]   effective weight (weight-norm applied: g * v / ||v||_row), zero padded
-//   WT_l  [in_ld, out_ld]   its transpose (the dgrad / input-gradient passes read it as the "B" operand)
-//   b_l   [out_ld]
-// with in_ld = round_up(in_dim, 16), out_ld = round_up(out_dim, 16).  The gradient buffer of a network has
-// the same layout (the WT region is unused), so weight-norm backward is one kernel over the whole network.
+//   W_l    [out_ld, in_ld]    effective weight (weight-norm applied: g * v / ||v||_row), zero padded
+//   WT_l   [in_ld, out_ld]    its transpose (the dgrad / input-gradient passes read it as the "B" operand)
+//   b_l    [out_ld]
+//   IW_l   [ceil(in_dim/32)][out_ld][32]   W_l  as tcgen05 operand tiles: per 32-column K block, the rows in the
+//   IWT_l  [ceil(out_dim/32)][in_ld][32]   W_l^T  SWIZZLE_128B K-major shared-memory image (tc_common.cuh), values
+//                                          rounded to tf32 - one linear cp.async.bulk per tile, no tensor map
+// with in_ld = round_up(in_dim, 16), out_ld = round_up(out_dim, 16).  The gradient buffer of a network uses
+// the W and b regions of the same layout, so weight-norm backward is one kernel over the whole network.
+// A layer may rotate its input columns (rot): packed column (c - rot) mod in_dim holds source column c; the
+// NeRF skip layer uses it to store [hidden | embedding] instead of the reference's [embedding | hidden].
 #pragma once
 #include "common.cuh"
 
@@ -18,6 +23,7 @@ struct MlpLayout {
   int in_dim[VDN_MAX_LAYERS], out_dim[VDN_MAX_LAYERS];
   int in_ld[VDN_MAX_LAYERS], out_ld[VDN_MAX_LAYERS];
   long long off_w[VDN_MAX_LAYERS], off_wt[VDN_MAX_LAYERS], off_b[VDN_MAX_LAYERS];
+  long long off_iw[VDN_MAX_LAYERS], off_iwt[VDN_MAX_LAYERS];
   long long total;  // floats
 };
 
@@ -37,6 +43,13 @@ inline int make_layout(int L, const int* in_dims, const int* out_dims, MlpLayout
     off += (long long)ly->in_ld[l] * ly->out_ld[l];
     ly->off_b[l] = off;
     off += ly->out_ld[l];
+  }
+  for (int l = 0; l < L; ++l) {
+    off = (off + 255) / 256 * 256;  // 1024-byte aligned tiles
+    ly->off_iw[l] = off;
+    off += (long long)((in_dims[l] + 31) / 32) * ly->out_ld[l] * 32;
+    ly->off_iwt[l] = off;
+    off += (long long)((out_dims[l] + 31) / 32) * ly->in_ld[l] * 32;
   }
   ly->total = off;
   return 0;

@@ -3,8 +3,7 @@
 //   * NeRF++ background field                                             reference fields.py:264-355
 // Post-activation tensors H_l are stored (ReLU backward only needs the sign), heads that share an input are
 // packed as one stacked weight so they run as one GEMM with a splitting epilogue.
-#include "gemm_simt.cuh"
-#include "mlp_layout.cuh"
+#include "gemm_tc.cuh"
 #include "pointwise.cuh"
 #include "../../include/vdn_b200.h"
 
@@ -77,7 +76,7 @@ extern "C" int vdn_rendernet_forward(const int* cfg, const float* packed, const 
       E = make_epilogue(c.squeeze_out ? EPI_SIGMOID : EPI_RELU, packed + c.ly.off_b[l], out, c.d_out);
     else
       E = make_epilogue(EPI_RELU, packed + c.ly.off_b[l], H + (long long)l * N * c.ldH, c.ldH);
-    e = launch_gemm_nt((int)N, c.ly.out_dim[l], c.ly.in_ld[l], A, packed + c.ly.off_w[l], c.ly.in_ld[l], E, st);
+    e = launch_gemm_nt((int)N, c.ly.out_dim[l], c.ly.in_ld[l], A, wref(c.ly, packed, l), E, st);
     if (e) return e;
   }
   return 0;
@@ -130,15 +129,14 @@ extern "C" int vdn_rendernet_backward(const int* cfg, const float* packed, long 
     if (e) return e;
     e = launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);
     if (e) return e;
-    const float* WT = packed + ly.off_wt[l];
     if (l > 0) {
       Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(l - 1) & 1], c.ldH);
       E.aux = H + (long long)(l - 1) * N * c.ldH; E.ldaux = c.ldH; E.split = 0;
-      e = launch_gemm_nt(M, ly.in_dim[l], ly.out_ld[l], zbar, WT, ly.out_ld[l], E, st);
+      e = launch_gemm_nt(M, ly.in_dim[l], ly.out_ld[l], zbar, wtref(ly, packed, l), E, st);
       if (e) return e;
     } else if (d_cin) {
       Epilogue E = make_epilogue(EPI_STORE, nullptr, d_cin, c.ldIn);
-      e = launch_gemm_nt(M, c.in0, ly.out_ld[0], zbar, WT, ly.out_ld[0], E, st);
+      e = launch_gemm_nt(M, c.in0, ly.out_ld[0], zbar, wtref(ly, packed, 0), E, st);
       if (e) return e;
     }
   }
@@ -229,9 +227,10 @@ extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float
   carve_nerf(c, N, blob, &b);
   const int M = (int)N, D = c.D;
   unsigned blocks = (unsigned)((N + 127) / 128);
-  // pts embedding -> E and the head of the skip buffer U (reference fields.py:334-335: cat[input_pts, h])
-  VDN_LAUNCH(embed_rows_kernel, blocks, 128, 0, st, pts, c.d_in, N, c.d_in, c.multires, 1.0f, b.E, c.ldE, b.U, c.ldU, 0, 1.0f,
-                                            c.d_e);
+  // pts embedding -> E and the tail of the skip buffer U.  The reference concatenates [input_pts, h]
+  // (fields.py:334-335); the packed weight of the next layer has its columns rotated so U is [h | input_pts].
+  VDN_LAUNCH(embed_rows_kernel, blocks, 128, 0, st, pts, c.d_in, N, c.d_in, c.multires, 1.0f, b.E, c.ldE, b.U, c.ldU,
+             c.W, 1.0f, c.ldU);
   // view embedding -> tail of VIN (reference fields.py:340: cat[feature, input_views])
   VDN_LAUNCH(embed_rows_kernel, blocks, 128, 0, st, views, c.d_in_view, N, c.d_in_view, c.multires_view, 1.0f, nullptr, 0,
                                             b.VIN, c.ldV, c.W, 1.0f, c.ldV);
@@ -240,36 +239,29 @@ extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float
   for (int i = 0; i < D; ++i) {
     Operand A = nerf_input(c, b, i);
     Epilogue E = make_epilogue(EPI_RELU, packed + ly.off_b[i], b.H[i], c.ldH);
-    if (i == c.skip) { E.c = b.U; E.ldc = c.ldU; E.coff = c.d_e; }
-    e = launch_gemm_nt(M, c.W, ly.in_ld[i], A, packed + ly.off_w[i], ly.in_ld[i], E, st);
+    if (i == c.skip) { E.c = b.U; E.ldc = c.ldU; E.coff = 0; }
+    e = launch_gemm_nt(M, c.W, ly.in_ld[i], A, wref(ly, packed, i), E, st);
     if (e) return e;
-    if (i == c.skip) {  // zero the padding columns of U once per call
-      long long tot = N * (c.ldU - (c.W + c.d_e));
-      if (tot > 0)
-        VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, nullptr, 0, 0, N, b.U, c.ldU,
-                                                                           c.W + c.d_e, c.ldU, 0.0f);
-    }
   }
   // heads on h_{D-1}: sigma (row 0) and the feature (rows 1..W) into VIN[:, :W]
   {
     Operand A = nerf_input(c, b, D);
     Epilogue E = make_epilogue(EPI_SPLIT, packed + ly.off_b[D], b.VIN, c.ldV);
     E.c2 = sigma; E.ldc2 = 1; E.split = 1; E.scale = 1.0f;
-    e = launch_gemm_nt(M, 1 + c.W, ly.in_ld[D], A, packed + ly.off_w[D], ly.in_ld[D], E, st);
+    e = launch_gemm_nt(M, 1 + c.W, ly.in_ld[D], A, wref(ly, packed, D), E, st);
     if (e) return e;
   }
   {
     Operand A = make_operand(b.VIN, c.ldV, c.ldV, c.vin);
     Epilogue E = make_epilogue(EPI_RELU, packed + ly.off_b[D + 1], b.HV, c.ldHV);
-    e = launch_gemm_nt(M, c.W / 2, ly.in_ld[D + 1], A, packed + ly.off_w[D + 1], ly.in_ld[D + 1], E, st);
+    e = launch_gemm_nt(M, c.W / 2, ly.in_ld[D + 1], A, wref(ly, packed, D + 1), E, st);
     if (e) return e;
   }
   {
     Operand A = make_operand(b.HV, c.ldHV, c.ldHV, c.W / 2);
     Epilogue E = make_epilogue(EPI_SPLIT, packed + ly.off_b[D + 2], dpt, c.dpt_dim);
     E.c2 = rgb; E.ldc2 = c.rgb_dims; E.split = c.rgb_dims; E.scale = 1.0f;
-    e = launch_gemm_nt(M, c.rgb_dims + c.dpt_dim, ly.in_ld[D + 2], A, packed + ly.off_w[D + 2], ly.in_ld[D + 2], E,
-                       st);
+    e = launch_gemm_nt(M, c.rgb_dims + c.dpt_dim, ly.in_ld[D + 2], A, wref(ly, packed, D + 2), E, st);
     if (e) return e;
   }
   return 0;
@@ -341,7 +333,7 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
     if (e) return e;
     Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZV, c.ldHV);
     E.aux = b.HV; E.ldaux = c.ldHV;
-    e = launch_gemm_nt(M, c.W / 2, ldo, zo, packed + ly.off_wt[D + 2], ldo, E, st);
+    e = launch_gemm_nt(M, c.W / 2, ldo, zo, wtref(ly, packed, D + 2), E, st);
     if (e) return e;
   }
   // view layer
@@ -360,12 +352,11 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
     if (e) return e;
     Epilogue E = make_epilogue(EPI_STORE, nullptr, ZHEAD, ldh);
     E.coff = 1;
-    e = launch_gemm_nt(M, c.W, c.ldHV, zv, packed + ly.off_wt[D + 1], ly.out_ld[D + 1], E, st);
+    e = launch_gemm_nt(M, c.W, c.ldHV, zv, wtref(ly, packed, D + 1), E, st);
     if (e) return e;
     if (d_views) {
       Epilogue E2 = make_epilogue(EPI_STORE, nullptr, DVIN, c.ldV);
-      e = launch_gemm_nt(M, c.d_ev, c.ldHV, zv, packed + ly.off_wt[D + 1] + (long long)c.W * ly.out_ld[D + 1],
-                         ly.out_ld[D + 1], E2, st);
+      e = launch_gemm_nt(M, c.d_ev, c.ldHV, zv, wtref(ly, packed, D + 1, c.W), E2, st);
       if (e) return e;
     }
   }
@@ -377,31 +368,29 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
     if (e) return e;
     Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(D - 1) & 1], c.ldH);
     E.aux = b.H[D - 1]; E.ldaux = c.ldH;
-    e = launch_gemm_nt(M, c.W, ldh, zh, packed + ly.off_wt[D], ldh, E, st);
+    e = launch_gemm_nt(M, c.W, ldh, zh, wtref(ly, packed, D), E, st);
     if (e) return e;
   }
   for (int i = D - 1; i >= 0; --i) {
     Operand zbar = make_operand(ZB[i & 1], c.ldH, c.ldH, c.W);
     e = wg(i, zbar, nerf_input(c, b, i));
     if (e) return e;
-    const float* WT = packed + ly.off_wt[i];
-    const int ldwt = ly.out_ld[i];
     if (i > 0) {
       // hidden part of the input cotangent, masked by the sign of h_{i-1}
       const bool after_skip = (i - 1 == c.skip);
       Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(i - 1) & 1], c.ldH);
-      if (after_skip) { E.aux = b.U; E.ldaux = c.ldU; E.split = c.d_e; }
+      if (after_skip) { E.aux = b.U; E.ldaux = c.ldU; E.split = 0; }
       else { E.aux = b.H[i - 1]; E.ldaux = c.ldH; E.split = 0; }
-      e = launch_gemm_nt(M, c.W, c.ldH, zbar, WT + (after_skip ? (long long)c.d_e * ldwt : 0), ldwt, E, st);
+      e = launch_gemm_nt(M, c.W, c.ldH, zbar, wtref(ly, packed, i), E, st);
       if (e) return e;
       if (after_skip && d_pts) {
         Epilogue E2 = make_epilogue(EPI_STORE, nullptr, EE1, c.ldE);
-        e = launch_gemm_nt(M, c.d_e, c.ldH, zbar, WT, ldwt, E2, st);
+        e = launch_gemm_nt(M, c.d_e, c.ldH, zbar, wtref(ly, packed, i, c.W), E2, st);
         if (e) return e;
       }
     } else if (d_pts) {
       Epilogue E2 = make_epilogue(EPI_STORE, nullptr, EE0, c.ldE);
-      e = launch_gemm_nt(M, c.d_e, c.ldH, zbar, WT, ldwt, E2, st);
+      e = launch_gemm_nt(M, c.d_e, c.ldH, zbar, wtref(ly, packed, 0), E2, st);
       if (e) return e;
     }
   }

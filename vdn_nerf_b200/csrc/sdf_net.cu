@@ -7,8 +7,7 @@
 //
 // Math: SURVEY.md Appendix A.  Storage: one pre-activation tensor Z_l per layer (activations are recomputed
 // in the consumer's operand prologue), plus G_l = d sdf / d(input of layer l) from the normals pass.
-#include "gemm_simt.cuh"
-#include "mlp_layout.cuh"
+#include "gemm_tc.cuh"
 #include "pointwise.cuh"
 #include "../../include/vdn_b200.h"
 
@@ -150,7 +149,6 @@ static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x
   if (e) return e;
   for (int l = 0; l < c.L; ++l) {
     Operand A = input_operand(c, b, l);
-    const float* W = packed + c.ly.off_w[l];
     const float* bias = packed + c.ly.off_b[l];
     Epilogue E;
     int ngemm = c.ly.out_dim[l];
@@ -164,7 +162,7 @@ static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x
     } else {
       E = make_epilogue(EPI_STORE, bias, b.Z[l], c.ldH);
     }
-    e = launch_gemm_nt((int)N, ngemm, c.ly.in_ld[l], A, W, c.ly.in_ld[l], E, st);
+    e = launch_gemm_nt((int)N, ngemm, c.ly.in_ld[l], A, wref(c.ly, packed, l), E, st);
     if (e) return e;
   }
   return 0;
@@ -224,7 +222,6 @@ extern "C" int vdn_sdf_normals(const int* cfg, float scale, const float* packed,
   for (int l = c.L - 2; l >= 0; --l) {
     GinRef gi = gin_of(c, packed, g, l);
     Operand A = make_operand(gi.p, gi.ld, c.ly.out_ld[l], c.ly.out_dim[l], PRO_DSIG, b.Z[l], c.ldH, gi.scale);
-    const float* WT = packed + c.ly.off_wt[l];
     Epilogue E;
     if (l > 0) {
       E = make_epilogue(EPI_STORE, nullptr, g.G[l], c.ldH);
@@ -235,7 +232,7 @@ extern "C" int vdn_sdf_normals(const int* cfg, float scale, const float* packed,
     } else {
       E = make_epilogue(EPI_STORE, nullptr, g.DE, c.ldE);
     }
-    int e = launch_gemm_nt((int)N, c.ly.in_dim[l], c.ly.out_ld[l], A, WT, c.ly.out_ld[l], E, st);
+    int e = launch_gemm_nt((int)N, c.ly.in_dim[l], c.ly.out_ld[l], A, wtref(c.ly, packed, l), E, st);
     if (e) return e;
   }
   long long tot = N * c.d_in;
@@ -309,7 +306,7 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
       E.c2 = ZG[l]; E.ldc2 = c.ldH;
       E.aux = b.Z[l]; E.ldaux = c.ldH;
       E.aux2 = gi.p; E.ldaux2 = gi.ld; E.scale2 = gi.scale;
-      e = launch_gemm_nt(M, ly.out_dim[l], ly.in_ld[l], qbar, packed + ly.off_w[l], ly.in_ld[l], E, st);
+      e = launch_gemm_nt(M, ly.out_dim[l], ly.in_ld[l], qbar, wref(ly, packed, l), E, st);
       if (e) return e;
       // Wbar_l += delta_l^T qbar_l with delta_l = softplus'(z_l) * Gin_l recomputed on the fly
       Operand delta = make_operand(gi.p, gi.ld, ly.out_ld[l], ly.out_dim[l], PRO_DSIG, b.Z[l], c.ldH, gi.scale);
@@ -349,24 +346,23 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
     if (e) return e;
     e = launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);
     if (e) return e;
-    const float* WT = packed + ly.off_wt[l];
     if (l > 0) {
       // ubar = zbar_l W_l restricted to the hidden part; epilogue -> zbar_{l-1}
       Epilogue E = make_epilogue(EPI_BWD_INJECT, nullptr, ZG[l - 1], c.ldH);
       E.aux = b.Z[l - 1]; E.ldaux = c.ldH;
       E.aux2 = have_n ? ZG[l - 1] : nullptr; E.ldaux2 = c.ldH;
       E.scale = (l == c.skip) ? kInvSqrt2 : 1.0f;
-      e = launch_gemm_nt(M, ly.out_dim[l - 1], ly.out_ld[l], zbar, WT, ly.out_ld[l], E, st);
+      e = launch_gemm_nt(M, ly.out_dim[l - 1], ly.out_ld[l], zbar, wtref(ly, packed, l), E, st);
       if (e) return e;
       if (l == c.skip && d_x) {  // embedding tail of the skip concat
         int off = ly.in_dim[l] - c.d_e;
         Epilogue E2 = make_epilogue(EPI_STORE, nullptr, ES, c.ldE);
-        e = launch_gemm_nt(M, c.d_e, ly.out_ld[l], zbar, WT + (long long)off * ly.out_ld[l], ly.out_ld[l], E2, st);
+        e = launch_gemm_nt(M, c.d_e, ly.out_ld[l], zbar, wtref(ly, packed, l, off), E2, st);
         if (e) return e;
       }
     } else if (d_x) {
       Epilogue E2 = make_epilogue(EPI_STORE, nullptr, EB, c.ldE);
-      e = launch_gemm_nt(M, c.d_e, ly.out_ld[0], zbar, WT, ly.out_ld[0], E2, st);
+      e = launch_gemm_nt(M, c.d_e, ly.out_ld[0], zbar, wtref(ly, packed, 0), E2, st);
       if (e) return e;
     }
   }

@@ -38,6 +38,26 @@ def launch_count() -> int:
     return int(_lib.load().vdn_launch_count())
 
 
+_PRECISIONS = {"fp32": 0, "tf32": 1}
+
+
+def set_precision(mode: str) -> None:
+    """'fp32': exact FFMA kernels (parity <= 1e-5); 'tf32': tcgen05 tensor-core kernels (parity <= 2e-3)."""
+    if mode not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+    check(_lib.load().vdn_set_mode(_PRECISIONS[mode]), "vdn_set_mode")
+
+
+def get_precision() -> str:
+    m = _lib.load().vdn_get_mode()
+    return [k for k, v in _PRECISIONS.items() if v == m][0]
+
+
+def tc_fault() -> int:
+    """Non-zero if a tensor-core kernel hit a barrier time-out since the library was loaded (synchronises)."""
+    return int(_lib.load().vdn_tc_fault())
+
+
 # ----------------------------------------------------------------------------------------------------
 # Packed parameters
 # ----------------------------------------------------------------------------------------------------
@@ -49,7 +69,7 @@ class PackedMLP:
     parameter's storage or version counter changes, i.e. once per optimiser step.
     """
 
-    def __init__(self, in_dims: Sequence[int], out_dims: Sequence[int], sources):
+    def __init__(self, in_dims: Sequence[int], out_dims: Sequence[int], sources, rot: Optional[Sequence[int]] = None):
         self.in_dims = [int(v) for v in in_dims]
         self.out_dims = [int(v) for v in out_dims]
         self.L = len(self.in_dims)
@@ -73,6 +93,7 @@ class PackedMLP:
             assert tot == self.out_dims[l], (l, tot, self.out_dims[l])
             rows += [srcs[0][0].shape[0], srcs[1][0].shape[0] if len(srcs) > 1 else 0]
         self._rows = int_array(rows)
+        self._rot = int_array(list(rot) if rot is not None else [0] * self.L)
         lib = _lib.load()
         L = self.L
         self.off_w = (ctypes.c_longlong * L)()
@@ -104,7 +125,7 @@ class PackedMLP:
             lib = _lib.load()
             check(lib.vdn_mlp_pack(self.L, self._in, self._out, self._src_ptrs(lambda s: s[0]),
                                    self._src_ptrs(lambda s: s[1]), self._src_ptrs(lambda s: s[2]), self._rows,
-                                   _p(buf), _stream()), "vdn_mlp_pack")
+                                   self._rot, _p(buf), _stream()), "vdn_mlp_pack")
             self._packed = buf
             self._key = key
         return self._packed
@@ -135,7 +156,7 @@ class PackedMLP:
                 db.append(gb.data_ptr() if gb is not None else 0)
         lib = _lib.load()
         check(lib.vdn_mlp_unpack_grads(self.L, self._in, self._out, self._src_ptrs(lambda s: s[0]),
-                                       self._src_ptrs(lambda s: s[1]), self._rows, _p(dpacked), ptr_array(dv),
+                                       self._src_ptrs(lambda s: s[1]), self._rows, self._rot, _p(dpacked), ptr_array(dv),
                                        ptr_array(dg), ptr_array(db), _stream()), "vdn_mlp_unpack_grads")
         return grads
 
@@ -377,7 +398,10 @@ class NerfHandle:
         if L <= 0:
             raise _lib.VdnLibraryError(f"unsupported NeRF configuration {self.cfg_list}")
         self.L = L
-        self.mlp = PackedMLP(list(ind[:L]), list(outd[:L]), sources_fn())
+        rot = [0] * L
+        if skip >= 0:
+            rot[skip + 1] = int(ind[0])      # skip layer input is stored as [hidden | embedding]
+        self.mlp = PackedMLP(list(ind[:L]), list(outd[:L]), sources_fn(), rot=rot)
 
 
 class _NerfFn(torch.autograd.Function):
