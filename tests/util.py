@@ -43,6 +43,14 @@ def relerr(got, want):
     return (got - want).abs().max().item() / (den if den > 0 else 1.0)
 
 
+def relerr_l2(got, want):
+    """||got - want||_2 / ||want||_2."""
+    got = torch.as_tensor(got).detach().double().cpu()
+    want = torch.as_tensor(want).detach().double().cpu()
+    den = want.norm().item()
+    return (got - want).norm().item() / (den if den > 0 else 1.0)
+
+
 def t(a, device=None):
     return torch.from_numpy(np.asarray(a)).to(device) if device else torch.from_numpy(np.asarray(a))
 

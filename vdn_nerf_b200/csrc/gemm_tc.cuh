@@ -135,33 +135,39 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
   bool ok = true;
 
   if (warp < 4) {
-    // ---- A producers: one row per thread --------------------------------------------------------
-    const int row = tid;
-    const int m = m0 + row;
-    const bool row_ok = m < M;
+    // ---- A producers: warp w owns rows [32w, 32w+32); per instruction the 32 lanes cover 4 rows x 8 chunks of
+    // 16 bytes, i.e. four full 128-byte row segments (coalesced global loads, conflict-free swizzled stores) ----
+    const int chunk = lane & 7;
+    int rows[8];
+    bool rok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      rows[i] = warp * 32 + i * 4 + (lane >> 3);
+      rok[i] = (m0 + rows[i]) < M;
+    }
     RawLoad raw[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) raw[c] = operand_load(A, m, c * 4, row_ok);
-    const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+    for (int i = 0; i < 8; ++i) raw[i] = operand_load(A, m0 + rows[i], chunk * 4, rok[i]);
     for (int kb = 0; kb < nkb && ok; ++kb) {
       const int s = kb & 1, ph = (kb >> 1) & 1;
       float4 v[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        v[c] = operand_finish(A, raw[c], kb * 32 + c * 4, row_ok);
-        v[c] = make_float4(to_tf32(v[c].x), to_tf32(v[c].y), to_tf32(v[c].z), to_tf32(v[c].w));
+      for (int i = 0; i < 8; ++i) {
+        v[i] = operand_finish(A, raw[i], kb * 32 + chunk * 4, rok[i]);
+        v[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
       }
       if (kb + 1 < nkb) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) raw[c] = operand_load(A, m, (kb + 1) * 32 + c * 4, row_ok);
+        for (int i = 0; i < 8; ++i) raw[i] = operand_load(A, m0 + rows[i], (kb + 1) * 32 + chunk * 4, rok[i]);
       }
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-      const uint32_t base = sA(s) + row_off;
+      const uint32_t base = sA(s);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t addr = base + (uint32_t)((c ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[c].x), "f"(v[c].y), "f"(v[c].z),
-                     "f"(v[c].w)
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t r = (uint32_t)rows[i];
+        const uint32_t addr = base + (r >> 3) * 1024u + (r & 7u) * 128u + (((uint32_t)chunk ^ (r & 7u)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z),
+                     "f"(v[i].w)
                      : "memory");
       }
       fence_proxy_async();
@@ -192,23 +198,45 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     }
   }
   // ---- epilogue: all eight warps drain the accumulator ------------------------------------------------
+  // TMEM hands every lane one row (32 consecutive columns per load).  Each warp transposes its 32x32 block
+  // through a private 4 KB staging tile (the pipeline stages are idle by now) so that the epilogue's global
+  // loads / stores again cover four full 128-byte row segments per instruction.
   __syncwarp();
-  ok = mbar_wait(smem_u32(&bar_acc), 0) && ok;
+  {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(smem_u32(&bar_acc), 0)) {
+      if (warp != 4) __nanosleep(256);
+      if (++spins > (1u << 24)) { ok = false; break; }
+    }
+  }
   tc_fence_after();
   if (ok) {
     const int q = warp & 3, half = warp >> 2;
-    const int m = m0 + q * 32 + lane;
     const int nch = (n_cta + 31) >> 5;
+    const uint32_t stg = smem0 + (uint32_t)warp * 4096u;
+    const int g = lane & 7;
     for (int ch = half; ch < nch; ch += 2) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
       tmem_ld_wait();
-      if (m < M) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          epi_store4(E, vec_ok != 0, m, n_base + ch * 32 + g * 4,
-                     make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]), N);
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = stg + (uint32_t)lane * 128u + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * c]), "f"(v[4 * c + 1]),
+                     "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                     : "memory");
       }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t r = (uint32_t)(i * 4 + (lane >> 3));
+        const uint32_t addr = stg + r * 128u + (((uint32_t)g ^ (r & 7u)) << 4);
+        float4 x;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+        const int m = m0 + q * 32 + (int)r;
+        if (m < M) epi_store4(E, vec_ok != 0, m, n_base + ch * 32 + g * 4, x, N);
+      }
+      __syncwarp();
     }
   } else if (fault) {
     *fault = 1;
