@@ -41,6 +41,10 @@ int vdn_set_mode(int mode);
 int vdn_get_mode(void);
 int vdn_tc_fault(void);
 
+/* Debug aid: when device_buf (256 int64, device memory) is non-null, CTA 0 of every tcgen05 GEMM launch records
+ * clock64() time stamps of its pipeline events there (csrc/gemm_tc.cuh).  Pass null to switch it off. */
+int vdn_debug_timeline(long long* device_buf);
+
 /* Measurement aid for bench.py: when enabled, CUDA events bracket every launch of a kernel family on its
  * stream (0 = gemm_nt, 1 = weight-gradient gemm_tn + reduce, 2 = tcgen05 chain kernels); vdn_prof_read sums the
  * recorded durations (ms), the number of spans and the executed FLOPs.  Enabling/disabling clears the record. */

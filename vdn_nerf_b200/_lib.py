@@ -29,6 +29,7 @@ SIGNATURES = {
     "vdn_set_mode": (I, [I]),
     "vdn_get_mode": (I, []),
     "vdn_tc_fault": (I, []),
+    "vdn_debug_timeline": (I, [P]),
     "vdn_sdf_layer_dims": (I, [P, P, P]),
     "vdn_sdf_blob_floats": (L, [P, L, I]),
     "vdn_sdf_blobg_floats": (L, [P, L]),

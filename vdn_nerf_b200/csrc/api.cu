@@ -9,6 +9,7 @@ namespace vdn {
 std::atomic<long long> g_launches{0};
 int g_mode = 0;
 int* g_tc_fault = nullptr;
+long long* g_tc_dbg = nullptr;
 
 // ---- optional profiling: CUDA events around kernel families, summed on read ----------------------------
 static bool g_prof_on = false;
@@ -56,6 +57,11 @@ extern "C" int vdn_tc_fault(void) {
   int h = 0;
   if (cudaMemcpy(&h, g_tc_fault, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return h;
+}
+
+extern "C" int vdn_debug_timeline(long long* device_buf) {
+  g_tc_dbg = device_buf;
+  return 0;
 }
 
 extern "C" int vdn_prof_enable(int on) {

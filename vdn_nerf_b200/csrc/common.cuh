@@ -54,6 +54,23 @@ __device__ __forceinline__ float softplus100_d2(float z) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// MUFU-based variants for the tensor-core mode, whose operands are rounded to tf32 (2^-11) anyway: absolute error
+// of softplus ~1e-8, relative error of its derivatives ~1e-6.
+__device__ __forceinline__ float softplus100_fast(float z) {
+  float t = z * kSoftplusBeta;
+  return t > kSoftplusThreshold ? z : __logf(1.0f + __expf(t)) * (1.0f / kSoftplusBeta);
+}
+__device__ __forceinline__ float softplus100_d1_fast(float z) {
+  float t = z * kSoftplusBeta;
+  return t > kSoftplusThreshold ? 1.0f : __fdividef(1.0f, 1.0f + __expf(-t));
+}
+__device__ __forceinline__ float softplus100_d2_fast(float z) {
+  float t = z * kSoftplusBeta;
+  if (t > kSoftplusThreshold) return 0.0f;
+  float s = __fdividef(1.0f, 1.0f + __expf(-t));
+  return kSoftplusBeta * s * (1.0f - s);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

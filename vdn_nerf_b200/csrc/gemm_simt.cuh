@@ -64,6 +64,27 @@ __device__ __forceinline__ float pro_apply(int kind, float a, float b, float sca
   }
 }
 
+__device__ __forceinline__ float pro_apply_fast(int kind, float a, float b, float scale) {
+  switch (kind) {
+    case PRO_SOFTPLUS: return softplus100_fast(a);
+    case PRO_DSIG: return softplus100_d1_fast(b) * a * scale;
+    case PRO_DSIGMOID: return a * b * (1.0f - b);
+    case PRO_RELUMASK: return b > 0.0f ? a : 0.0f;
+    default: return a;
+  }
+}
+
+// tensor-core mode: same as operand_finish with the MUFU-based activations
+__device__ __forceinline__ float4 operand_finish_fast(const Operand& o, const RawLoad& r, int c, bool row_ok) {
+  float4 v;
+  if (!row_ok || c >= o.width) return make_float4(0.f, 0.f, 0.f, 0.f);
+  v.x = (c + 0 < o.kvalid) ? pro_apply_fast(o.kind, r.a.x, r.b.x, o.scale) : 0.f;
+  v.y = (c + 1 < o.kvalid) ? pro_apply_fast(o.kind, r.a.y, r.b.y, o.scale) : 0.f;
+  v.z = (c + 2 < o.kvalid) ? pro_apply_fast(o.kind, r.a.z, r.b.z, o.scale) : 0.f;
+  v.w = (c + 3 < o.kvalid) ? pro_apply_fast(o.kind, r.a.w, r.b.w, o.scale) : 0.f;
+  return v;
+}
+
 __device__ __forceinline__ float4 operand_finish(const Operand& o, const RawLoad& r, int c, bool row_ok) {
   float4 v;
   if (!row_ok || c >= o.width) return make_float4(0.f, 0.f, 0.f, 0.f);

@@ -47,26 +47,26 @@ __device__ __forceinline__ void epi_store4(const Epilogue& e, bool vec_ok, int m
       break;
     case EPI_SOFTPLUS:
       st4(e.c + mm * e.ldc + e.coff + n,
-          make_float4(softplus100(v.x), softplus100(v.y), softplus100(v.z), softplus100(v.w)));
+          make_float4(softplus100_fast(v.x), softplus100_fast(v.y), softplus100_fast(v.z), softplus100_fast(v.w)));
       break;
     case EPI_SDF_SKIP:
       if (e.c) st4(e.c + mm * e.ldc + n, v);
-      st4(e.c2 + mm * e.ldc2 + n, make_float4(softplus100(v.x) * e.scale, softplus100(v.y) * e.scale,
-                                              softplus100(v.z) * e.scale, softplus100(v.w) * e.scale));
+      st4(e.c2 + mm * e.ldc2 + n, make_float4(softplus100_fast(v.x) * e.scale, softplus100_fast(v.y) * e.scale,
+                                              softplus100_fast(v.z) * e.scale, softplus100_fast(v.w) * e.scale));
       break;
     case EPI_GRAD_DUAL: {
       const float4 z = ld4(e.aux + mm * e.ldaux + n);
       float4 g = ld4(e.aux2 + mm * e.ldaux2 + n);
       g.x *= e.scale2; g.y *= e.scale2; g.z *= e.scale2; g.w *= e.scale2;
-      st4(e.c + mm * e.ldc + n, make_float4(softplus100_d1(z.x) * v.x * e.scale, softplus100_d1(z.y) * v.y * e.scale,
-                                            softplus100_d1(z.z) * v.z * e.scale, softplus100_d1(z.w) * v.w * e.scale));
-      st4(e.c2 + mm * e.ldc2 + n, make_float4(softplus100_d2(z.x) * g.x * v.x, softplus100_d2(z.y) * g.y * v.y,
-                                              softplus100_d2(z.z) * g.z * v.z, softplus100_d2(z.w) * g.w * v.w));
+      st4(e.c + mm * e.ldc + n, make_float4(softplus100_d1_fast(z.x) * v.x * e.scale, softplus100_d1_fast(z.y) * v.y * e.scale,
+                                            softplus100_d1_fast(z.z) * v.z * e.scale, softplus100_d1_fast(z.w) * v.w * e.scale));
+      st4(e.c2 + mm * e.ldc2 + n, make_float4(softplus100_d2_fast(z.x) * g.x * v.x, softplus100_d2_fast(z.y) * g.y * v.y,
+                                              softplus100_d2_fast(z.z) * g.z * v.z, softplus100_d2_fast(z.w) * g.w * v.w));
     } break;
     case EPI_BWD_INJECT: {
       const float4 z = ld4(e.aux + mm * e.ldaux + n);
-      float4 r = make_float4(softplus100_d1(z.x) * v.x * e.scale, softplus100_d1(z.y) * v.y * e.scale,
-                             softplus100_d1(z.z) * v.z * e.scale, softplus100_d1(z.w) * v.w * e.scale);
+      float4 r = make_float4(softplus100_d1_fast(z.x) * v.x * e.scale, softplus100_d1_fast(z.y) * v.y * e.scale,
+                             softplus100_d1_fast(z.z) * v.z * e.scale, softplus100_d1_fast(z.w) * v.w * e.scale);
       if (e.aux2) {
         const float4 q = ld4(e.aux2 + mm * e.ldaux2 + n);
         r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
@@ -102,8 +102,12 @@ inline bool epilogue_vec_ok(const Epilogue& e) {
 
 static __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bimg, int img_rows, int row0,
-                  Epilogue E, int vec_ok, int* __restrict__ fault) {
+                  Epilogue E, int vec_ok, int* __restrict__ fault, long long* __restrict__ dbg) {
   using namespace tc;
+  // optional timeline of CTA 0 (debug): dbg[role*64 + event] = clock64()
+  const bool rec = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define VDN_TL(role, ev) do { if (rec) dbg[(role) * 64 + (ev)] = clock64(); } while (0)
+  if (threadIdx.x == 0) VDN_TL(0, 0);
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc;
   __shared__ uint32_t tmem_base_s;
@@ -133,6 +137,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   bool ok = true;
+  if (threadIdx.x == 0) VDN_TL(0, 1);
 
   if (warp < 4) {
     // ---- A producers: warp w owns rows [32w, 32w+32); per instruction the 32 lanes cover 4 rows x 8 chunks of
@@ -153,14 +158,16 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        v[i] = operand_finish(A, raw[i], kb * 32 + chunk * 4, rok[i]);
+        v[i] = operand_finish_fast(A, raw[i], kb * 32 + chunk * 4, rok[i]);
         v[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
       }
       if (kb + 1 < nkb) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) raw[i] = operand_load(A, m0 + rows[i], (kb + 1) * 32 + chunk * 4, rok[i]);
       }
+      if (tid == 0) VDN_TL(1, 3 * kb);
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+      if (tid == 0) VDN_TL(1, 3 * kb + 1);
       const uint32_t base = sA(s);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -172,13 +179,16 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bar_full[s]));
+      if (tid == 0) VDN_TL(1, 3 * kb + 2);
     }
   } else if (tid == 128) {
     // ---- MMA issuer ------------------------------------------------------------------------------
     const uint32_t idesc = umma_idesc_tf32(128, (uint32_t)n_mma);
     for (int kb = 0; kb < nkb && ok; ++kb) {
       const int s = kb & 1, ph = (kb >> 1) & 1;
+      VDN_TL(2, 2 * kb);
       ok = mbar_wait(smem_u32(&bar_full[s]), ph);
+      VDN_TL(2, 2 * kb + 1);
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
@@ -193,6 +203,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     for (int kb = 0; kb < nkb && ok; ++kb) {
       const int s = kb & 1, ph = (kb >> 1) & 1;
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+      VDN_TL(3, kb);
       mbar_arrive_expect_tx(smem_u32(&bar_full[s]), bytes);
       bulk_g2s(sB(s), Bimg + ((size_t)kb * img_rows + row0 + n_base) * 32, bytes, smem_u32(&bar_full[s]));
     }
@@ -210,6 +221,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     }
   }
   tc_fence_after();
+  if (threadIdx.x == 0) VDN_TL(0, 2);
   if (ok) {
     const int q = warp & 3, half = warp >> 2;
     const int nch = (n_cta + 31) >> 5;
@@ -241,9 +253,12 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
   } else if (fault) {
     *fault = 1;
   }
+  if (threadIdx.x == 0) VDN_TL(0, 3);
   tc_fence_before();
   __syncthreads();
   if (warp == 6) tmem_dealloc(tmem_base, ncols);
+  if (threadIdx.x == 0) VDN_TL(0, 4);
+#undef VDN_TL
 }
 
 // Operand of the weight side: plain row-major pointer for the FFMA kernels, swizzled tile image for tcgen05.
@@ -266,6 +281,7 @@ inline WeightRef wtref(const MlpLayout& ly, const float* packed, int l, int row0
 
 extern int g_mode;       // 0: exact fp32 (FFMA kernels), 1: tf32 tensor cores (tcgen05); set by vdn_set_mode
 extern int* g_tc_fault;  // device flag raised by a timed-out barrier wait in a tcgen05 kernel
+extern long long* g_tc_dbg;  // optional device buffer (256 int64) receiving CTA 0's timeline (vdn_debug_timeline)
 
 static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const WeightRef& B, const Epilogue& E,
                              cudaStream_t st) {
@@ -282,7 +298,7 @@ static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const
   dim3 grid((M + TC_BM - 1) / TC_BM, (N + 255) / 256);
   prof_begin(PROF_TC, st, 2.0 * M * N * K);
   VDN_LAUNCH(gemm_nt_tc_kernel, grid, TC_THREADS, smem, st, M, N, nkb, A, B.img, B.img_rows, B.row0, E,
-             epilogue_vec_ok(E) ? 1 : 0, g_tc_fault);
+             epilogue_vec_ok(E) ? 1 : 0, g_tc_fault, g_tc_dbg);
   prof_end(PROF_TC, st);
   return (int)cudaGetLastError();
 }
