@@ -4,11 +4,14 @@
 //   gemm_nt_tc : C[M,N] = epi( pro(A)[M,K] * W[N,K]^T + bias )
 //
 // One CTA owns a 128-row tile and up to 256 output columns; two CTAs are co-resident per SM so one tile's
-// epilogue overlaps the other's MMAs.  Warp roles: warps 0-3 transform the A operand (global -> registers ->
-// prologue -> tf32 round -> SWIZZLE_128B shared-memory image, one row per thread), one thread streams the
-// pre-swizzled weight tiles with cp.async.bulk (TMA engine), one thread issues tcgen05.mma kind::tf32 into a
-// TMEM accumulator, then all eight warps drain TMEM with tcgen05.ld and run the epilogue.  A 2-stage mbarrier
-// ring (full / empty) connects them; every wait is bounded and raises a device fault flag instead of hanging.
+// epilogue overlaps the other's MMAs.  Warp roles: warps 0-3 transform the A operand (coalesced global loads ->
+// prologue -> tf32 round -> SWIZZLE_128B shared-memory image), one thread streams the pre-swizzled weight tiles
+// with cp.async.bulk (TMA engine), one thread issues tcgen05.mma kind::tf32 into a TMEM accumulator, then all
+// eight warps drain TMEM with tcgen05.ld, transpose through shared memory and run the epilogue with coalesced
+// global accesses.  A 2-stage mbarrier ring (full / empty) connects the roles; every wait is bounded and raises a
+// device fault flag instead of hanging.  The prologue / epilogue kind is switched once per tile-row group, outside
+// the per-element loops, so the executed instruction footprint stays small (the first version, with the switch
+// inlined per element, was instruction-fetch bound).
 #pragma once
 #include "gemm_simt.cuh"
 #include "mlp_layout.cuh"
@@ -23,63 +26,131 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+__device__ __forceinline__ float4 f4_map_sp(float4 a) {
+  return make_float4(softplus100_fast(a.x), softplus100_fast(a.y), softplus100_fast(a.z), softplus100_fast(a.w));
+}
+__device__ __forceinline__ float4 f4_map_sp1(float4 a) {
+  return make_float4(softplus100_d1_fast(a.x), softplus100_d1_fast(a.y), softplus100_d1_fast(a.z),
+                     softplus100_d1_fast(a.w));
+}
+__device__ __forceinline__ float4 f4_map_sp2(float4 a) {
+  return make_float4(softplus100_d2_fast(a.x), softplus100_d2_fast(a.y), softplus100_d2_fast(a.z),
+                     softplus100_d2_fast(a.w));
+}
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// Vector (4 consecutive columns) form of epi_store for the elementwise epilogues; scalar fallback otherwise.
-__device__ __forceinline__ void epi_store4(const Epilogue& e, bool vec_ok, int m, int n, float4 v, int N) {
-  if (!vec_ok || n + 3 >= N) {
-    const float a[4] = {v.x, v.y, v.z, v.w};
+// Prologue of 8 float4 groups (8 rows, same 4 columns): kind switched once.
+__device__ __forceinline__ void tc_prologue8(const Operand& A, const RawLoad (&raw)[8], float4 (&v)[8]) {
+  switch (A.kind) {
+    case PRO_SOFTPLUS:
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (n + j < N) epi_store(e, m, n + j, a[j]);
-    return;
+      for (int i = 0; i < 8; ++i) v[i] = f4_map_sp(raw[i].a);
+      break;
+    case PRO_DSIG:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = f4_scale(f4_mul(f4_map_sp1(raw[i].b), raw[i].a), A.scale);
+      break;
+    case PRO_DSIGMOID:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = raw[i].b;
+        v[i] = f4_mul(raw[i].a, make_float4(b.x * (1.f - b.x), b.y * (1.f - b.y), b.z * (1.f - b.z), b.w * (1.f - b.w)));
+      }
+      break;
+    case PRO_RELUMASK:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = raw[i].a, b = raw[i].b;
+        v[i] = make_float4(b.x > 0.f ? a.x : 0.f, b.y > 0.f ? a.y : 0.f, b.z > 0.f ? a.z : 0.f, b.w > 0.f ? a.w : 0.f);
+      }
+      break;
+    default:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = raw[i].a;
+      break;
   }
-  if (e.bias) {
-    const float4 b = *reinterpret_cast<const float4*>(e.bias + n);
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-  }
-  const size_t mm = (size_t)m;
-  auto st4 = [](float* p, float4 x) { *reinterpret_cast<float4*>(p) = x; };
+}
+
+// Slow path of the epilogue (ragged column ranges, unaligned or splitting epilogues): out of line.
+static __device__ __noinline__ void tc_epi_scalar4(const Epilogue& e, int m, int n, float4 v, int N) {
+  const float a[4] = {v.x, v.y, v.z, v.w};
+  for (int j = 0; j < 4; ++j)
+    if (n + j < N) epi_store(e, m, n + j, a[j]);
+}
+
+// Vector epilogue for 8 rows x 4 columns (same columns for all rows); kind switched once.
+__device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M, int n, float4 (&x)[8]) {
+  // row of group i is mbase + 4 i
+#define m_(i) (mbase + 4 * (i))
+#define mok_(i) (mbase + 4 * (i) < M)
+  auto st4 = [](float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; };
   auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+  if (e.bias) {
+    const float4 b = ld4(e.bias + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = f4_add(x[i], b);
+  }
   switch (e.kind) {
-    case EPI_STORE: st4(e.c + mm * e.ldc + e.coff + n, v); break;
+    case EPI_STORE:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mok_(i)) st4(e.c + (size_t)m_(i) * e.ldc + e.coff + n, x[i]);
+      break;
     case EPI_RELU:
-      st4(e.c + mm * e.ldc + e.coff + n, make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)));
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mok_(i))
+          st4(e.c + (size_t)m_(i) * e.ldc + e.coff + n,
+              make_float4(fmaxf(x[i].x, 0.f), fmaxf(x[i].y, 0.f), fmaxf(x[i].z, 0.f), fmaxf(x[i].w, 0.f)));
       break;
     case EPI_SOFTPLUS:
-      st4(e.c + mm * e.ldc + e.coff + n,
-          make_float4(softplus100_fast(v.x), softplus100_fast(v.y), softplus100_fast(v.z), softplus100_fast(v.w)));
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mok_(i)) st4(e.c + (size_t)m_(i) * e.ldc + e.coff + n, f4_map_sp(x[i]));
       break;
     case EPI_SDF_SKIP:
-      if (e.c) st4(e.c + mm * e.ldc + n, v);
-      st4(e.c2 + mm * e.ldc2 + n, make_float4(softplus100_fast(v.x) * e.scale, softplus100_fast(v.y) * e.scale,
-                                              softplus100_fast(v.z) * e.scale, softplus100_fast(v.w) * e.scale));
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mok_(i)) {
+          if (e.c) st4(e.c + (size_t)m_(i) * e.ldc + n, x[i]);
+          st4(e.c2 + (size_t)m_(i) * e.ldc2 + n, f4_scale(f4_map_sp(x[i]), e.scale));
+        }
       break;
-    case EPI_GRAD_DUAL: {
-      const float4 z = ld4(e.aux + mm * e.ldaux + n);
-      float4 g = ld4(e.aux2 + mm * e.ldaux2 + n);
-      g.x *= e.scale2; g.y *= e.scale2; g.z *= e.scale2; g.w *= e.scale2;
-      st4(e.c + mm * e.ldc + n, make_float4(softplus100_d1_fast(z.x) * v.x * e.scale, softplus100_d1_fast(z.y) * v.y * e.scale,
-                                            softplus100_d1_fast(z.z) * v.z * e.scale, softplus100_d1_fast(z.w) * v.w * e.scale));
-      st4(e.c2 + mm * e.ldc2 + n, make_float4(softplus100_d2_fast(z.x) * g.x * v.x, softplus100_d2_fast(z.y) * g.y * v.y,
-                                              softplus100_d2_fast(z.z) * g.z * v.z, softplus100_d2_fast(z.w) * g.w * v.w));
-    } break;
-    case EPI_BWD_INJECT: {
-      const float4 z = ld4(e.aux + mm * e.ldaux + n);
-      float4 r = make_float4(softplus100_d1_fast(z.x) * v.x * e.scale, softplus100_d1_fast(z.y) * v.y * e.scale,
-                             softplus100_d1_fast(z.z) * v.z * e.scale, softplus100_d1_fast(z.w) * v.w * e.scale);
-      if (e.aux2) {
-        const float4 q = ld4(e.aux2 + mm * e.ldaux2 + n);
-        r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
-      }
-      st4(e.c + mm * e.ldc + n, r);
-    } break;
-    case EPI_RELU_MASK: {
-      const float4 h = ld4(e.aux + mm * e.ldaux + e.split + n);
-      st4(e.c + mm * e.ldc + n, make_float4(h.x > 0.f ? v.x : 0.f, h.y > 0.f ? v.y : 0.f, h.z > 0.f ? v.z : 0.f,
-                                            h.w > 0.f ? v.w : 0.f));
-    } break;
+    case EPI_GRAD_DUAL:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mok_(i)) {
+          const float4 z = ld4(e.aux + (size_t)m_(i) * e.ldaux + n);
+          const float4 g = f4_scale(ld4(e.aux2 + (size_t)m_(i) * e.ldaux2 + n), e.scale2);
+          st4(e.c + (size_t)m_(i) * e.ldc + n, f4_scale(f4_mul(f4_map_sp1(z), x[i]), e.scale));
+          st4(e.c2 + (size_t)m_(i) * e.ldc2 + n, f4_mul(f4_mul(f4_map_sp2(z), g), x[i]));
+        }
+      break;
+    case EPI_BWD_INJECT:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mok_(i)) {
+          const float4 z = ld4(e.aux + (size_t)m_(i) * e.ldaux + n);
+          float4 r = f4_scale(f4_mul(f4_map_sp1(z), x[i]), e.scale);
+          if (e.aux2) r = f4_add(r, ld4(e.aux2 + (size_t)m_(i) * e.ldaux2 + n));
+          st4(e.c + (size_t)m_(i) * e.ldc + n, r);
+        }
+      break;
+    case EPI_RELU_MASK:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mok_(i)) {
+          const float4 h = ld4(e.aux + (size_t)m_(i) * e.ldaux + e.split + n);
+          st4(e.c + (size_t)m_(i) * e.ldc + n, make_float4(h.x > 0.f ? x[i].x : 0.f, h.y > 0.f ? x[i].y : 0.f,
+                                                         h.z > 0.f ? x[i].z : 0.f, h.w > 0.f ? x[i].w : 0.f));
+        }
+      break;
     default: break;
   }
+#undef m_
+#undef mok_
 }
 
 inline bool epilogue_vec_ok(const Epilogue& e) {
@@ -119,9 +190,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
   uint32_t ncols = 32;
   while (ncols < (uint32_t)n_mma) ncols <<= 1;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = 16384u + (uint32_t)n_mma * 128u;
-  auto sA = [&](int s) { return smem0 + (uint32_t)s * ((stage_bytes + 1023u) & ~1023u); };
-  auto sB = [&](int s) { return sA(s) + 16384u; };
+  const uint32_t stage_stride = (16384u + (uint32_t)n_mma * 128u + 1023u) & ~1023u;
 
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -143,40 +212,58 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     // ---- A producers: warp w owns rows [32w, 32w+32); per instruction the 32 lanes cover 4 rows x 8 chunks of
     // 16 bytes, i.e. four full 128-byte row segments (coalesced global loads, conflict-free swizzled stores) ----
     const int chunk = lane & 7;
-    int rows[8];
-    bool rok[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      rows[i] = warp * 32 + i * 4 + (lane >> 3);
-      rok[i] = (m0 + rows[i]) < M;
-    }
+    const int rbase = warp * 32 + (lane >> 3);                   // row of group i: rbase + 4 i
+    const uint32_t r7e = (uint32_t)(lane >> 3), r7o = r7e + 4u;   // (row & 7) for even / odd i
+    const uint32_t soff_e = (uint32_t)(warp * 4) * 1024u + r7e * 128u + (((uint32_t)chunk ^ r7e) << 4);
+    const uint32_t soff_o = (uint32_t)(warp * 4) * 1024u + r7o * 128u + (((uint32_t)chunk ^ r7o) << 4);
+    const bool two = A.kind >= PRO_DSIG;
+    const float* pa0 = A.p + (size_t)(m0 + rbase) * A.ld + chunk * 4;
+    const float* pb0 = two ? A.p2 + (size_t)(m0 + rbase) * A.ld2 + chunk * 4 : nullptr;
+    const size_t stepa = (size_t)4 * A.ld, stepb = (size_t)4 * A.ld2;
+    const int mlim = M - m0 - rbase;                              // group i is a valid row iff 4 i < mlim
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     RawLoad raw[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) raw[i] = operand_load(A, m0 + rows[i], chunk * 4, rok[i]);
-    for (int kb = 0; kb < nkb && ok; ++kb) {
-      const int s = kb & 1, ph = (kb >> 1) & 1;
-      float4 v[8];
+    auto gload = [&](int kb) {
+      const int col = kb * 32 + chunk * 4;
+      const bool cok = col < A.width;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        v[i] = operand_finish_fast(A, raw[i], kb * 32 + chunk * 4, rok[i]);
+        const bool p = cok && (4 * i < mlim);
+        raw[i].a = p ? *reinterpret_cast<const float4*>(pa0 + i * stepa + kb * 32) : zero4;
+        raw[i].b = (p && two) ? *reinterpret_cast<const float4*>(pb0 + i * stepb + kb * 32) : zero4;
+      }
+    };
+    gload(0);
+    for (int kb = 0; kb < nkb && ok; ++kb) {
+      const int s = kb & 1, ph = (kb >> 1) & 1;
+      const int col = kb * 32 + chunk * 4;
+      float4 v[8];
+      tc_prologue8(A, raw, v);
+      if (col + 3 >= A.kvalid || col >= A.width) {  // ragged K edge: zero the columns beyond the logical extent
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (col + 0 >= A.kvalid) v[i].x = 0.f;
+          if (col + 1 >= A.kvalid) v[i].y = 0.f;
+          if (col + 2 >= A.kvalid) v[i].z = 0.f;
+          if (col + 3 >= A.kvalid) v[i].w = 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!(4 * i < mlim)) v[i] = zero4;
         v[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
       }
-      if (kb + 1 < nkb) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) raw[i] = operand_load(A, m0 + rows[i], (kb + 1) * 32 + chunk * 4, rok[i]);
-      }
+      if (kb + 1 < nkb) gload(kb + 1);
       if (tid == 0) VDN_TL(1, 3 * kb);
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
       if (tid == 0) VDN_TL(1, 3 * kb + 1);
-      const uint32_t base = sA(s);
+      const uint32_t base = smem0 + (uint32_t)s * stage_stride;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t r = (uint32_t)rows[i];
-        const uint32_t addr = base + (r >> 3) * 1024u + (r & 7u) * 128u + (((uint32_t)chunk ^ (r & 7u)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z),
-                     "f"(v[i].w)
+      for (int i = 0; i < 8; ++i)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((i & 1) ? soff_o : soff_e) +
+                                                                     (uint32_t)(i >> 1) * 1024u),
+                     "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
                      : "memory");
-      }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bar_full[s]));
       if (tid == 0) VDN_TL(1, 3 * kb + 2);
@@ -190,10 +277,10 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       ok = mbar_wait(smem_u32(&bar_full[s]), ph);
       VDN_TL(2, 2 * kb + 1);
       tc_fence_after();
+      const uint32_t a0 = smem0 + (uint32_t)s * stage_stride, b0 = a0 + 16384u;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        umma_tf32(tmem_base, umma_desc_sw128(sA(s) + ks * 32), umma_desc_sw128(sB(s) + ks * 32), idesc,
-                  (kb | ks) ? 1u : 0u);
+        umma_tf32(tmem_base, umma_desc_sw128(a0 + ks * 32), umma_desc_sw128(b0 + ks * 32), idesc, (kb | ks) ? 1u : 0u);
       umma_commit(smem_u32(&bar_empty[s]));
     }
     umma_commit(smem_u32(&bar_acc));
@@ -205,7 +292,8 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
       VDN_TL(3, kb);
       mbar_arrive_expect_tx(smem_u32(&bar_full[s]), bytes);
-      bulk_g2s(sB(s), Bimg + ((size_t)kb * img_rows + row0 + n_base) * 32, bytes, smem_u32(&bar_full[s]));
+      bulk_g2s(smem0 + (uint32_t)s * stage_stride + 16384u, Bimg + ((size_t)kb * img_rows + row0 + n_base) * 32, bytes,
+               smem_u32(&bar_full[s]));
     }
   }
   // ---- epilogue: all eight warps drain the accumulator ------------------------------------------------
@@ -216,7 +304,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
   {
     uint32_t spins = 0;
     while (!mbar_try_wait(smem_u32(&bar_acc), 0)) {
-      if (warp != 4) __nanosleep(256);
+      if (warp != 4) __nanosleep(200);
       if (++spins > (1u << 24)) { ok = false; break; }
     }
   }
@@ -227,28 +315,35 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     const int nch = (n_cta + 31) >> 5;
     const uint32_t stg = smem0 + (uint32_t)warp * 4096u;
     const int g = lane & 7;
+    const int mbase = m0 + q * 32 + (lane >> 3);                  // row of group i: mbase + 4 i
+    const uint32_t e7e = (uint32_t)(lane >> 3), e7o = e7e + 4u;
+    const uint32_t roff_e = e7e * 128u + (((uint32_t)g ^ e7e) << 4);
+    const uint32_t roff_o = e7o * 128u + (((uint32_t)g ^ e7o) << 4);
+    const uint32_t woff = (uint32_t)lane * 128u;
     for (int ch = half; ch < nch; ch += 2) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t addr = stg + (uint32_t)lane * 128u + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * c]), "f"(v[4 * c + 1]),
-                     "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + woff + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4)),
+                     "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
                      : "memory");
-      }
       __syncwarp();
+      float4 x[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t r = (uint32_t)(i * 4 + (lane >> 3));
-        const uint32_t addr = stg + r * 128u + (((uint32_t)g ^ (r & 7u)) << 4);
-        float4 x;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
-        const int m = m0 + q * 32 + (int)r;
-        if (m < M) epi_store4(E, vec_ok != 0, m, n_base + ch * 32 + g * 4, x, N);
-      }
+      for (int i = 0; i < 8; ++i)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                     : "r"(stg + ((i & 1) ? roff_o : roff_e) + (uint32_t)(i >> 1) * 1024u));
       __syncwarp();
+      const int n = n_base + ch * 32 + g * 4;
+      if (vec_ok && n + 3 < N) {
+        tc_epilogue8(E, mbase, M, n, x);
+      } else if (n < N) {
+        for (int i = 0; i < 8; ++i)
+          if (mbase + 4 * i < M) tc_epi_scalar4(E, mbase + 4 * i, n, x[i], N);
+      }
     }
   } else if (fault) {
     *fault = 1;
@@ -279,12 +374,12 @@ inline WeightRef wtref(const MlpLayout& ly, const float* packed, int l, int row0
                    ly.in_ld[l], row0};
 }
 
-extern int g_mode;       // 0: exact fp32 (FFMA kernels), 1: tf32 tensor cores (tcgen05); set by vdn_set_mode
-extern int* g_tc_fault;  // device flag raised by a timed-out barrier wait in a tcgen05 kernel
+extern int g_mode;           // 0: exact fp32 (FFMA kernels), 1: tf32 tensor cores (tcgen05); set by vdn_set_mode
+extern int* g_tc_fault;      // device flag raised by a timed-out barrier wait in a tcgen05 kernel
 extern long long* g_tc_dbg;  // optional device buffer (256 int64) receiving CTA 0's timeline (vdn_debug_timeline)
 
 static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const WeightRef& B, const Epilogue& E,
-                             cudaStream_t st) {
+                                    cudaStream_t st) {
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int n_mma_max = ((N < 256 ? N : 256) + 15) & ~15;
   const size_t stage = ((size_t)16384 + (size_t)n_mma_max * 128 + 1023) & ~(size_t)1023;
