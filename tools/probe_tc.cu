@@ -98,6 +98,118 @@ __global__ void __launch_bounds__(128) probe_gemm(const float* __restrict__ A, c
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// D[128, N] = sum_p A[p, 0:128] * X[p, 0:N] over P points (a multiple of 32): both operands MN-major, the layout of
+// the weight-gradient GEMM.  Tiles are [32 points x 32 features] SWIZZLE_128B images, feature chunks 4 KB apart.
+__global__ void __launch_bounds__(128) probe_gemm_mn(const float* __restrict__ A, const float* __restrict__ X, int N,
+                                                    int P, float* __restrict__ D, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;            // 4 chunks x 4 KB
+  uint8_t* sX = smem + 16384;    // 8 chunks x 4 KB
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) { mbar_init(smem_u32(&bar_mma), 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t idesc = umma_idesc_tf32_mn(128, N);
+  bool ok = true;
+  for (int st = 0; st < P / 32 && ok; ++st) {
+    for (int i = tid; i < 32 * 128; i += 128) {
+      int p = i / 128, n = i % 128;
+      *reinterpret_cast<float*>(sA + (n >> 5) * 4096 + sw128_offset(p, n & 31)) = A[(st * 32 + p) * 128 + n];
+    }
+    for (int i = tid; i < 32 * N; i += 128) {
+      int p = i / N, n = i % N;
+      *reinterpret_cast<float*>(sX + (n >> 5) * 4096 + sw128_offset(p, n & 31)) = X[(st * 32 + p) * N + n];
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      for (int g = 0; g < 4; ++g)
+        umma_tf32(tmem_base, umma_desc_sw128_mn(smem_u32(sA) + g * 1024, 4096, 1024),
+                  umma_desc_sw128_mn(smem_u32(sX) + g * 1024, 4096, 1024), idesc, (st | g) ? 1u : 0u);
+      umma_commit(smem_u32(&bar_mma));
+    }
+    ok = mbar_wait(smem_u32(&bar_mma), st & 1);
+    tc_fence_after();
+    __syncthreads();
+  }
+  if (!ok) {
+    if (tid == 0) status[0] = 1;
+  } else {
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      int r = warp * 32 + (tid & 31);
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < N) D[r * N + c0 + j] = v[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static int run_gemm_mn(int N, int P) {
+  std::vector<float> A((size_t)P * 128), X((size_t)P * N), D(128 * N, -1.f), R(128 * N, 0.f);
+  srand(99 + N + P);
+  for (auto& v : A) v = (float)(rand() % 7 - 3);
+  for (auto& v : X) v = (float)(rand() % 7 - 3);
+  for (int p = 0; p < P; ++p)
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < N; ++n) R[m * N + n] += A[p * 128 + m] * X[p * N + n];
+  float *dA, *dX, *dD;
+  int* dS;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dX, X.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMalloc(&dS, 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, D.size() * 4)); CK(cudaMemset(dS, 0, 4));
+  const int smem = 16384 + 32768 + 1024;
+  CK(cudaFuncSetAttribute(probe_gemm_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_gemm_mn<<<1, 128, smem>>>(dA, dX, N, P, dD, dS);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("probe_gemm_mn N=%d P=%d: LAUNCH FAILED %s\n", N, P, cudaGetErrorString(e)); return 2; }
+  int st = 0;
+  CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0, first = -1;
+  double maxerr = 0;
+  for (size_t i = 0; i < D.size(); ++i) {
+    double er = fabs((double)D[i] - R[i]);
+    if (!(er <= 1e-3)) { if (first < 0) first = (int)i; ++bad; }
+    if (er > maxerr) maxerr = er;
+  }
+  printf("probe_gemm_mn N=%d P=%d: %s (timeout=%d, mismatches=%d/%zu, maxerr=%g", N, P, (bad == 0 && st == 0) ? "PASS" : "FAIL",
+         st, bad, D.size(), maxerr);
+  if (first >= 0) printf(", first bad (m=%d,n=%d) got %g want %g", first / N, first % N, D[first], R[first]);
+  printf(")\n");
+  if (bad) {
+    for (int m = 0; m < 4; ++m) {
+      printf("  row %d got:", m);
+      for (int n = 0; n < 8; ++n) printf(" %6.0f", D[m * N + n]);
+      printf("   want:");
+      for (int n = 0; n < 8; ++n) printf(" %6.0f", R[m * N + n]);
+      printf("\n");
+    }
+    for (int m : {32, 64}) {
+      printf("  row %d got:", m);
+      for (int n : {0, 1, 32, 33, 64, 128}) if (n < N) printf(" %6.0f", D[m * N + n]);
+      printf("   want:");
+      for (int n : {0, 1, 32, 33, 64, 128}) if (n < N) printf(" %6.0f", R[m * N + n]);
+      printf("\n");
+    }
+  }
+  cudaFree(dA); cudaFree(dX); cudaFree(dD); cudaFree(dS);
+  return bad == 0 && st == 0 ? 0 : 1;
+}
+
 // Issue `iters` x 4 back-to-back MMAs (N=256, K=8 each) on fixed operands and report cycles per MMA.
 __global__ void __launch_bounds__(128) probe_rate(int iters, long long* cycles, int* status) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -202,6 +314,10 @@ int main() {
   fails += run_gemm(16, 64, 0, 1) != 0;
   fails += run_gemm(256, 64, 1, 1) != 0;
   fails += run_gemm(224, 256, 1, 1) != 0;
+  fails += run_gemm_mn(256, 32) != 0;
+  fails += run_gemm_mn(256, 128) != 0;
+  fails += run_gemm_mn(64, 64) != 0;
+  fails += run_gemm_mn(16, 64) != 0;
   {
     long long* dC;
     int* dS;

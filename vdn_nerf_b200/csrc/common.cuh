@@ -54,20 +54,20 @@ __device__ __forceinline__ float softplus100_d2(float z) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// MUFU-based variants for the tensor-core mode, whose operands are rounded to tf32 (2^-11) anyway: absolute error
-// of softplus ~1e-8, relative error of its derivatives ~1e-6.
+// MUFU-based, branch-free variants for the tensor-core mode, whose operands are rounded to tf32 (2^-11) anyway:
+// absolute error of softplus ~1e-8, relative error of its derivatives ~1e-6.  Branch-free matters: with a branch
+// per element the compiler serialises the MUFU chains and the operand producer becomes latency bound.
 __device__ __forceinline__ float softplus100_fast(float z) {
-  float t = z * kSoftplusBeta;
-  return t > kSoftplusThreshold ? z : __logf(1.0f + __expf(t)) * (1.0f / kSoftplusBeta);
+  const float t = z * kSoftplusBeta;
+  const float s = __logf(1.0f + __expf(fminf(t, kSoftplusThreshold))) * (1.0f / kSoftplusBeta);
+  return t > kSoftplusThreshold ? z : s;
 }
+// sigmoid(100 z); above the threshold 1/(1+e^-20) already rounds to 1.0f, matching the reference's branch
 __device__ __forceinline__ float softplus100_d1_fast(float z) {
-  float t = z * kSoftplusBeta;
-  return t > kSoftplusThreshold ? 1.0f : __fdividef(1.0f, 1.0f + __expf(-t));
+  return __fdividef(1.0f, 1.0f + __expf(-z * kSoftplusBeta));
 }
 __device__ __forceinline__ float softplus100_d2_fast(float z) {
-  float t = z * kSoftplusBeta;
-  if (t > kSoftplusThreshold) return 0.0f;
-  float s = __fdividef(1.0f, 1.0f + __expf(-t));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-z * kSoftplusBeta));
   return kSoftplusBeta * s * (1.0f - s);
 }
 

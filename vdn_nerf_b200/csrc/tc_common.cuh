@@ -81,6 +81,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// shared-memory matrix descriptor, MN-major, SWIZZLE_128B: rows of the image are K indices (8-row groups
+// sbo_bytes apart), the 128-byte row holds 32 consecutive M/N indices, further 32-index chunks lbo_bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor for kind::tf32 with both operands MN-major (the weight-gradient GEMM)
+__host__ __device__ __forceinline__ uint32_t umma_idesc_tf32_mn(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major
 __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
