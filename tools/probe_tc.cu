@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) probe_gemm(const float* __restrict__ A, c
 // D[128, N] = sum_p A[p, 0:128] * X[p, 0:N] over P points (a multiple of 32): both operands MN-major, the layout of
 // the weight-gradient GEMM.  Tiles are [32 points x 32 features] SWIZZLE_128B images, feature chunks 4 KB apart.
 __global__ void __launch_bounds__(128) probe_gemm_mn(const float* __restrict__ A, const float* __restrict__ X, int N,
-                                                    int P, float* __restrict__ D, int* __restrict__ status) {
+                                                    int P, int sbo, float* __restrict__ D, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;            // 4 chunks x 4 KB
@@ -120,19 +120,19 @@ __global__ void __launch_bounds__(128) probe_gemm_mn(const float* __restrict__ A
   for (int st = 0; st < P / 32 && ok; ++st) {
     for (int i = tid; i < 32 * 128; i += 128) {
       int p = i / 128, n = i % 128;
-      *reinterpret_cast<float*>(sA + (n >> 5) * 4096 + sw128_offset(p, n & 31)) = A[(st * 32 + p) * 128 + n];
+      *reinterpret_cast<float*>(sA + (n >> 5) * 4096 + sw128_32b_offset(p, n & 31)) = A[(st * 32 + p) * 128 + n];
     }
     for (int i = tid; i < 32 * N; i += 128) {
       int p = i / N, n = i % N;
-      *reinterpret_cast<float*>(sX + (n >> 5) * 4096 + sw128_offset(p, n & 31)) = X[(st * 32 + p) * N + n];
+      *reinterpret_cast<float*>(sX + (n >> 5) * 4096 + sw128_32b_offset(p, n & 31)) = X[(st * 32 + p) * N + n];
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       for (int g = 0; g < 4; ++g)
-        umma_tf32(tmem_base, umma_desc_sw128_mn(smem_u32(sA) + g * 1024, 4096, 1024),
-                  umma_desc_sw128_mn(smem_u32(sX) + g * 1024, 4096, 1024), idesc, (st | g) ? 1u : 0u);
+        umma_tf32(tmem_base, umma_desc_sw128_mn(smem_u32(sA) + g * 1024, 4096, sbo),
+                  umma_desc_sw128_mn(smem_u32(sX) + g * 1024, 4096, sbo), idesc, (st | g) ? 1u : 0u);
       umma_commit(smem_u32(&bar_mma));
     }
     ok = mbar_wait(smem_u32(&bar_mma), st & 1);
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) probe_gemm_mn(const float* __restrict__ A
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-static int run_gemm_mn(int N, int P) {
+static int run_gemm_mn(int N, int P, int sbo = 512) {
   std::vector<float> A((size_t)P * 128), X((size_t)P * N), D(128 * N, -1.f), R(128 * N, 0.f);
   srand(99 + N + P);
   for (auto& v : A) v = (float)(rand() % 7 - 3);
@@ -173,7 +173,7 @@ static int run_gemm_mn(int N, int P) {
   CK(cudaMemset(dD, 0xff, D.size() * 4)); CK(cudaMemset(dS, 0, 4));
   const int smem = 16384 + 32768 + 1024;
   CK(cudaFuncSetAttribute(probe_gemm_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe_gemm_mn<<<1, 128, smem>>>(dA, dX, N, P, dD, dS);
+  probe_gemm_mn<<<1, 128, smem>>>(dA, dX, N, P, sbo, dD, dS);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("probe_gemm_mn N=%d P=%d: LAUNCH FAILED %s\n", N, P, cudaGetErrorString(e)); return 2; }
   int st = 0;
@@ -186,7 +186,7 @@ static int run_gemm_mn(int N, int P) {
     if (!(er <= 1e-3)) { if (first < 0) first = (int)i; ++bad; }
     if (er > maxerr) maxerr = er;
   }
-  printf("probe_gemm_mn N=%d P=%d: %s (timeout=%d, mismatches=%d/%zu, maxerr=%g", N, P, (bad == 0 && st == 0) ? "PASS" : "FAIL",
+  printf("probe_gemm_mn sbo=%d N=%d P=%d: %s (timeout=%d, mismatches=%d/%zu, maxerr=%g", sbo, N, P, (bad == 0 && st == 0) ? "PASS" : "FAIL",
          st, bad, D.size(), maxerr);
   if (first >= 0) printf(", first bad (m=%d,n=%d) got %g want %g", first / N, first % N, D[first], R[first]);
   printf(")\n");

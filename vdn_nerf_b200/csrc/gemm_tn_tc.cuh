@@ -1,0 +1,262 @@
+// tcgen05 weight-gradient GEMM (tensor-core mode):  P[s][n,k] = sum_{m in split s} proA(A)[m,n] * proX(X)[m,k]
+//
+// The reduction runs over the batch (points), so both operands are MN-major for the MMA: a shared-memory tile is
+// [32 points x 32 features] in the SWIZZLE_128B_BASE32B image (rows = points; the only layout tf32 supports for
+// MN-major operands), read by the tensor core with K = points.  One CTA owns 128 output rows (n) x up to 256 output columns (k) and a contiguous
+// split of the batch; its accumulator stays in TMEM for the whole split and is written once, as a partial slab
+// that reduce_partials_kernel sums deterministically.  Eight producer warps transform both operands (coalesced
+// loads -> prologue -> tf32 round -> swizzled store), one thread issues the MMAs, a 2-stage mbarrier ring
+// connects them, two CTAs share an SM.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace vdn {
+
+constexpr int TN_THREADS = 320;   // warps 0-7 producers + epilogue, warp 8 MMA issuer, warp 9 TMEM allocation
+constexpr int TN_P = 32;          // points per pipeline stage
+constexpr uint32_t TN_TILE = 4096;                 // bytes of one [32 x 32] tile
+constexpr uint32_t TN_STAGE = 12 * TN_TILE;        // 4 tiles of A (128 n) + 8 tiles of X (256 k)
+
+__device__ __forceinline__ float4 tn_pro4(int kind, float scale, float4 a, float4 b) {
+  switch (kind) {
+    case PRO_SOFTPLUS: return f4_map_sp(a);
+    case PRO_DSIG: return f4_scale(f4_mul(f4_map_sp1(b), a), scale);
+    case PRO_DSIGMOID: return f4_mul(a, make_float4(b.x * (1.f - b.x), b.y * (1.f - b.y), b.z * (1.f - b.z), b.w * (1.f - b.w)));
+    case PRO_RELUMASK: return make_float4(b.x > 0.f ? a.x : 0.f, b.y > 0.f ? a.y : 0.f, b.z > 0.f ? a.z : 0.f, b.w > 0.f ? a.w : 0.f);
+    default: return a;
+  }
+}
+
+static __global__ void __launch_bounds__(TN_THREADS, 2)
+gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__ P, int ldp, int rows_per_split,
+                  int* __restrict__ fault) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[2], bar_empty[2], bar_acc;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * 128;
+  const int split = blockIdx.y;
+  const int k0 = blockIdx.z * 256;
+  const int kt = min(256, K - k0);
+  const int k_mma = (kt + 15) & ~15;
+  const int nxt = (kt + 31) >> 5;                       // X tiles per stage actually needed
+  const int mbeg = split * rows_per_split;
+  const int mend = min(M, mbeg + rows_per_split);
+  const int nst = mend > mbeg ? (mend - mbeg + TN_P - 1) / TN_P : 0;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 256);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_acc), 1);
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc(smem_u32(&tmem_base_s), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  bool ok = true;
+
+  if (warp < 8) {
+    // ---- producers: warp w owns rows (points) 4w..4w+3 of every tile; a warp instruction covers 4 rows x 128 B ----
+    const int chunk = lane & 7;
+    const uint32_t r = (uint32_t)(warp * 4 + (lane >> 3));   // point row inside the stage, 0..31
+    // SWIZZLE_128B_BASE32B image: 4-row groups of 512 B, 32-byte blocks of row r permuted by (r % 4)
+    const uint32_t soff = (r >> 2) * 512u + (r & 3u) * 128u + (((((uint32_t)chunk >> 1) ^ r) & 3u) << 5) +
+                          (((uint32_t)chunk & 1u) << 4);
+    const bool twoA = A.kind >= PRO_DSIG;   // the X side only takes single-operand prologues (none / softplus)
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int st = 0; st < nst && ok; ++st) {
+      const int s = st & 1, ph = (st >> 1) & 1;
+      const int m = mbeg + st * TN_P + (int)r;
+      const bool rok = m < mend;
+      float4 va[4], vx[8];
+      // A side: n columns n0 + 32 t + 4 chunk
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int c = n0 + t * 32 + chunk * 4;
+        float4 a = zero4, b = zero4;
+        if (rok && c < A.width) {
+          a = *reinterpret_cast<const float4*>(A.p + (size_t)m * A.ld + c);
+          if (twoA) b = *reinterpret_cast<const float4*>(A.p2 + (size_t)m * A.ld2 + c);
+        }
+        va[t] = a;
+        if (twoA) vx[t] = b;   // borrow vx as scratch for the second operand of the A side
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int c = n0 + t * 32 + chunk * 4;
+        float4 v = tn_pro4(A.kind, A.scale, va[t], vx[t]);
+        if (!rok || c >= A.width) v = zero4;
+        if (c + 0 >= A.kvalid) v.x = 0.f;
+        if (c + 1 >= A.kvalid) v.y = 0.f;
+        if (c + 2 >= A.kvalid) v.z = 0.f;
+        if (c + 3 >= A.kvalid) v.w = 0.f;
+        va[t] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      }
+      // X side: k columns k0 + 32 t + 4 chunk
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = k0 + t * 32 + chunk * 4;
+        float4 a = zero4;
+        if (t < nxt && rok && c < X.width) a = *reinterpret_cast<const float4*>(X.p + (size_t)m * X.ld + c);
+        vx[t] = a;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = k0 + t * 32 + chunk * 4;
+        float4 v = (X.kind == PRO_SOFTPLUS) ? f4_map_sp(vx[t]) : vx[t];
+        if (!(t < nxt && rok && c < X.width)) v = zero4;
+        if (c + 0 >= X.kvalid) v.x = 0.f;
+        if (c + 1 >= X.kvalid) v.y = 0.f;
+        if (c + 2 >= X.kvalid) v.z = 0.f;
+        if (c + 3 >= X.kvalid) v.w = 0.f;
+        vx[t] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      }
+      ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+      const uint32_t base = smem0 + (uint32_t)s * TN_STAGE + soff;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)t * TN_TILE), "f"(va[t].x),
+                     "f"(va[t].y), "f"(va[t].z), "f"(va[t].w)
+                     : "memory");
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (t < nxt)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(4 + t) * TN_TILE),
+                       "f"(vx[t].x), "f"(vx[t].y), "f"(vx[t].z), "f"(vx[t].w)
+                       : "memory");
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bar_full[s]));
+    }
+  } else if (tid == 8 * 32) {
+    // ---- MMA issuer: 4 MMAs (8 points each) per stage, both operands MN-major ------------------------------
+    const uint32_t idesc = umma_idesc_tf32_mn(128, (uint32_t)k_mma);
+    for (int st = 0; st < nst && ok; ++st) {
+      const int s = st & 1, ph = (st >> 1) & 1;
+      ok = mbar_wait(smem_u32(&bar_full[s]), ph);
+      tc_fence_after();
+      const uint32_t a0 = smem0 + (uint32_t)s * TN_STAGE, x0 = a0 + 4 * TN_TILE;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        umma_tf32(tmem_base, umma_desc_sw128_mn(a0 + g * 1024, TN_TILE, 512), umma_desc_sw128_mn(x0 + g * 1024, TN_TILE, 512),
+                  idesc, (st | g) ? 1u : 0u);
+      umma_commit(smem_u32(&bar_empty[s]));
+    }
+    umma_commit(smem_u32(&bar_acc));
+  }
+  // ---- epilogue: the eight producer warps write the partial tile ----------------------------------------------
+  __syncwarp();
+  if (warp < 8) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(smem_u32(&bar_acc), 0)) {
+      __nanosleep(100);
+      if (++spins > (1u << 24)) { ok = false; break; }
+    }
+    tc_fence_after();
+    if (ok) {
+      const int q = warp & 3, half = warp >> 2;
+      const int nch = (kt + 31) >> 5;
+      const uint32_t stg = smem0 + (uint32_t)warp * 4096u;
+      const int g = lane & 7;
+      const int nbase = n0 + q * 32 + (lane >> 3);
+      float* Ps = P + (size_t)split * N * ldp;
+      for (int ch = half; ch < nch; ch += 2) {
+        float v[32];
+        if (nst > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)lane * 128u +
+                                                                       (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4)),
+                       "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                       : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rr = (uint32_t)(i * 4 + (lane >> 3));
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                       : "r"(stg + rr * 128u + (((uint32_t)g ^ (rr & 7u)) << 4)));
+          const int n = nbase + 4 * i;
+          const int k = k0 + ch * 32 + g * 4;
+          if (n < N) {
+            float* dst = Ps + (size_t)n * ldp + k;
+            if (k + 3 < K && (ldp & 3) == 0) {
+              *reinterpret_cast<float4*>(dst) = x;
+            } else {
+              if (k + 0 < K) dst[0] = x.x;
+              if (k + 1 < K) dst[1] = x.y;
+              if (k + 2 < K) dst[2] = x.z;
+              if (k + 3 < K) dst[3] = x.w;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    } else if (fault) {
+      *fault = 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 256);
+}
+
+// Row splits of the batch for the tensor-core weight gradient (also sizes the partial slabs).
+inline int wgrad_splits_tc(int M) {
+  int s = (M + 511) / 512;
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  return s;
+}
+
+static inline int launch_wgrad_tc(int M, int N, int K, const Operand& A0, const Operand& X0, float* partials, float* dW,
+                                  int ldd, int accumulate, cudaStream_t st) {
+  const int S = wgrad_splits_tc(M);
+  int rows = (M + S - 1) / S;
+  rows = (rows + TN_P - 1) / TN_P * TN_P;
+  const int ldp = (K + 3) & ~3;
+  static bool attr_set = false;
+  const size_t smem = 2 * TN_STAGE + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((N + 127) / 128, S, (K + 255) / 256);
+  prof_begin(PROF_WGRAD, st, 2.0 * M * N * K);
+  VDN_LAUNCH(gemm_tn_tc_kernel, grid, TN_THREADS, smem, st, M, N, K, A0, X0, partials, ldp, rows, g_tc_fault);
+  int e = (int)cudaGetLastError();
+  if (e) return e;
+  const int total = N * K;
+  VDN_LAUNCH(reduce_partials_kernel, (total + 255) / 256, 256, 0, st, partials, S, N, K, ldp, dW, ldd, accumulate);
+  prof_end(PROF_WGRAD, st);
+  return (int)cudaGetLastError();
+}
+
+// Mode dispatch for the weight gradient (single operand pair).
+inline int launch_wgrad_any(int M, int N, int K, const Operand& A0, const Operand& X0, float* partials, float* dW, int ldd,
+                            int accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (g_mode == 1 && operand_ok(A0) && operand_ok(X0) && X0.kind <= PRO_SOFTPLUS) return launch_wgrad_tc(M, N, K, A0, X0, partials, dW, ldd, accumulate, st);
+  return launch_wgrad(M, N, K, A0, X0, nullptr, nullptr, partials, dW, ldd, accumulate, st);
+}
+
+// Number of partial slabs either path may write (for workspace sizing).
+inline long long wgrad_max_splits(long long M) {
+  int a = wgrad_splits((int)M), b = wgrad_splits_tc((int)M);
+  return a > b ? a : b;
+}
+
+}  // namespace vdn

@@ -3,7 +3,7 @@
 //   * NeRF++ background field                                             reference fields.py:264-355
 // Post-activation tensors H_l are stored (ReLU backward only needs the sign), heads that share an input are
 // packed as one stacked weight so they run as one GEMM with a splitting epilogue.
-#include "gemm_tc.cuh"
+#include "gemm_tn_tc.cuh"
 #include "pointwise.cuh"
 #include "../../include/vdn_b200.h"
 
@@ -85,10 +85,10 @@ extern "C" int vdn_rendernet_forward(const int* cfg, const float* packed, const 
 extern "C" long long vdn_rendernet_bwd_ws_floats(const int* cfg, long long N) {
   RnCfg c;
   if (parse_rn_cfg(cfg, &c)) return -1;
-  long long S = wgrad_splits((int)N);
+  long long S = wgrad_max_splits(N);
   long long maxw = 0, maxo = 0;
   for (int l = 0; l < c.L; ++l) {
-    long long w = (long long)c.ly.out_dim[l] * c.ly.in_dim[l];
+    long long w = (long long)c.ly.out_dim[l] * ((c.ly.in_dim[l] + 3) & ~3);
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
@@ -124,7 +124,7 @@ extern "C" int vdn_rendernet_backward(const int* cfg, const float* packed, long 
                                 : make_operand(ZB[l & 1], c.ldH, ly.out_ld[l], ly.out_dim[l]);
     Operand u = (l == 0) ? make_operand(CIN, c.ldIn, c.ldIn, c.in0)
                          : make_operand(H + (long long)(l - 1) * N * c.ldH, c.ldH, ly.in_ld[l], ly.in_dim[l]);
-    int e = launch_wgrad(M, ly.out_dim[l], ly.in_dim[l], zbar, u, nullptr, nullptr, partials, dpacked + ly.off_w[l],
+    int e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l],
                          ly.in_ld[l], 1, st);
     if (e) return e;
     e = launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);
@@ -270,10 +270,10 @@ extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float
 extern "C" long long vdn_nerf_bwd_ws_floats(const int* cfg, long long N) {
   NerfCfg c;
   if (parse_nerf_cfg(cfg, &c)) return -1;
-  long long S = wgrad_splits((int)N);
+  long long S = wgrad_max_splits(N);
   long long maxw = 0, maxo = 0;
   for (int l = 0; l < c.L; ++l) {
-    long long w = (long long)c.ly.out_dim[l] * c.ly.in_dim[l];
+    long long w = (long long)c.ly.out_dim[l] * ((c.ly.in_dim[l] + 3) & ~3);
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
@@ -305,7 +305,7 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
   float* partials = p;
   int e;
   auto wg = [&](int l, const Operand& zbar, const Operand& u) -> int {
-    int r = launch_wgrad(M, ly.out_dim[l], ly.in_dim[l], zbar, u, nullptr, nullptr, partials, dpacked + ly.off_w[l],
+    int r = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l],
                          ly.in_ld[l], 1, st);
     if (r) return r;
     return launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);

@@ -7,7 +7,7 @@
 //
 // Math: SURVEY.md Appendix A.  Storage: one pre-activation tensor Z_l per layer (activations are recomputed
 // in the consumer's operand prologue), plus G_l = d sdf / d(input of layer l) from the normals pass.
-#include "gemm_tc.cuh"
+#include "gemm_tn_tc.cuh"
 #include "pointwise.cuh"
 #include "../../include/vdn_b200.h"
 
@@ -244,10 +244,10 @@ extern "C" int vdn_sdf_normals(const int* cfg, float scale, const float* packed,
 extern "C" long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N) {
   SdfCfg c;
   if (parse_sdf_cfg(cfg, 1.0f, &c)) return -1;
-  long long S = wgrad_splits((int)N);
+  long long S = wgrad_max_splits(N);
   long long maxw = 0, maxo = 0;
   for (int l = 0; l < c.L; ++l) {
-    long long w = (long long)c.ly.out_dim[l] * c.ly.in_dim[l];
+    long long w = (long long)c.ly.out_dim[l] * ((c.ly.in_dim[l] + 3) & ~3);
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
@@ -310,7 +310,7 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
       if (e) return e;
       // Wbar_l += delta_l^T qbar_l with delta_l = softplus'(z_l) * Gin_l recomputed on the fly
       Operand delta = make_operand(gi.p, gi.ld, ly.out_ld[l], ly.out_dim[l], PRO_DSIG, b.Z[l], c.ldH, gi.scale);
-      e = launch_wgrad(M, ly.out_dim[l], ly.in_dim[l], delta, qbar, nullptr, nullptr, partials,
+      e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], delta, qbar, partials,
                        dpacked + ly.off_w[l], ly.in_ld[l], 1, st);
       if (e) return e;
     }
@@ -341,7 +341,7 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
     Operand zbar = (l == L - 1) ? make_operand(ZL, ly.out_ld[l], ly.out_ld[l], ly.out_dim[l])
                                 : make_operand(ZG[l], c.ldH, ly.out_ld[l], ly.out_dim[l]);
     Operand u = input_operand(c, b, l);
-    e = launch_wgrad(M, ly.out_dim[l], ly.in_dim[l], zbar, u, nullptr, nullptr, partials, dpacked + ly.off_w[l],
+    e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l],
                      ly.in_ld[l], 1, st);
     if (e) return e;
     e = launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);

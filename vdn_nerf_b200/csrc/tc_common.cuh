@@ -81,15 +81,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
-// shared-memory matrix descriptor, MN-major, SWIZZLE_128B: rows of the image are K indices (8-row groups
-// sbo_bytes apart), the 128-byte row holds 32 consecutive M/N indices, further 32-index chunks lbo_bytes apart
+// MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B layout (CUTLASS: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"): rows of the image are K indices, the 128-byte row holds 32
+// consecutive M/N indices, rows come in groups of 4 (sbo_bytes apart) and inside a group the four 32-byte blocks
+// of row r are XOR-permuted by (r % 4); further 32-index chunks of M/N are lbo_bytes apart.
+__host__ __device__ __forceinline__ uint32_t sw128_32b_offset(uint32_t r, uint32_t c) {   // row r (K), column c (<32)
+  return (r >> 2) * 512u + (r & 3u) * 128u + ((((c >> 3) ^ r) & 3u) << 5) + ((c & 7u) << 2);
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
   return d;
 }
 // instruction descriptor for kind::tf32 with both operands MN-major (the weight-gradient GEMM)
