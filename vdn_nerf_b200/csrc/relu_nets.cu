@@ -92,7 +92,7 @@ extern "C" long long vdn_rendernet_bwd_ws_floats(const int* cfg, long long N) {
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
-  return 2 * N * c.ldH + N * c.ly.out_ld[c.L - 1] + S * maxw + S * maxo + 64;
+  return 2 * N * c.ldH + N * c.ly.out_ld[c.L - 1] + S * maxw + 256 * maxo + 64;
 }
 
 // d_out: [N, d_out] contiguous cotangent of the network output; `out` is the forward output.
@@ -278,7 +278,7 @@ extern "C" long long vdn_nerf_bwd_ws_floats(const int* cfg, long long N) {
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
   return 2 * N * c.ldH + N * c.ly.out_ld[c.D] + N * c.ldHV + N * c.ly.out_ld[c.D + 2] + N * c.ldV +
-         2 * N * c.ldE + S * maxw + S * maxo + 64;
+         2 * N * c.ldE + S * maxw + 256 * maxo + 64;
 }
 
 // d_pts (nullable): [N, d_in]; d_views (nullable): [N, 3].

@@ -252,7 +252,7 @@ extern "C" long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N) {
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
   return 3 * N * c.ldH + (long long)(c.L - 1) * N * c.ldH + N * c.ly.out_ld[c.L - 1] + 3 * N * c.ldE +
-         S * maxw + S * maxo + 64;
+         S * maxw + 256 * maxo + 64;
 }
 
 extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed, const float* x, long long N,
