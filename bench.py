@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--rays", type=int, default=512, help="rays per step per GPU")
     ap.add_argument("--resolution", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="fp32: exact FFMA kernels; tf32: tcgen05 tensor-core kernels (fp32 accumulate)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -26,12 +26,12 @@ echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 
 if [ "${1:-}" != "quick" ]; then
   echo "== bench train tf32"; timeout 900 python bench.py --precision tf32 --steps 10 --warmup 3 > $OUT/bench_train_tf32.json 2> $OUT/bench_train_tf32.err; echo "exit $?"; tail -c 1800 $OUT/bench_train_tf32.json; tail -3 $OUT/bench_train_tf32.err
   echo "== bench grid tf32"; timeout 900 python bench.py --precision tf32 --workload grid --steps 3 --warmup 3 > $OUT/bench_grid_tf32.json 2> $OUT/bench_grid_tf32.err; echo "exit $?"; tail -c 1500 $OUT/bench_grid_tf32.json; tail -3 $OUT/bench_grid_tf32.err
-  echo "== bench train"; timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "exit $?"; tail -c 1800 $OUT/bench_train.json; tail -3 $OUT/bench_train.err
-  echo "== bench grid"; timeout 900 python bench.py --workload grid --steps 2 --warmup 3 > $OUT/bench_grid.json 2> $OUT/bench_grid.err; echo "exit $?"; tail -c 1500 $OUT/bench_grid.json; tail -3 $OUT/bench_grid.err
+  echo "== bench train"; timeout 900 python bench.py --precision fp32 --steps 10 --warmup 3 > $OUT/bench_train.json 2> $OUT/bench_train.err; echo "exit $?"; tail -c 1800 $OUT/bench_train.json; tail -3 $OUT/bench_train.err
+  echo "== bench grid"; timeout 900 python bench.py --precision fp32 --workload grid --steps 2 --warmup 3 > $OUT/bench_grid.json 2> $OUT/bench_grid.err; echo "exit $?"; tail -c 1500 $OUT/bench_grid.json; tail -3 $OUT/bench_grid.err
   echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "exit $?"; tail -c 900 $OUT/bench_ref.json
   echo "== ncu launch list"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_train.csv \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_train.log 2>&1; echo "ncu exit $?"
+      python bench.py --precision tf32 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_train.log 2>&1; echo "ncu exit $?"
   wc -l $OUT/launches_train.csv
 fi
 echo "== done"

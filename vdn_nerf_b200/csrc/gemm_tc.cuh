@@ -4,11 +4,11 @@
 //   gemm_nt_tc : C[M,N] = epi( pro(A)[M,K] * W[N,K]^T + bias )
 //
 // One CTA owns a 128-row tile and up to 256 output columns; two CTAs are co-resident per SM so one tile's
-// epilogue overlaps the other's MMAs.  Warp roles: warps 0-3 transform the A operand (coalesced global loads ->
-// prologue -> tf32 round -> SWIZZLE_128B shared-memory image), one thread streams the pre-swizzled weight tiles
-// with cp.async.bulk (TMA engine), one thread issues tcgen05.mma kind::tf32 into a TMEM accumulator, then all
-// eight warps drain TMEM with tcgen05.ld, transpose through shared memory and run the epilogue with coalesced
-// global accesses.  A 2-stage mbarrier ring (full / empty) connects the roles; every wait is bounded and raises a
+// epilogue overlaps the other's MMAs.  Warp roles: warps 0-7 transform the A operand (coalesced global loads two
+// K blocks ahead -> prologue -> tf32 round -> SWIZZLE_128B shared-memory image) and thread 0 streams the
+// pre-swizzled weight tile of each stage with cp.async.bulk (TMA engine); one thread of warp 8 issues tcgen05.mma
+// kind::tf32 into a TMEM accumulator; then the eight warps drain TMEM with tcgen05.ld, transpose through shared
+// memory and run the epilogue with coalesced global accesses.  A 2-stage mbarrier ring (full / empty) connects the roles; every wait is bounded and raises a
 // device fault flag instead of hanging.  The prologue / epilogue kind is switched once per tile-row group, outside
 // the per-element loops, so the executed instruction footprint stays small (the first version, with the switch
 // inlined per element, was instruction-fetch bound).
@@ -19,7 +19,8 @@
 
 namespace vdn {
 
-constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 2, TC_THREADS = 256;
+constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_THREADS = 288;   // warps 0-7: operand producers, then epilogue; warp 8: TMEM allocation + MMA issue
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -41,34 +42,34 @@ __device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float
 __device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// Prologue of 8 float4 groups (8 rows, same 4 columns): kind switched once.
-__device__ __forceinline__ void tc_prologue8(const Operand& A, const RawLoad (&raw)[8], float4 (&v)[8]) {
+// Prologue of 4 float4 groups (4 rows, same 4 columns): kind switched once.
+__device__ __forceinline__ void tc_prologue4(const Operand& A, const RawLoad (&raw)[4], float4 (&v)[4]) {
   switch (A.kind) {
     case PRO_SOFTPLUS:
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = f4_map_sp(raw[i].a);
+      for (int i = 0; i < 4; ++i) v[i] = f4_map_sp(raw[i].a);
       break;
     case PRO_DSIG:
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = f4_scale(f4_mul(f4_map_sp1(raw[i].b), raw[i].a), A.scale);
+      for (int i = 0; i < 4; ++i) v[i] = f4_scale(f4_mul(f4_map_sp1(raw[i].b), raw[i].a), A.scale);
       break;
     case PRO_DSIGMOID:
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float4 b = raw[i].b;
         v[i] = f4_mul(raw[i].a, make_float4(b.x * (1.f - b.x), b.y * (1.f - b.y), b.z * (1.f - b.z), b.w * (1.f - b.w)));
       }
       break;
     case PRO_RELUMASK:
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float4 a = raw[i].a, b = raw[i].b;
         v[i] = make_float4(b.x > 0.f ? a.x : 0.f, b.y > 0.f ? a.y : 0.f, b.z > 0.f ? a.z : 0.f, b.w > 0.f ? a.w : 0.f);
       }
       break;
     default:
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = raw[i].a;
+      for (int i = 0; i < 4; ++i) v[i] = raw[i].a;
       break;
   }
 }
@@ -81,14 +82,13 @@ static __device__ __noinline__ void tc_epi_scalar4(const Epilogue& e, int m, int
 }
 
 // Vector epilogue for 8 rows x 4 columns (same columns for all rows); kind switched once.
-__device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M, int n, float4 (&x)[8]) {
+__device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M, int n, float4 (&x)[8], float4 b) {
   // row of group i is mbase + 4 i
 #define m_(i) (mbase + 4 * (i))
 #define mok_(i) (mbase + 4 * (i) < M)
   auto st4 = [](float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; };
   auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
-  if (e.bias) {
-    const float4 b = ld4(e.bias + n);
+  if (e.bias) {   // b = bias[n .. n+3], fetched by the caller ahead of time
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = f4_add(x[i], b);
   }
@@ -194,13 +194,13 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
 
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 128 + 1);
+      mbar_init(smem_u32(&bar_full[s]), 256 + 1);   // 256 producer threads + the expect_tx arrival of the weight tile
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
     mbar_fence_init();
   }
-  if (warp == 6) tmem_alloc(smem_u32(&tmem_base_s), ncols);
+  if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), ncols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -208,40 +208,40 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
   bool ok = true;
   if (threadIdx.x == 0) VDN_TL(0, 1);
 
-  if (warp < 4) {
-    // ---- A producers: warp w owns rows [32w, 32w+32); per instruction the 32 lanes cover 4 rows x 8 chunks of
-    // 16 bytes, i.e. four full 128-byte row segments (coalesced global loads, conflict-free swizzled stores) ----
+  if (warp < 8) {
+    // ---- A producers: warp w owns rows [16w, 16w+16); per instruction the 32 lanes cover 4 rows x 8 chunks of
+    // 16 bytes, i.e. four full 128-byte row segments (coalesced global loads, conflict-free swizzled stores).
+    // Global loads run two K blocks ahead of their use (double-buffered registers). ----
     const int chunk = lane & 7;
-    const int rbase = warp * 32 + (lane >> 3);                   // row of group i: rbase + 4 i
+    const int rbase = warp * 16 + (lane >> 3);                    // row of group i: rbase + 4 i
     const uint32_t r7e = (uint32_t)(lane >> 3), r7o = r7e + 4u;   // (row & 7) for even / odd i
-    const uint32_t soff_e = (uint32_t)(warp * 4) * 1024u + r7e * 128u + (((uint32_t)chunk ^ r7e) << 4);
-    const uint32_t soff_o = (uint32_t)(warp * 4) * 1024u + r7o * 128u + (((uint32_t)chunk ^ r7o) << 4);
+    const uint32_t soff_e = (uint32_t)(warp * 2) * 1024u + r7e * 128u + (((uint32_t)chunk ^ r7e) << 4);
+    const uint32_t soff_o = (uint32_t)(warp * 2) * 1024u + r7o * 128u + (((uint32_t)chunk ^ r7o) << 4);
     const bool two = A.kind >= PRO_DSIG;
     const float* pa0 = A.p + (size_t)(m0 + rbase) * A.ld + chunk * 4;
     const float* pb0 = two ? A.p2 + (size_t)(m0 + rbase) * A.ld2 + chunk * 4 : nullptr;
     const size_t stepa = (size_t)4 * A.ld, stepb = (size_t)4 * A.ld2;
     const int mlim = M - m0 - rbase;                              // group i is a valid row iff 4 i < mlim
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    RawLoad raw[8];
-    auto gload = [&](int kb) {
+    RawLoad raw0[4], raw1[4];
+    auto gload = [&](int kb, RawLoad (&raw)[4]) {
       const int col = kb * 32 + chunk * 4;
       const bool cok = col < A.width;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const bool p = cok && (4 * i < mlim);
         raw[i].a = p ? *reinterpret_cast<const float4*>(pa0 + i * stepa + kb * 32) : zero4;
         raw[i].b = (p && two) ? *reinterpret_cast<const float4*>(pb0 + i * stepb + kb * 32) : zero4;
       }
     };
-    gload(0);
-    for (int kb = 0; kb < nkb && ok; ++kb) {
+    auto produce = [&](int kb, RawLoad (&raw)[4]) {
       const int s = kb & 1, ph = (kb >> 1) & 1;
       const int col = kb * 32 + chunk * 4;
-      float4 v[8];
-      tc_prologue8(A, raw, v);
+      float4 v[4];
+      tc_prologue4(A, raw, v);
       if (col + 3 >= A.kvalid || col >= A.width) {  // ragged K edge: zero the columns beyond the logical extent
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           if (col + 0 >= A.kvalid) v[i].x = 0.f;
           if (col + 1 >= A.kvalid) v[i].y = 0.f;
           if (col + 2 >= A.kvalid) v[i].z = 0.f;
@@ -249,17 +249,22 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         if (!(4 * i < mlim)) v[i] = zero4;
         v[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
       }
-      if (kb + 1 < nkb) gload(kb + 1);
+      if (kb + 2 < nkb) gload(kb + 2, raw);          // refill the buffer just consumed
       if (tid == 0) VDN_TL(1, 3 * kb);
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
       if (tid == 0) VDN_TL(1, 3 * kb + 1);
       const uint32_t base = smem0 + (uint32_t)s * stage_stride;
+      if (tid == 0) {                                // the stage is free: stream its weight tile (TMA engine)
+        const uint32_t bytes = (uint32_t)n_mma * 128u;
+        mbar_arrive_expect_tx(smem_u32(&bar_full[s]), bytes);
+        bulk_g2s(base + 16384u, Bimg + ((size_t)kb * img_rows + row0 + n_base) * 32, bytes, smem_u32(&bar_full[s]));
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((i & 1) ? soff_o : soff_e) +
                                                                      (uint32_t)(i >> 1) * 1024u),
                      "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
@@ -267,8 +272,14 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       fence_proxy_async();
       mbar_arrive(smem_u32(&bar_full[s]));
       if (tid == 0) VDN_TL(1, 3 * kb + 2);
+    };
+    gload(0, raw0);
+    if (nkb > 1) gload(1, raw1);
+    for (int kb = 0; kb < nkb && ok; kb += 2) {
+      produce(kb, raw0);
+      if (kb + 1 < nkb && ok) produce(kb + 1, raw1);
     }
-  } else if (tid == 128) {
+  } else if (tid == 8 * 32) {
     // ---- MMA issuer ------------------------------------------------------------------------------
     const uint32_t idesc = umma_idesc_tf32(128, (uint32_t)n_mma);
     for (int kb = 0; kb < nkb && ok; ++kb) {
@@ -284,74 +295,76 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       umma_commit(smem_u32(&bar_empty[s]));
     }
     umma_commit(smem_u32(&bar_acc));
-  } else if (tid == 160) {
-    // ---- weight tiles through the TMA engine ------------------------------------------------------
-    const uint32_t bytes = (uint32_t)n_mma * 128u;
-    for (int kb = 0; kb < nkb && ok; ++kb) {
-      const int s = kb & 1, ph = (kb >> 1) & 1;
-      ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-      VDN_TL(3, kb);
-      mbar_arrive_expect_tx(smem_u32(&bar_full[s]), bytes);
-      bulk_g2s(smem0 + (uint32_t)s * stage_stride + 16384u, Bimg + ((size_t)kb * img_rows + row0 + n_base) * 32, bytes,
-               smem_u32(&bar_full[s]));
-    }
   }
-  // ---- epilogue: all eight warps drain the accumulator ------------------------------------------------
+  // ---- epilogue: the eight producer warps drain the accumulator ------------------------------------------
   // TMEM hands every lane one row (32 consecutive columns per load).  Each warp transposes its 32x32 block
   // through a private 4 KB staging tile (the pipeline stages are idle by now) so that the epilogue's global
   // loads / stores again cover four full 128-byte row segments per instruction.
   __syncwarp();
-  {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(smem_u32(&bar_acc), 0)) {
-      if (warp != 4) __nanosleep(200);
-      if (++spins > (1u << 24)) { ok = false; break; }
-    }
-  }
-  tc_fence_after();
-  if (threadIdx.x == 0) VDN_TL(0, 2);
-  if (ok) {
+  if (warp < 8) {
     const int q = warp & 3, half = warp >> 2;
     const int nch = (n_cta + 31) >> 5;
-    const uint32_t stg = smem0 + (uint32_t)warp * 4096u;
     const int g = lane & 7;
-    const int mbase = m0 + q * 32 + (lane >> 3);                  // row of group i: mbase + 4 i
-    const uint32_t e7e = (uint32_t)(lane >> 3), e7o = e7e + 4u;
-    const uint32_t roff_e = e7e * 128u + (((uint32_t)g ^ e7e) << 4);
-    const uint32_t roff_o = e7o * 128u + (((uint32_t)g ^ e7o) << 4);
-    const uint32_t woff = (uint32_t)lane * 128u;
-    for (int ch = half; ch < nch; ch += 2) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-      tmem_ld_wait();
+    // bias of this thread's columns, fetched while the last MMAs are still running
+    float4 bias_r[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + woff + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4)),
-                     "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
-                     : "memory");
-      __syncwarp();
-      float4 x[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
-                     : "r"(stg + ((i & 1) ? roff_o : roff_e) + (uint32_t)(i >> 1) * 1024u));
-      __syncwarp();
-      const int n = n_base + ch * 32 + g * 4;
-      if (vec_ok && n + 3 < N) {
-        tc_epilogue8(E, mbase, M, n, x);
-      } else if (n < N) {
-        for (int i = 0; i < 8; ++i)
-          if (mbase + 4 * i < M) tc_epi_scalar4(E, mbase + 4 * i, n, x[i], N);
+    for (int j = 0; j < 4; ++j) {
+      const int n = n_base + (half + 2 * j) * 32 + g * 4;
+      bias_r[j] = (E.bias && vec_ok && n + 3 < N) ? *reinterpret_cast<const float4*>(E.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(smem_u32(&bar_acc), 0)) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) { ok = false; break; }
       }
     }
-  } else if (fault) {
-    *fault = 1;
+    tc_fence_after();
+    if (threadIdx.x == 0) VDN_TL(0, 2);
+    if (ok) {
+      const uint32_t stg = smem0 + (uint32_t)warp * 4096u;
+      const int mbase = m0 + q * 32 + (lane >> 3);                  // row of group i: mbase + 4 i
+      const uint32_t e7e = (uint32_t)(lane >> 3), e7o = e7e + 4u;
+      const uint32_t roff_e = e7e * 128u + (((uint32_t)g ^ e7e) << 4);
+      const uint32_t roff_o = e7o * 128u + (((uint32_t)g ^ e7o) << 4);
+      const uint32_t woff = (uint32_t)lane * 128u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = half + 2 * j;
+        if (ch < nch) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + woff + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4)),
+                         "f"(v[4 * c]), "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                         : "memory");
+          __syncwarp();
+          float4 x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                         : "r"(stg + ((i & 1) ? roff_o : roff_e) + (uint32_t)(i >> 1) * 1024u));
+          __syncwarp();
+          const int n = n_base + ch * 32 + g * 4;
+          if (vec_ok && n + 3 < N) {
+            tc_epilogue8(E, mbase, M, n, x, bias_r[j]);
+          } else if (n < N) {
+            for (int i = 0; i < 8; ++i)
+              if (mbase + 4 * i < M) tc_epi_scalar4(E, mbase + 4 * i, n, x[i], N);
+          }
+        }
+      }
+    } else if (fault) {
+      *fault = 1;
+    }
   }
   if (threadIdx.x == 0) VDN_TL(0, 3);
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) tmem_dealloc(tmem_base, ncols);
+  if (warp == 8) tmem_dealloc(tmem_base, ncols);
   if (threadIdx.x == 0) VDN_TL(0, 4);
 #undef VDN_TL
 }
