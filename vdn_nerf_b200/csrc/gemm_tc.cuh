@@ -238,6 +238,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       const int s = kb & 1, ph = (kb >> 1) & 1;
       const int col = kb * 32 + chunk * 4;
       float4 v[4];
+      if (tid == 0) VDN_TL(4, 2 * kb);
       tc_prologue4(A, raw, v);
       if (col + 3 >= A.kvalid || col >= A.width) {  // ragged K edge: zero the columns beyond the logical extent
 #pragma unroll
@@ -253,6 +254,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
         if (!(4 * i < mlim)) v[i] = zero4;
         v[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
       }
+      if (tid == 0) VDN_TL(4, 2 * kb + 1);
       if (kb + 2 < nkb) gload(kb + 2, raw);          // refill the buffer just consumed
       if (tid == 0) VDN_TL(1, 3 * kb);
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
@@ -269,7 +271,9 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
                                                                      (uint32_t)(i >> 1) * 1024u),
                      "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
                      : "memory");
+      if (tid == 0) VDN_TL(5, 2 * kb);
       fence_proxy_async();
+      if (tid == 0) VDN_TL(5, 2 * kb + 1);
       mbar_arrive(smem_u32(&bar_full[s]));
       if (tid == 0) VDN_TL(1, 3 * kb + 2);
     };

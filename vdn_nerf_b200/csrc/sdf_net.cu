@@ -8,6 +8,7 @@
 // Math: SURVEY.md Appendix A.  Storage: one pre-activation tensor Z_l per layer (activations are recomputed
 // in the consumer's operand prologue), plus G_l = d sdf / d(input of layer l) from the normals pass.
 #include "gemm_tn_tc.cuh"
+#include "sdf_chain_tc.cuh"
 #include "pointwise.cuh"
 #include "../../include/vdn_b200.h"
 
@@ -143,6 +144,11 @@ static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x
                             float* feat, int ldf, float* blob, int save, float out_mul, cudaStream_t st) {
   if (N <= 0) return 0;
   if (N > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  if (g_mode == 1 && !feat && !save) {   // tensor-core mode, value only: fused chain kernel
+    int r = launch_sdf_chain(c.ly, c.d_in, c.multires, c.d_hidden, c.skip, c.scale, packed, x, nullptr, nullptr, nullptr,
+                             0, 0, 0, N, sdf, lds, out_mul, st);
+    if (r >= 0) return r;
+  }
   SdfBlob b;
   carve_blob(c, N, save, blob, &b);
   int e = launch_embed(c, x, N, b, st);
@@ -203,6 +209,11 @@ extern "C" int vdn_grid_sdf(const int* cfg, float scale, const float* packed, co
   if (c.d_in != 3 || i1 <= i0) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   long long count = (long long)(i1 - i0) * ny * nz;
+  if (g_mode == 1) {   // tensor-core mode: lattice points are generated inside the fused chain kernel
+    int r = launch_sdf_chain(c.ly, c.d_in, c.multires, c.d_hidden, c.skip, c.scale, packed, nullptr, xs, ys, zs, ny, nz,
+                             i0, count, u_slab, 1, out_mul, st);
+    if (r >= 0) return r;
+  }
   VDN_LAUNCH(grid_points_kernel, (unsigned)((count + 255) / 256), 256, 0, st, xs, ys, zs, i0, ny, nz, count, pts);
   int e = (int)cudaGetLastError();
   if (e) return e;

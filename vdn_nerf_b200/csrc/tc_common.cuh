@@ -43,9 +43,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 // Bounded wait: returns false (and the caller bails out) instead of hanging the GPU if a barrier never flips.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t max_spins = 1u << 26) {
-  for (uint32_t i = 0; i < max_spins; ++i)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t max_spins = 1u << 24) {
+  for (uint32_t i = 0; i < max_spins; ++i) {
     if (mbar_try_wait(bar, parity)) return true;
+  }
   return false;
 }
 
