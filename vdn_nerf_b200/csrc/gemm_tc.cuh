@@ -309,13 +309,6 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     const int q = warp & 3, half = warp >> 2;
     const int nch = (n_cta + 31) >> 5;
     const int g = lane & 7;
-    // bias of this thread's columns, fetched while the last MMAs are still running
-    float4 bias_r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n_base + (half + 2 * j) * 32 + g * 4;
-      bias_r[j] = (E.bias && vec_ok && n + 3 < N) ? *reinterpret_cast<const float4*>(E.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     {
       uint32_t spins = 0;
       while (!mbar_try_wait(smem_u32(&bar_acc), 0)) {
@@ -332,10 +325,13 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       const uint32_t roff_e = e7e * 128u + (((uint32_t)g ^ e7e) << 4);
       const uint32_t roff_o = e7o * 128u + (((uint32_t)g ^ e7o) << 4);
       const uint32_t woff = (uint32_t)lane * 128u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ch = half + 2 * j;
-        if (ch < nch) {
+#pragma unroll 1
+      for (int ch = half; ch < nch; ch += 2) {
+        {
+          const int n = n_base + ch * 32 + g * 4;
+          // bias of this thread's columns: issued before the TMEM load so its latency overlaps
+          const float4 bias4 = (E.bias && vec_ok && n + 3 < N) ? __ldg(reinterpret_cast<const float4*>(E.bias + n))
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
           tmem_ld_wait();
@@ -352,9 +348,8 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
                          : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
                          : "r"(stg + ((i & 1) ? roff_o : roff_e) + (uint32_t)(i >> 1) * 1024u));
           __syncwarp();
-          const int n = n_base + ch * 32 + g * 4;
           if (vec_ok && n + 3 < N) {
-            tc_epilogue8(E, mbase, M, n, x, bias_r[j]);
+            tc_epilogue8(E, mbase, M, n, x, bias4);
           } else if (n < N) {
             for (int i = 0; i < 8; ++i)
               if (mbase + 4 * i < M) tc_epi_scalar4(E, mbase + 4 * i, n, x[i], N);

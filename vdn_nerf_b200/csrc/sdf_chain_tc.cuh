@@ -45,11 +45,46 @@ struct ChainArgs {
 };
 
 // embedding column c (< d_e) of point y: [y | sin(2^k y) | cos(2^k y)]_k, d = 3 (embedder.py:15-36)
-__device__ __forceinline__ float chain_embed_col(const float (&y)[3], int c) {
+static __device__ __noinline__ float chain_embed_col(float y0, float y1, float y2, int c) {
+  const float y[3] = {y0, y1, y2};
   if (c < 3) return y[c];
   const int k = (c - 3) / 6, rem = (c - 3) - 6 * k;
   const float f = (float)(1 << k);
   return rem < 3 ? sinf(y[rem] * f) : cosf(y[rem - 3] * f);
+}
+
+// Chunk of 32 output columns that is not entirely real outputs: the tail of the layer before the skip connection
+// (remaining columns carry the embedding, fields.py:82-83) or zero padding.  Cold path, kept out of line.
+static __device__ __noinline__ void chain_ragged_chunk(uint32_t tacc, int n0, int n_mma, int out_dim, const float* bias,
+                                                       float osc, int d_e_tail, float y0, float y1, float y2,
+                                                       uint32_t abase, uint32_t r7) {
+  using namespace tc;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+  if (n0 < n_mma) {
+    tmem_ld32(tacc + (uint32_t)n0, v);
+    tmem_ld_wait();
+  }
+  for (int c4 = 0; c4 < 8; ++c4) {
+    float o[4];
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + c4 * 4 + j;
+      float r = 0.0f;
+      if (nn < out_dim) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) acc = (t == c4 * 4 + j) ? v[t] : acc;
+        r = softplus100_fast(acc + bias[nn]) * osc;
+      } else if (nn - out_dim < d_e_tail) {
+        r = chain_embed_col(y0, y1, y2, nn - out_dim) * osc;
+      }
+      o[j] = to_tf32(r);
+    }
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(abase + (((uint32_t)c4 ^ r7) << 4)), "f"(o[0]), "f"(o[1]),
+                 "f"(o[2]), "f"(o[3])
+                 : "memory");
+  }
 }
 
 static __global__ void __launch_bounds__(CH_THREADS, 1)
@@ -108,7 +143,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c = h * 32 + c4 * 4 + j;
-            v[j] = c < a.d_e ? to_tf32(chain_embed_col(y, c)) : 0.0f;
+            v[j] = c < a.d_e ? to_tf32(chain_embed_col(y[0], y[1], y[2], c)) : 0.0f;
           }
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((uint32_t)c4 ^ r7) << 4)), "f"(v[0]),
                        "f"(v[1]), "f"(v[2]), "f"(v[3])
@@ -140,36 +175,28 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
         const bool skip_next = (l + 1 == a.skip);
         const float osc = skip_next ? kInvSqrt2 : 1.0f;
         for (int ch = h; ch < 8; ch += 2) {
-          float v[32];
           const int n0 = ch * 32;
-          if (n0 < Ly.n_mma) {
+          const uint32_t abase = sA + (uint32_t)ch * 16384u + rowoff;
+          if (n0 + 32 <= Ly.out_dim) {
+            // hot path: a full chunk of real outputs; bias loads are issued before waiting on the TMEM load
+            float v[32];
             tmem_ld32(tacc + (uint32_t)n0, v);
+            float4 b[8];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) b[c4] = __ldg(reinterpret_cast<const float4*>(bias + n0) + c4);
             tmem_ld_wait();
-          }
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float o[4];
-            const int n = n0 + c4 * 4;
-            if (n + 3 < Ly.out_dim) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
-              o[0] = softplus100_fast(v[c4 * 4 + 0] + b.x) * osc;
-              o[1] = softplus100_fast(v[c4 * 4 + 1] + b.y) * osc;
-              o[2] = softplus100_fast(v[c4 * 4 + 2] + b.z) * osc;
-              o[3] = softplus100_fast(v[c4 * 4 + 3] + b.w) * osc;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int nn = n + j;
-                float r = 0.0f;
-                if (nn < Ly.out_dim) r = softplus100_fast(v[c4 * 4 + j] + bias[nn]) * osc;
-                else if (skip_next && nn - Ly.out_dim < a.d_e) r = chain_embed_col(y, nn - Ly.out_dim) * osc;
-                o[j] = r;
-              }
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float o0 = softplus100_fast(v[c4 * 4 + 0] + b[c4].x) * osc;
+              const float o1 = softplus100_fast(v[c4 * 4 + 1] + b[c4].y) * osc;
+              const float o2 = softplus100_fast(v[c4 * 4 + 2] + b[c4].z) * osc;
+              const float o3 = softplus100_fast(v[c4 * 4 + 3] + b[c4].w) * osc;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(abase + (((uint32_t)c4 ^ r7) << 4)),
+                           "f"(to_tf32(o0)), "f"(to_tf32(o1)), "f"(to_tf32(o2)), "f"(to_tf32(o3))
+                           : "memory");
             }
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA + (uint32_t)ch * 16384u + rowoff +
-                                                                         (((uint32_t)c4 ^ r7) << 4)),
-                         "f"(to_tf32(o[0])), "f"(to_tf32(o[1])), "f"(to_tf32(o[2])), "f"(to_tf32(o[3]))
-                         : "memory");
+          } else {
+            chain_ragged_chunk(tacc, n0, Ly.n_mma, Ly.out_dim, bias, osc, skip_next ? a.d_e : 0, y[0], y[1], y[2], abase, r7);
           }
           fence_proxy_async();
           tc_fence_before();
