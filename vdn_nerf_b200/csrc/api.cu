@@ -94,9 +94,7 @@ extern "C" int vdn_embed_fwd(const float* x, long long N, int d, int multires, f
   if (N <= 0) return 0;
   if (d < 1 || d > 8 || multires < 0 || multires > 16) return (int)cudaErrorInvalidValue;
   const int d_e = d * (1 + 2 * multires);
-  VDN_LAUNCH(embed_rows_kernel, (unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream, x, d, N, d, multires, 1.0f, out, d_e,
-                                                                                 nullptr, 0, 0, 1.0f, 0);
-  return (int)cudaGetLastError();
+  return launch_embed_rows(x, d, N, d, multires, 1.0f, out, d_e, nullptr, 0, 0, 1.0f, 0, (cudaStream_t)stream);
 }
 
 extern "C" int vdn_embed_bwd(const float* x, long long N, int d, int multires, const float* d_out, float* d_x,

@@ -29,7 +29,7 @@ __device__ __forceinline__ float4 tn_pro4(int kind, float scale, float4 a, float
 
 static __global__ void __launch_bounds__(TN_THREADS, 2)
 gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__ P, int ldp, int rows_per_split,
-                  int* __restrict__ fault) {
+                  int atomic_out, float* __restrict__ db, int* __restrict__ fault) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[2], bar_empty[2], bar_acc;
@@ -70,6 +70,9 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
                           (((uint32_t)chunk & 1u) << 4);
     const bool twoA = A.kind >= PRO_DSIG;   // the X side only takes single-operand prologues (none / softplus)
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // fused bias gradient: column sums of the A side (db[n] += sum_m A[m,n]) ride along for free
+    const bool do_bias = db != nullptr && blockIdx.z == 0;
+    float4 bsum[4] = {zero4, zero4, zero4, zero4};
     for (int st = 0; st < nst && ok; ++st) {
       const int s = st & 1, ph = (st >> 1) & 1;
       const int m = mbeg + st * TN_P + (int)r;
@@ -96,6 +99,7 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
         if (c + 1 >= A.kvalid) v.y = 0.f;
         if (c + 2 >= A.kvalid) v.z = 0.f;
         if (c + 3 >= A.kvalid) v.w = 0.f;
+        bsum[t] = f4_add(bsum[t], v);
         va[t] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
       }
       // X side: k columns k0 + 32 t + 4 chunk
@@ -133,6 +137,26 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
       fence_proxy_async();
       mbar_arrive(smem_u32(&bar_full[s]));
     }
+    if (do_bias) {   // reduce over the 4 row lanes of the warp, then one atomic per column and warp
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float4 v = bsum[t];
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+          v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+          v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+          v.z += __shfl_xor_sync(0xffffffffu, v.z, off);
+          v.w += __shfl_xor_sync(0xffffffffu, v.w, off);
+        }
+        const int n = n0 + t * 32 + chunk * 4;
+        if ((lane >> 3) == 0) {
+          if (n + 0 < N) atomicAdd(db + n + 0, v.x);
+          if (n + 1 < N) atomicAdd(db + n + 1, v.y);
+          if (n + 2 < N) atomicAdd(db + n + 2, v.z);
+          if (n + 3 < N) atomicAdd(db + n + 3, v.w);
+        }
+      }
+    }
   } else if (tid == 8 * 32) {
     // ---- MMA issuer: 4 MMAs (8 points each) per stage, both operands MN-major ------------------------------
     const uint32_t idesc = umma_idesc_tf32_mn(128, (uint32_t)k_mma);
@@ -164,8 +188,10 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
       const uint32_t stg = smem0 + (uint32_t)warp * 4096u;
       const int g = lane & 7;
       const int nbase = n0 + q * 32 + (lane >> 3);
-      float* Ps = P + (size_t)split * N * ldp;
-      for (int ch = half; ch < nch; ch += 2) {
+      // atomic_out: every split adds its tile straight into the gradient matrix (red.global.add, no partial slabs)
+      float* Ps = atomic_out ? P : P + (size_t)split * N * ldp;
+      const bool skip_all = atomic_out && nst == 0;   // an empty split has nothing to add
+      for (int ch = half; ch < nch && !skip_all; ch += 2) {
         float v[32];
         if (nst > 0) {
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
@@ -190,7 +216,17 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
                        : "r"(stg + rr * 128u + (((uint32_t)g ^ (rr & 7u)) << 4)));
           const int n = nbase + 4 * i;
           const int k = k0 + ch * 32 + g * 4;
-          if (n < N) {
+          if (n < N && atomic_out) {
+            float* dst = Ps + (size_t)n * ldp + k;
+            if (k + 3 < K && (ldp & 3) == 0) {
+              atomicAdd(reinterpret_cast<float4*>(dst), x);
+            } else {
+              if (k + 0 < K) atomicAdd(dst + 0, x.x);
+              if (k + 1 < K) atomicAdd(dst + 1, x.y);
+              if (k + 2 < K) atomicAdd(dst + 2, x.z);
+              if (k + 3 < K) atomicAdd(dst + 3, x.w);
+            }
+          } else if (n < N) {
             float* dst = Ps + (size_t)n * ldp + k;
             if (k + 3 < K && (ldp & 3) == 0) {
               *reinterpret_cast<float4*>(dst) = x;
@@ -221,12 +257,14 @@ inline int wgrad_splits_tc(int M) {
   return s;
 }
 
+// In the tensor-core mode the splits accumulate into dW with fp32 atomics (red.global.add.v4.f32): no partial slabs,
+// no second kernel; the summation order over splits is then not deterministic (differences at the 1e-7 level).
+// `accumulate` must be 1 (the packed gradient buffer is zero-initialised by the caller).
 static inline int launch_wgrad_tc(int M, int N, int K, const Operand& A0, const Operand& X0, float* partials, float* dW,
-                                  int ldd, int accumulate, cudaStream_t st) {
+                                  int ldd, int accumulate, float* db, cudaStream_t st) {
   const int S = wgrad_splits_tc(M);
   int rows = (M + S - 1) / S;
   rows = (rows + TN_P - 1) / TN_P * TN_P;
-  const int ldp = (K + 3) & ~3;
   static bool attr_set = false;
   const size_t smem = 2 * TN_STAGE + 1024;
   if (!attr_set) {
@@ -236,21 +274,30 @@ static inline int launch_wgrad_tc(int M, int N, int K, const Operand& A0, const 
   }
   dim3 grid((N + 127) / 128, S, (K + 255) / 256);
   prof_begin(PROF_WGRAD, st, 2.0 * M * N * K);
-  VDN_LAUNCH(gemm_tn_tc_kernel, grid, TN_THREADS, smem, st, M, N, K, A0, X0, partials, ldp, rows, g_tc_fault);
-  int e = (int)cudaGetLastError();
-  if (e) return e;
-  const int total = N * K;
-  VDN_LAUNCH(reduce_partials_kernel, (total + 255) / 256, 256, 0, st, partials, S, N, K, ldp, dW, ldd, accumulate);
+  if (accumulate) {
+    VDN_LAUNCH(gemm_tn_tc_kernel, grid, TN_THREADS, smem, st, M, N, K, A0, X0, dW, ldd, rows, 1, db, g_tc_fault);
+  } else {
+    const int ldp = (K + 3) & ~3;
+    VDN_LAUNCH(gemm_tn_tc_kernel, grid, TN_THREADS, smem, st, M, N, K, A0, X0, partials, ldp, rows, 0, db, g_tc_fault);
+    int e = (int)cudaGetLastError();
+    if (e) return e;
+    const int total = N * K;
+    VDN_LAUNCH(reduce_partials_kernel, (total + 255) / 256, 256, 0, st, partials, S, N, K, ldp, dW, ldd, 0);
+  }
   prof_end(PROF_WGRAD, st);
   return (int)cudaGetLastError();
 }
 
-// Mode dispatch for the weight gradient (single operand pair).
+// Mode dispatch for the weight gradient (single operand pair).  db (nullable): bias gradient, db[n] += sum_m A0[m,n];
+// the tensor-core kernel fuses it, the fp32 path runs the column-sum kernels.
 inline int launch_wgrad_any(int M, int N, int K, const Operand& A0, const Operand& X0, float* partials, float* dW, int ldd,
-                            int accumulate, cudaStream_t st) {
+                            int accumulate, float* db, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if (g_mode == 1 && operand_ok(A0) && operand_ok(X0) && X0.kind <= PRO_SOFTPLUS) return launch_wgrad_tc(M, N, K, A0, X0, partials, dW, ldd, accumulate, st);
-  return launch_wgrad(M, N, K, A0, X0, nullptr, nullptr, partials, dW, ldd, accumulate, st);
+  if (g_mode == 1 && operand_ok(A0) && operand_ok(X0) && X0.kind <= PRO_SOFTPLUS)
+    return launch_wgrad_tc(M, N, K, A0, X0, partials, dW, ldd, accumulate, db, st);
+  int e = launch_wgrad(M, N, K, A0, X0, nullptr, nullptr, partials, dW, ldd, accumulate, st);
+  if (e || !db) return e;
+  return launch_colsum(M, N, A0, partials, db, 1, st);
 }
 
 // Number of partial slabs either path may write (for workspace sizing).

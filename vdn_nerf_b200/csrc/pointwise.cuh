@@ -7,31 +7,44 @@ namespace vdn {
 
 // e(y) = [y | sin(2^0 y) | cos(2^0 y) | ... ]  with y = x * scale  (reference embedder.py:15-36).
 // Writes row m of `e` (ld lde; columns >= d_e zeroed up to lde) and, when u != nullptr, the same values
-// times uscale into u[m, ucol ... ucol+d_e) (the skip-connection tail of the SDF net, fields.py:82-83).
+// times uscale into u[m, ucol ... ucol+d_e) (zero up to u_pad_to): the skip-connection tail of the SDF net
+// (fields.py:82-83) or of the NeRF field.  One thread per output element, so stores are coalesced.
 static __global__ void embed_rows_kernel(const float* __restrict__ x, int ldx, long long N, int d, int L, float scale,
                                   float* __restrict__ e, int lde, float* __restrict__ u, int ldu, int ucol,
                                   float uscale, int u_pad_to) {
-  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= N) return;
-  float* er = e ? e + m * lde : nullptr;
-  float* ur = u ? u + m * ldu + ucol : nullptr;
+  const int we = e ? lde : 0;
+  const int wu = u ? (u_pad_to - ucol) : 0;
+  const int wt = we + wu;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * wt) return;
+  const long long m = idx / wt;
+  int c = (int)(idx - m * wt);
+  const bool to_u = c >= we;
+  if (to_u) c -= we;
   const int d_e = d * (1 + 2 * L);
-  for (int j = 0; j < d; ++j) {
-    float y = x[m * ldx + j] * scale;
-    if (er) er[j] = y;
-    if (ur) ur[j] = y * uscale;
-    float f = 1.0f;
-    for (int k = 0; k < L; ++k) {
-      float s, c;
-      sincosf(y * f, &s, &c);
-      int cs = d + (2 * k) * d + j, cc = cs + d;
-      if (er) { er[cs] = s; er[cc] = c; }
-      if (ur) { ur[cs] = s * uscale; ur[cc] = c * uscale; }
-      f *= 2.0f;
+  float v = 0.0f;
+  if (c < d_e) {
+    if (c < d) {
+      v = x[m * ldx + c] * scale;
+    } else {
+      const int t = c - d, k = t / (2 * d), rem = t - k * 2 * d;
+      const float f = (float)(1 << k);
+      const float y = x[m * ldx + (rem < d ? rem : rem - d)] * scale;
+      v = rem < d ? sinf(y * f) : cosf(y * f);
     }
   }
-  if (er) for (int j = d_e; j < lde; ++j) er[j] = 0.0f;
-  if (ur) for (int j = ucol + d_e; j < u_pad_to; ++j) u[m * ldu + j] = 0.0f;
+  if (to_u) u[m * ldu + ucol + c] = v * uscale;
+  else e[m * lde + c] = v;
+}
+
+inline int launch_embed_rows(const float* x, int ldx, long long N, int d, int L, float scale, float* e, int lde, float* u,
+                             int ldu, int ucol, float uscale, int u_pad_to, cudaStream_t st) {
+  const long long wt = (e ? lde : 0) + (u ? (u_pad_to - ucol) : 0);
+  const long long total = N * wt;
+  if (total <= 0) return 0;
+  VDN_LAUNCH(embed_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, st, x, ldx, N, d, L, scale, e, lde, u, ldu, ucol,
+             uscale, u_pad_to);
+  return (int)cudaGetLastError();
 }
 
 // out[m, j] (+)= oscale * sum_c de[m,c] * d e_c / d y_j  (= J_e^T de), j < d.   de rows have ld ldde.

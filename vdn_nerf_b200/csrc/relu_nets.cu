@@ -124,10 +124,8 @@ extern "C" int vdn_rendernet_backward(const int* cfg, const float* packed, long 
                                 : make_operand(ZB[l & 1], c.ldH, ly.out_ld[l], ly.out_dim[l]);
     Operand u = (l == 0) ? make_operand(CIN, c.ldIn, c.ldIn, c.in0)
                          : make_operand(H + (long long)(l - 1) * N * c.ldH, c.ldH, ly.in_ld[l], ly.in_dim[l]);
-    int e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l],
-                         ly.in_ld[l], 1, st);
-    if (e) return e;
-    e = launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);
+    int e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l], ly.in_ld[l], 1,
+                             dpacked + ly.off_b[l], st);
     if (e) return e;
     if (l > 0) {
       Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(l - 1) & 1], c.ldH);
@@ -226,15 +224,13 @@ extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float
   NerfBlob b;
   carve_nerf(c, N, blob, &b);
   const int M = (int)N, D = c.D;
-  unsigned blocks = (unsigned)((N + 127) / 128);
   // pts embedding -> E and the tail of the skip buffer U.  The reference concatenates [input_pts, h]
   // (fields.py:334-335); the packed weight of the next layer has its columns rotated so U is [h | input_pts].
-  VDN_LAUNCH(embed_rows_kernel, blocks, 128, 0, st, pts, c.d_in, N, c.d_in, c.multires, 1.0f, b.E, c.ldE, b.U, c.ldU,
-             c.W, 1.0f, c.ldU);
+  int e = launch_embed_rows(pts, c.d_in, N, c.d_in, c.multires, 1.0f, b.E, c.ldE, b.U, c.ldU, c.W, 1.0f, c.ldU, st);
+  if (e) return e;
   // view embedding -> tail of VIN (reference fields.py:340: cat[feature, input_views])
-  VDN_LAUNCH(embed_rows_kernel, blocks, 128, 0, st, views, c.d_in_view, N, c.d_in_view, c.multires_view, 1.0f, nullptr, 0,
-                                            b.VIN, c.ldV, c.W, 1.0f, c.ldV);
-  int e = (int)cudaGetLastError();
+  e = launch_embed_rows(views, c.d_in_view, N, c.d_in_view, c.multires_view, 1.0f, nullptr, 0, b.VIN, c.ldV, c.W, 1.0f,
+                        c.ldV, st);
   if (e) return e;
   for (int i = 0; i < D; ++i) {
     Operand A = nerf_input(c, b, i);
@@ -305,10 +301,8 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
   float* partials = p;
   int e;
   auto wg = [&](int l, const Operand& zbar, const Operand& u) -> int {
-    int r = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l],
-                         ly.in_ld[l], 1, st);
-    if (r) return r;
-    return launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);
+    return launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l], ly.in_ld[l], 1,
+                            dpacked + ly.off_b[l], st);
   };
   // output heads
   {

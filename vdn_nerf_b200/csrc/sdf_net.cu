@@ -105,13 +105,9 @@ static Operand input_operand(const SdfCfg& c, const SdfBlob& b, int l) {
 }
 
 static int launch_embed(const SdfCfg& c, const float* x, long long N, const SdfBlob& b, cudaStream_t st) {
-  int threads = 128;
-  long long blocks = (N + threads - 1) / threads;
   int ucol = 0;
   if (c.skip >= 0) ucol = c.ly.in_dim[c.skip] - c.d_e;
-  VDN_LAUNCH(embed_rows_kernel, (unsigned)blocks, threads, 0, st, x, c.d_in, N, c.d_in, c.multires, c.scale, b.E, c.ldE, b.U,
-                                                         c.ldH, ucol, kInvSqrt2, c.ldH);
-  return (int)cudaGetLastError();
+  return launch_embed_rows(x, c.d_in, N, c.d_in, c.multires, c.scale, b.E, c.ldE, b.U, c.ldH, ucol, kInvSqrt2, c.ldH, st);
 }
 
 }  // namespace vdn
@@ -321,8 +317,8 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
       if (e) return e;
       // Wbar_l += delta_l^T qbar_l with delta_l = softplus'(z_l) * Gin_l recomputed on the fly
       Operand delta = make_operand(gi.p, gi.ld, ly.out_ld[l], ly.out_dim[l], PRO_DSIG, b.Z[l], c.ldH, gi.scale);
-      e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], delta, qbar, partials,
-                       dpacked + ly.off_w[l], ly.in_ld[l], 1, st);
+      e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], delta, qbar, partials, dpacked + ly.off_w[l], ly.in_ld[l], 1,
+                           nullptr, st);
       if (e) return e;
     }
     // a_{L-1} is the first row of the last weight: its cotangent is the column sum of Gin-bar_{L-2}
@@ -352,10 +348,8 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
     Operand zbar = (l == L - 1) ? make_operand(ZL, ly.out_ld[l], ly.out_ld[l], ly.out_dim[l])
                                 : make_operand(ZG[l], c.ldH, ly.out_ld[l], ly.out_dim[l]);
     Operand u = input_operand(c, b, l);
-    e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l],
-                     ly.in_ld[l], 1, st);
-    if (e) return e;
-    e = launch_colsum(M, ly.out_dim[l], zbar, partials, dpacked + ly.off_b[l], 1, st);
+    e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l], ly.in_ld[l], 1,
+                         dpacked + ly.off_b[l], st);
     if (e) return e;
     if (l > 0) {
       // ubar = zbar_l W_l restricted to the hidden part; epilogue -> zbar_{l-1}
