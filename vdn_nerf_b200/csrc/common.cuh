@@ -55,19 +55,37 @@ __device__ __forceinline__ float softplus100_d2(float z) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // MUFU-based, branch-free variants for the tensor-core mode, whose operands are rounded to tf32 (2^-11) anyway:
-// absolute error of softplus ~1e-8, relative error of its derivatives ~1e-6.  Branch-free matters: with a branch
-// per element the compiler serialises the MUFU chains and the operand producer becomes latency bound.
+// absolute error of softplus ~1e-8, relative error of its derivatives ~1e-6.  They are written with raw
+// ex2/lg2/rcp.approx.ftz and folded constants (8 / 4 / 7 instructions): per 128x32 operand block the tensor pipe
+// needs 512 cycles, i.e. 2048 issue slots of the SM - at the ~20 instructions per element of __expf/__logf the
+// element-wise work, not the MMA, bounds the kernel.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+constexpr float kBetaLog2e = 144.26950408889634f;          // 100 * log2(e)
+constexpr float kThrLog2e = 28.853900817779268f;           // 20 * log2(e)
+constexpr float kLn2OverBeta = 0.0069314718055994531f;     // ln(2) / 100
 __device__ __forceinline__ float softplus100_fast(float z) {
-  const float t = z * kSoftplusBeta;
-  const float s = __logf(1.0f + __expf(fminf(t, kSoftplusThreshold))) * (1.0f / kSoftplusBeta);
-  return t > kSoftplusThreshold ? z : s;
+  const float t = z * kBetaLog2e;
+  const float s = lg2_approx(1.0f + ex2_approx(fminf(t, kThrLog2e))) * kLn2OverBeta;
+  return t > kThrLog2e ? z : s;
 }
 // sigmoid(100 z); above the threshold 1/(1+e^-20) already rounds to 1.0f, matching the reference's branch
-__device__ __forceinline__ float softplus100_d1_fast(float z) {
-  return __fdividef(1.0f, 1.0f + __expf(-z * kSoftplusBeta));
-}
+__device__ __forceinline__ float softplus100_d1_fast(float z) { return rcp_approx(1.0f + ex2_approx(-z * kBetaLog2e)); }
 __device__ __forceinline__ float softplus100_d2_fast(float z) {
-  const float s = __fdividef(1.0f, 1.0f + __expf(-z * kSoftplusBeta));
+  const float s = rcp_approx(1.0f + ex2_approx(-z * kBetaLog2e));
   return kSoftplusBeta * s * (1.0f - s);
 }
 
