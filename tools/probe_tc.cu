@@ -210,6 +210,114 @@ static int run_gemm_mn(int N, int P, int sbo = 512) {
   return bad == 0 && st == 0 ? 0 : 1;
 }
 
+// D[128, N] = A[128, K] * B[N, K]^T with the A operand in TENSOR MEMORY (written with tcgen05.st), B in shared memory.
+__global__ void __launch_bounds__(128) probe_gemm_ts(const float* __restrict__ A, const float* __restrict__ B, int N, int K,
+                                                    float* __restrict__ D, int* __restrict__ status) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;   // 256 x 32 fp32 = 32 KB per K block
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { mbar_init(smem_u32(&bar_mma), 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tA = tmem_base + 256;   // A lives in columns [256, 256 + K)
+  // every thread owns one row of A: write it to TMEM, 32 columns at a time
+  for (int c0 = 0; c0 < K; c0 += 32) {
+    float v[32];
+    for (int j = 0; j < 32; ++j) v[j] = A[(warp * 32 + lane) * K + c0 + j];
+    tmem_st32(tA + ((uint32_t)(warp * 32) << 16) + c0, v);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  const uint32_t idesc = umma_idesc_tf32(128, N);
+  bool ok = true;
+  for (int kb = 0; kb < K / 32 && ok; ++kb) {
+    for (int i = tid; i < N * 32; i += 128) {
+      int r = i >> 5, k = i & 31;
+      *reinterpret_cast<float*>(sB + sw128_offset(r, k)) = B[r * K + kb * 32 + k];
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      for (int ks = 0; ks < 4; ++ks)
+        umma_tf32_ts(tmem_base, tA + kb * 32 + ks * 8, umma_desc_sw128(smem_u32(sB) + ks * 32), idesc, (kb | ks) ? 1u : 0u);
+      umma_commit(smem_u32(&bar_mma));
+    }
+    ok = mbar_wait(smem_u32(&bar_mma), kb & 1);
+    tc_fence_after();
+    __syncthreads();
+  }
+  if (!ok) {
+    if (tid == 0) status[0] = 1;
+  } else {
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      int r = warp * 32 + lane;
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < N) D[r * N + c0 + j] = v[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static int run_gemm_ts(int N, int K) {
+  std::vector<float> A(128 * K), B(256 * K), D(128 * N, -1.f), R(128 * N);
+  srand(4321 + N + K);
+  for (auto& v : A) v = (float)(rand() % 7 - 3);
+  for (auto& v : B) v = (float)(rand() % 7 - 3);
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = 0;
+      for (int k = 0; k < K; ++k) s += A[m * K + k] * B[n * K + k];
+      R[m * N + n] = s;
+    }
+  float *dA, *dB, *dD;
+  int* dS;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4)); CK(cudaMalloc(&dS, 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, D.size() * 4)); CK(cudaMemset(dS, 0, 4));
+  const int smem = 32768 + 1024;
+  probe_gemm_ts<<<1, 128, smem>>>(dA, dB, N, K, dD, dS);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("probe_gemm_ts N=%d K=%d: LAUNCH FAILED %s\n", N, K, cudaGetErrorString(e)); return 2; }
+  int st = 0;
+  CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0, first = -1;
+  double maxerr = 0;
+  for (size_t i = 0; i < D.size(); ++i) {
+    double er = fabs((double)D[i] - R[i]);
+    if (!(er <= 1e-3)) { if (first < 0) first = (int)i; ++bad; }
+    if (er > maxerr) maxerr = er;
+  }
+  printf("probe_gemm_ts (A in TMEM) N=%d K=%d: %s (timeout=%d, mismatches=%d/%zu, maxerr=%g", N, K,
+         (bad == 0 && st == 0) ? "PASS" : "FAIL", st, bad, D.size(), maxerr);
+  if (first >= 0) printf(", first bad (m=%d,n=%d) got %g want %g", first / N, first % N, D[first], R[first]);
+  printf(")\n");
+  if (bad)
+    for (int m : {0, 1, 32, 33}) {
+      printf("  row %d got:", m);
+      for (int n = 0; n < 6; ++n) printf(" %6.0f", D[m * N + n]);
+      printf("   want:");
+      for (int n = 0; n < 6; ++n) printf(" %6.0f", R[m * N + n]);
+      printf("\n");
+    }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dS);
+  return bad == 0 && st == 0 ? 0 : 1;
+}
+
 // Issue `iters` x 4 back-to-back MMAs (N=256, K=8 each) on fixed operands and report cycles per MMA.
 __global__ void __launch_bounds__(128) probe_rate(int iters, long long* cycles, int* status) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -314,6 +422,9 @@ int main() {
   fails += run_gemm(16, 64, 0, 1) != 0;
   fails += run_gemm(256, 64, 1, 1) != 0;
   fails += run_gemm(224, 256, 1, 1) != 0;
+  fails += run_gemm_ts(256, 32) != 0;
+  fails += run_gemm_ts(256, 256) != 0;
+  fails += run_gemm_ts(16, 64) != 0;
   fails += run_gemm_mn(256, 32) != 0;
   fails += run_gemm_mn(256, 128) != 0;
   fails += run_gemm_mn(64, 64) != 0;

@@ -5,13 +5,15 @@
 //   (renderer.py:369-370, 201) and by extract_fields (renderer.py:10-30, 446).
 //
 // Per CTA (persistent, one per SM, tiles of 128 points):
-//   * the activation tile A [128 x 256] lives in shared memory as eight SWIZZLE_128B K-blocks (128 KB);
-//   * weight tiles ([n x 32] pre-swizzled tf32 images, mlp_layout.cuh) stream through a 3-stage ring (96 KB),
+//   * the activation tile A [128 x 256] lives in TENSOR MEMORY (columns 256..511; lane = point, one column per
+//     feature) and is the A operand of the MMAs - with tf32 a 128x256x8 MMA would otherwise read 4 KB of A plus 8 KB
+//     of B from shared memory every 128 cycles, i.e. 75 % of the shared-memory port, before any staging traffic;
+//   * weight tiles ([n x 32] pre-swizzled tf32 images, mlp_layout.cuh) stream through a 6-stage ring (192 KB),
 //     fetched by one thread with cp.async.bulk (TMA engine) running ahead across layers and tiles;
-//   * one thread issues tcgen05.mma kind::tf32; the two 256-column TMEM accumulators alternate between layers;
-//   * eight warps run the epilogue of layer l (TMEM -> +bias -> softplus -> tf32 -> swizzled store into A) chunk by
-//     chunk (32 columns) and signal each finished K-block on its own mbarrier, so the MMAs of layer l+1 start
-//     while the epilogue of layer l is still running (the tensor pipe trails the epilogue by one chunk);
+//   * one thread issues tcgen05.mma kind::tf32 into the 256-column accumulator D (TMEM columns 0..255);
+//   * eight warps run the epilogue of layer l: drain D into registers (tcgen05.ld) and release it, then per 32-column
+//     chunk +bias -> softplus -> tf32 -> tcgen05.st into A, signalling each finished K-block on its own mbarrier, so
+//     the MMAs of layer l+1 start while the epilogue of layer l is still running;
 //   * the skip connection cat[h, e]/sqrt2 (fields.py:82-83) is formed in the epilogue of the preceding layer, the
 //     embedding e is recomputed from the point (no extra buffer);
 //   * in grid mode the lattice point is generated from its index (no point tensor in HBM).
@@ -22,10 +24,9 @@
 namespace vdn {
 
 constexpr int CH_THREADS = 320;     // warps 0-7: embedding + epilogue; warp 8: TMEM alloc + MMA issue; warp 9: weight stream
-constexpr int CH_WSTAGES = 3;
-constexpr uint32_t CH_A_BYTES = 8 * 16384;
+constexpr int CH_WSTAGES = 6;
 constexpr uint32_t CH_W_STAGE = 32768;
-constexpr size_t CH_SMEM = CH_A_BYTES + CH_WSTAGES * CH_W_STAGE + 1024;
+constexpr size_t CH_SMEM = CH_WSTAGES * CH_W_STAGE + 1024;
 
 struct ChainLayer {
   long long img_off, bias_off;   // float offsets into the packed buffer
@@ -53,72 +54,46 @@ static __device__ __noinline__ float chain_embed_col(float y0, float y1, float y
   return rem < 3 ? sinf(y[rem] * f) : cosf(y[rem - 3] * f);
 }
 
-// Chunk of 32 output columns that is not entirely real outputs: the tail of the layer before the skip connection
-// (remaining columns carry the embedding, fields.py:82-83) or zero padding.  Cold path, kept out of line.
-static __device__ __noinline__ void chain_ragged_chunk(uint32_t tacc, int n0, int n_mma, int out_dim, const float* bias,
-                                                       float osc, int d_e_tail, float y0, float y1, float y2,
-                                                       uint32_t abase, uint32_t r7) {
-  using namespace tc;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-  if (n0 < n_mma) {
-    tmem_ld32(tacc + (uint32_t)n0, v);
-    tmem_ld_wait();
-  }
-  for (int c4 = 0; c4 < 8; ++c4) {
-    float o[4];
-    for (int j = 0; j < 4; ++j) {
-      const int nn = n0 + c4 * 4 + j;
-      float r = 0.0f;
-      if (nn < out_dim) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 32; ++t) acc = (t == c4 * 4 + j) ? v[t] : acc;
-        r = softplus100_fast(acc + bias[nn]) * osc;
-      } else if (nn - out_dim < d_e_tail) {
-        r = chain_embed_col(y0, y1, y2, nn - out_dim) * osc;
-      }
-      o[j] = to_tf32(r);
-    }
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(abase + (((uint32_t)c4 ^ r7) << 4)), "f"(o[0]), "f"(o[1]),
-                 "f"(o[2]), "f"(o[3])
-                 : "memory");
-  }
+// One output element of a chunk that is not entirely real outputs: the tail of the layer before the skip connection
+// carries the embedding (fields.py:82-83), anything beyond is zero padding.  Cold path.
+static __device__ __noinline__ float chain_ragged_elem(float acc, int nn, int out_dim, const float* bias, float osc,
+                                                       int d_e_tail, float y0, float y1, float y2) {
+  if (nn < out_dim) return softplus100_fast(acc + bias[nn]) * osc;
+  if (nn - out_dim < d_e_tail) return chain_embed_col(y0, y1, y2, nn - out_dim) * osc;
+  return 0.0f;
 }
 
 static __global__ void __launch_bounds__(CH_THREADS, 1)
 sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_full[CH_WSTAGES], w_empty[CH_WSTAGES], a_ready[8], d_full[2];
+  __shared__ uint64_t w_full[CH_WSTAGES], w_empty[CH_WSTAGES], a_ready[8], d_full, d_drained;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = smem0, sW = smem0 + CH_A_BYTES;
+  const uint32_t sW = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const long long ntiles = (a.N + 127) / 128;
 
   if (tid == 0) {
     for (int s = 0; s < CH_WSTAGES; ++s) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
     for (int j = 0; j < 8; ++j) mbar_init(smem_u32(&a_ready[j]), 128);
-    mbar_init(smem_u32(&d_full[0]), 1);
-    mbar_init(smem_u32(&d_full[1]), 1);
+    mbar_init(smem_u32(&d_full), 1);
+    mbar_init(smem_u32(&d_drained), 256);
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = tmem_base_s;   // accumulator D: columns [0,256); activation tile A: columns [256,512)
   bool ok = true;
 
   if (warp < 8) {
     // ================= embedding + epilogue warps =================
     const int q = warp & 3, h = warp >> 2;           // TMEM lane quarter, column half
     const int row = q * 32 + lane;
-    const uint32_t rowoff = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
-    const uint32_t r7 = (uint32_t)(row & 7);
-    uint32_t dcnt0 = 0, dcnt1 = 0;                    // completions consumed of d_full[0], d_full[1]
+    const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t tA = tD + 256u;
+    uint32_t dcnt = 0;                                // completions of d_full consumed
     for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
       const long long m = tile * 128 + row;
       const bool valid = m < a.N;
@@ -134,98 +109,105 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
           y[0] = a.xs[i] * a.scale; y[1] = a.ys[j] * a.scale; y[2] = a.zs[k] * a.scale;
         }
       }
-      // ---- positional encoding -> K-block h of A (columns 32h .. 32h+31) ----
+      // ---- positional encoding -> K-block h of A (columns 32h .. 32h+31 of the activation tile in TMEM) ----
       {
-        const uint32_t base = sA + (uint32_t)h * 16384u + rowoff;
+        float v[32];
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = h * 32 + c4 * 4 + j;
-            v[j] = c < a.d_e ? to_tf32(chain_embed_col(y[0], y[1], y[2], c)) : 0.0f;
-          }
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((uint32_t)c4 ^ r7) << 4)), "f"(v[0]),
-                       "f"(v[1]), "f"(v[2]), "f"(v[3])
-                       : "memory");
+        for (int j = 0; j < 32; ++j) {
+          const int c = h * 32 + j;
+          v[j] = c < a.d_e ? to_tf32(chain_embed_col(y[0], y[1], y[2], c)) : 0.0f;
         }
-        fence_proxy_async();
+        tmem_st32(tA + (uint32_t)(h * 32), v);
+        tmem_st_wait();
+        tc_fence_before();
         mbar_arrive(smem_u32(&a_ready[h]));
       }
       // ---- layer epilogues ----
       for (int l = 0; l < a.L && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
-        const int acc = l & 1;
-        uint32_t& dc = acc ? dcnt1 : dcnt0;
-        ok = mbar_wait(smem_u32(&d_full[acc]), dc & 1);
-        ++dc;
+        ok = mbar_wait(smem_u32(&d_full), dcnt & 1);
+        ++dcnt;
         tc_fence_after();
-        const uint32_t tacc = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
         const float* bias = a.packed + Ly.bias_off;
         if (l == a.L - 1) {
           if (h == 0) {
             float v[32];
-            tmem_ld32(tacc, v);
+            tmem_ld32(tD, v);
             tmem_ld_wait();
             if (valid) a.out[m * a.lds] = (v[0] + bias[0]) * (a.out_mul / a.scale);
           }
           tc_fence_before();
+          mbar_arrive(smem_u32(&d_drained));
           continue;
         }
+        // drain this thread's four 32-column chunks of the accumulator into registers, then release D so the MMAs
+        // of the next layer may overwrite it while the activations are still being computed
+        float v0[32], v1[32], v2[32], v3[32];
+        tmem_ld32(tD + (uint32_t)((h + 0) * 32), v0);
+        tmem_ld32(tD + (uint32_t)((h + 2) * 32), v1);
+        tmem_ld32(tD + (uint32_t)((h + 4) * 32), v2);
+        tmem_ld32(tD + (uint32_t)((h + 6) * 32), v3);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&d_drained));
         const bool skip_next = (l + 1 == a.skip);
         const float osc = skip_next ? kInvSqrt2 : 1.0f;
-        for (int ch = h; ch < 8; ch += 2) {
+        const bool ragged = Ly.out_dim < 256;
+        const int d_e_tail = skip_next ? a.d_e : 0;
+        auto finish = [&](float (&v)[32], int ch) {
           const int n0 = ch * 32;
-          const uint32_t abase = sA + (uint32_t)ch * 16384u + rowoff;
-          if (n0 + 32 <= Ly.out_dim) {
-            // hot path: a full chunk of real outputs; bias loads are issued before waiting on the TMEM load
-            float v[32];
-            tmem_ld32(tacc + (uint32_t)n0, v);
-            float4 b[8];
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) b[c4] = __ldg(reinterpret_cast<const float4*>(bias + n0) + c4);
-            tmem_ld_wait();
+          if (!ragged) {
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
-              const float o0 = softplus100_fast(v[c4 * 4 + 0] + b[c4].x) * osc;
-              const float o1 = softplus100_fast(v[c4 * 4 + 1] + b[c4].y) * osc;
-              const float o2 = softplus100_fast(v[c4 * 4 + 2] + b[c4].z) * osc;
-              const float o3 = softplus100_fast(v[c4 * 4 + 3] + b[c4].w) * osc;
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(abase + (((uint32_t)c4 ^ r7) << 4)),
-                           "f"(to_tf32(o0)), "f"(to_tf32(o1)), "f"(to_tf32(o2)), "f"(to_tf32(o3))
-                           : "memory");
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0) + c4);
+              v[c4 * 4 + 0] = to_tf32(softplus100_fast(v[c4 * 4 + 0] + b.x) * osc);
+              v[c4 * 4 + 1] = to_tf32(softplus100_fast(v[c4 * 4 + 1] + b.y) * osc);
+              v[c4 * 4 + 2] = to_tf32(softplus100_fast(v[c4 * 4 + 2] + b.z) * osc);
+              v[c4 * 4 + 3] = to_tf32(softplus100_fast(v[c4 * 4 + 3] + b.w) * osc);
             }
           } else {
-            chain_ragged_chunk(tacc, n0, Ly.n_mma, Ly.out_dim, bias, osc, skip_next ? a.d_e : 0, y[0], y[1], y[2], abase, r7);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] = to_tf32(chain_ragged_elem(n0 + j < Ly.n_mma ? v[j] : 0.0f, n0 + j, Ly.out_dim, bias, osc, d_e_tail,
+                                               y[0], y[1], y[2]));
           }
-          fence_proxy_async();
+          tmem_st32(tA + (uint32_t)n0, v);
+          tmem_st_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&a_ready[ch]));
-        }
+        };
+        finish(v0, h + 0);
+        finish(v1, h + 2);
+        finish(v2, h + 4);
+        finish(v3, h + 6);
       }
     }
   } else if (tid == 8 * 32) {
-    // ================= MMA issuer =================
+    // ================= MMA issuer: A from tensor memory, weights from shared memory =================
     uint32_t acnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t wt = 0;   // weight tiles consumed
+    uint32_t wt = 0, drained = 0;
+    const uint32_t tAcol = tmem_base + 256u;
     for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
       for (int l = 0; l < a.L && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
         const uint32_t idesc = umma_idesc_tf32(128, (uint32_t)Ly.n_mma);
-        const uint32_t dacc = tmem_base + (uint32_t)(l & 1) * 256u;
+        // the accumulator of the previous layer must have been drained (first layer ever: passes immediately)
+        ok = mbar_wait(smem_u32(&d_drained), (drained & 1) ^ 1);
+        ++drained;
         for (int kb = 0; kb < Ly.nkb && ok; ++kb, ++wt) {
           const uint32_t ws = wt % CH_WSTAGES, wph = (wt / CH_WSTAGES) & 1;
           ok = mbar_wait(smem_u32(&w_full[ws]), wph);
           ok = ok && mbar_wait(smem_u32(&a_ready[kb]), acnt[kb] & 1);
           ++acnt[kb];
           tc_fence_after();
-          const uint32_t a0 = sA + (uint32_t)kb * 16384u, b0 = sW + ws * CH_W_STAGE;
+          const uint32_t b0 = sW + ws * CH_W_STAGE;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(dacc, umma_desc_sw128(a0 + ks * 32), umma_desc_sw128(b0 + ks * 32), idesc, (kb | ks) ? 1u : 0u);
+            umma_tf32_ts(tmem_base, tAcol + (uint32_t)(kb * 32 + ks * 8), umma_desc_sw128(b0 + ks * 32), idesc,
+                         (kb | ks) ? 1u : 0u);
           umma_commit(smem_u32(&w_empty[ws]));
         }
-        umma_commit(smem_u32(&d_full[l & 1]));
+        umma_commit(smem_u32(&d_full));
       }
     }
   } else if (tid == 9 * 32) {
