@@ -78,9 +78,10 @@ constexpr float kBetaLog2e = 144.26950408889634f;          // 100 * log2(e)
 constexpr float kThrLog2e = 28.853900817779268f;           // 20 * log2(e)
 constexpr float kLn2OverBeta = 0.0069314718055994531f;     // ln(2) / 100
 __device__ __forceinline__ float softplus100_fast(float z) {
-  const float t = z * kBetaLog2e;
-  const float s = lg2_approx(1.0f + ex2_approx(fminf(t, kThrLog2e))) * kLn2OverBeta;
-  return t > kThrLog2e ? z : s;
+  // softplus(z) >= z everywhere and the clamped branch never exceeds z above the clamp, so max() selects exactly
+  // like the reference's threshold (7 instructions)
+  const float s = lg2_approx(1.0f + ex2_approx(fminf(z * kBetaLog2e, kThrLog2e))) * kLn2OverBeta;
+  return fmaxf(z, s);
 }
 // sigmoid(100 z); above the threshold 1/(1+e^-20) already rounds to 1.0f, matching the reference's branch
 __device__ __forceinline__ float softplus100_d1_fast(float z) { return rcp_approx(1.0f + ex2_approx(-z * kBetaLog2e)); }

@@ -11,7 +11,7 @@
 //   * weight tiles ([n x 32] pre-swizzled tf32 images, mlp_layout.cuh) stream through a 6-stage ring (192 KB),
 //     fetched by one thread with cp.async.bulk (TMA engine) running ahead across layers and tiles;
 //   * one thread issues tcgen05.mma kind::tf32 into the 256-column accumulator D (TMEM columns 0..255);
-//   * eight warps run the epilogue of layer l: drain D into registers (tcgen05.ld) and release it, then per 32-column
+//   * sixteen warps run the epilogue of layer l: drain D into registers (tcgen05.ld) and release it, then per 32-column
 //     chunk +bias -> softplus -> tf32 -> tcgen05.st into A, signalling each finished K-block on its own mbarrier, so
 //     the MMAs of layer l+1 start while the epilogue of layer l is still running;
 //   * the skip connection cat[h, e]/sqrt2 (fields.py:82-83) is formed in the epilogue of the preceding layer, the
@@ -23,7 +23,8 @@
 
 namespace vdn {
 
-constexpr int CH_THREADS = 320;     // warps 0-7: embedding + epilogue; warp 8: TMEM alloc + MMA issue; warp 9: weight stream
+constexpr int CH_EPI_WARPS = 16;    // four warps per scheduler: the epilogue is latency bound with fewer
+constexpr int CH_THREADS = (CH_EPI_WARPS + 2) * 32;   // + warp 16: TMEM alloc + MMA issue; warp 17: weight stream
 constexpr int CH_WSTAGES = 6;
 constexpr uint32_t CH_W_STAGE = 32768;
 constexpr size_t CH_SMEM = CH_WSTAGES * CH_W_STAGE + 1024;
@@ -77,19 +78,19 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
     for (int s = 0; s < CH_WSTAGES; ++s) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
     for (int j = 0; j < 8; ++j) mbar_init(smem_u32(&a_ready[j]), 128);
     mbar_init(smem_u32(&d_full), 1);
-    mbar_init(smem_u32(&d_drained), 256);
+    mbar_init(smem_u32(&d_drained), CH_EPI_WARPS * 32);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (warp == CH_EPI_WARPS) tmem_alloc(smem_u32(&tmem_base_s), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;   // accumulator D: columns [0,256); activation tile A: columns [256,512)
   bool ok = true;
 
-  if (warp < 8) {
+  if (warp < CH_EPI_WARPS) {
     // ================= embedding + epilogue warps =================
-    const int q = warp & 3, h = warp >> 2;           // TMEM lane quarter, column half
+    const int q = warp & 3, h = warp >> 2;           // TMEM lane quarter, column group (chunks h and h+4)
     const int row = q * 32 + lane;
     const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t tA = tD + 256u;
@@ -110,7 +111,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
         }
       }
       // ---- positional encoding -> K-block h of A (columns 32h .. 32h+31 of the activation tile in TMEM) ----
-      {
+      if (h < 2) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -142,11 +143,9 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
         }
         // drain this thread's four 32-column chunks of the accumulator into registers, then release D so the MMAs
         // of the next layer may overwrite it while the activations are still being computed
-        float v0[32], v1[32], v2[32], v3[32];
+        float v0[32], v1[32];
         tmem_ld32(tD + (uint32_t)((h + 0) * 32), v0);
-        tmem_ld32(tD + (uint32_t)((h + 2) * 32), v1);
-        tmem_ld32(tD + (uint32_t)((h + 4) * 32), v2);
-        tmem_ld32(tD + (uint32_t)((h + 6) * 32), v3);
+        tmem_ld32(tD + (uint32_t)((h + 4) * 32), v1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(&d_drained));
@@ -177,12 +176,10 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
           mbar_arrive(smem_u32(&a_ready[ch]));
         };
         finish(v0, h + 0);
-        finish(v1, h + 2);
-        finish(v2, h + 4);
-        finish(v3, h + 6);
+        finish(v1, h + 4);
       }
     }
-  } else if (tid == 8 * 32) {
+  } else if (tid == CH_EPI_WARPS * 32) {
     // ================= MMA issuer: A from tensor memory, weights from shared memory =================
     uint32_t acnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t wt = 0, drained = 0;
@@ -210,7 +207,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
         umma_commit(smem_u32(&d_full));
       }
     }
-  } else if (tid == 9 * 32) {
+  } else if (tid == (CH_EPI_WARPS + 1) * 32) {
     // ================= weight stream (TMA engine) =================
     uint32_t wt = 0;
     for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
@@ -229,7 +226,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
   if (!ok && fault) *fault = 1;
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 512);
+  if (warp == CH_EPI_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
 // Returns -1 when the configuration is not supported by the fused chain (caller falls back to the layer-wise path).
