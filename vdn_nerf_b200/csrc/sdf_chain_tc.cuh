@@ -11,9 +11,9 @@
 //   * weight tiles ([n x 32] pre-swizzled tf32 images, mlp_layout.cuh) stream through a 6-stage ring (192 KB),
 //     fetched by one thread with cp.async.bulk (TMA engine) running ahead across layers and tiles;
 //   * one thread issues tcgen05.mma kind::tf32 into the 256-column accumulator D (TMEM columns 0..255);
-//   * sixteen warps run the epilogue of layer l: drain D into registers (tcgen05.ld) and release it, then per 32-column
-//     chunk +bias -> softplus -> tf32 -> tcgen05.st into A, signalling each finished K-block on its own mbarrier, so
-//     the MMAs of layer l+1 start while the epilogue of layer l is still running;
+//   * sixteen warps run the epilogue of layer l: drain D into registers (tcgen05.ld) and release it, then - all warps
+//     on the same 32-column chunk, chunk after chunk - +bias -> softplus -> tf32 -> tcgen05.st into A, signalling each
+//     finished K-block on its own mbarrier, so the MMAs of layer l+1 trail the epilogue of layer l by one chunk;
 //   * the skip connection cat[h, e]/sqrt2 (fields.py:82-83) is formed in the epilogue of the preceding layer, the
 //     embedding e is recomputed from the point (no extra buffer);
 //   * in grid mode the lattice point is generated from its index (no point tensor in HBM).
@@ -76,7 +76,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
 
   if (tid == 0) {
     for (int s = 0; s < CH_WSTAGES; ++s) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
-    for (int j = 0; j < 8; ++j) mbar_init(smem_u32(&a_ready[j]), 128);
+    for (int j = 0; j < 8; ++j) mbar_init(smem_u32(&a_ready[j]), CH_EPI_WARPS * 32);
     mbar_init(smem_u32(&d_full), 1);
     mbar_init(smem_u32(&d_drained), CH_EPI_WARPS * 32);
     mbar_fence_init();
@@ -90,9 +90,12 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
 
   if (warp < CH_EPI_WARPS) {
     // ================= embedding + epilogue warps =================
-    const int q = warp & 3, h = warp >> 2;           // TMEM lane quarter, column group (chunks h and h+4)
+    // warp (q, h): TMEM lane quarter q (rows 32q..32q+31), columns [32 ch + 8 h, +8) of every 32-column chunk ch.
+    // All sixteen warps work on the same chunk, chunk after chunk, so K-block ch of the next layer's operand is
+    // complete after 1/8 of the epilogue and the tensor pipe trails the epilogue by one chunk.
+    const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
-    const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 8);
     const uint32_t tA = tD + 256u;
     uint32_t dcnt = 0;                                // completions of d_full consumed
     for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
@@ -110,18 +113,19 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
           y[0] = a.xs[i] * a.scale; y[1] = a.ys[j] * a.scale; y[2] = a.zs[k] * a.scale;
         }
       }
-      // ---- positional encoding -> K-block h of A (columns 32h .. 32h+31 of the activation tile in TMEM) ----
-      if (h < 2) {
-        float v[32];
+      // ---- positional encoding -> K-blocks 0 and 1 of A (activation tile in TMEM) ----
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = h * 32 + j;
+      for (int ch = 0; ch < 2; ++ch) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = ch * 32 + h * 8 + j;
           v[j] = c < a.d_e ? to_tf32(chain_embed_col(y[0], y[1], y[2], c)) : 0.0f;
         }
-        tmem_st32(tA + (uint32_t)(h * 32), v);
+        tmem_st8(tA + (uint32_t)(ch * 32), v);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(smem_u32(&a_ready[h]));
+        mbar_arrive(smem_u32(&a_ready[ch]));
       }
       // ---- layer epilogues ----
       for (int l = 0; l < a.L && ok; ++l) {
@@ -132,8 +136,8 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
         const float* bias = a.packed + Ly.bias_off;
         if (l == a.L - 1) {
           if (h == 0) {
-            float v[32];
-            tmem_ld32(tD, v);
+            float v[8];
+            tmem_ld8(tD, v);
             tmem_ld_wait();
             if (valid) a.out[m * a.lds] = (v[0] + bias[0]) * (a.out_mul / a.scale);
           }
@@ -141,42 +145,42 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
           mbar_arrive(smem_u32(&d_drained));
           continue;
         }
-        // drain this thread's four 32-column chunks of the accumulator into registers, then release D so the MMAs
-        // of the next layer may overwrite it while the activations are still being computed
-        float v0[32], v1[32];
-        tmem_ld32(tD + (uint32_t)((h + 0) * 32), v0);
-        tmem_ld32(tD + (uint32_t)((h + 4) * 32), v1);
+        // drain this thread's 8 x 8 accumulator columns into registers, then release D so the MMAs of the next layer
+        // may overwrite it while the activations are still being computed
+        float v[8][8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) tmem_ld8(tD + (uint32_t)(ch * 32), v[ch]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(&d_drained));
         const bool skip_next = (l + 1 == a.skip);
         const float osc = skip_next ? kInvSqrt2 : 1.0f;
-        const bool ragged = Ly.out_dim < 256;
         const int d_e_tail = skip_next ? a.d_e : 0;
-        auto finish = [&](float (&v)[32], int ch) {
-          const int n0 = ch * 32;
-          if (!ragged) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0) + c4);
-              v[c4 * 4 + 0] = to_tf32(softplus100_fast(v[c4 * 4 + 0] + b.x) * osc);
-              v[c4 * 4 + 1] = to_tf32(softplus100_fast(v[c4 * 4 + 1] + b.y) * osc);
-              v[c4 * 4 + 2] = to_tf32(softplus100_fast(v[c4 * 4 + 2] + b.z) * osc);
-              v[c4 * 4 + 3] = to_tf32(softplus100_fast(v[c4 * 4 + 3] + b.w) * osc);
-            }
-          } else {
+        for (int ch = 0; ch < 8; ++ch) {
+          const int n0 = ch * 32 + h * 8;
+          if (ch * 32 + 32 <= Ly.out_dim) {      // chunk of real outputs (uniform over the CTA)
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
+            v[ch][0] = to_tf32(softplus100_fast(v[ch][0] + b0.x) * osc);
+            v[ch][1] = to_tf32(softplus100_fast(v[ch][1] + b0.y) * osc);
+            v[ch][2] = to_tf32(softplus100_fast(v[ch][2] + b0.z) * osc);
+            v[ch][3] = to_tf32(softplus100_fast(v[ch][3] + b0.w) * osc);
+            v[ch][4] = to_tf32(softplus100_fast(v[ch][4] + b1.x) * osc);
+            v[ch][5] = to_tf32(softplus100_fast(v[ch][5] + b1.y) * osc);
+            v[ch][6] = to_tf32(softplus100_fast(v[ch][6] + b1.z) * osc);
+            v[ch][7] = to_tf32(softplus100_fast(v[ch][7] + b1.w) * osc);
+          } else {                                // tail of the layer before the skip connection / zero padding
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = to_tf32(chain_ragged_elem(n0 + j < Ly.n_mma ? v[j] : 0.0f, n0 + j, Ly.out_dim, bias, osc, d_e_tail,
-                                               y[0], y[1], y[2]));
+            for (int j = 0; j < 8; ++j)
+              v[ch][j] = to_tf32(chain_ragged_elem(n0 + j < Ly.n_mma ? v[ch][j] : 0.0f, n0 + j, Ly.out_dim, bias, osc,
+                                                   d_e_tail, y[0], y[1], y[2]));
           }
-          tmem_st32(tA + (uint32_t)n0, v);
+          tmem_st8(tA + (uint32_t)(ch * 32), v[ch]);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&a_ready[ch]));
-        };
-        finish(v0, h + 0);
-        finish(v1, h + 4);
+        }
       }
     }
   } else if (tid == CH_EPI_WARPS * 32) {
