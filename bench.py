@@ -276,13 +276,14 @@ def run_ours(args):
         lib.vdn_prof_enable(0)
         local_pts = float(hi - lo) * res * res
         ach = 2.0 * F_SDF1 * local_pts / (fam_ms * 1e-3) / 1e12
-        kname = "gemm_nt_tc_kernel (tcgen05 kind::tf32)" if args.precision == "tf32" else "gemm_nt_kernel (FFMA)"
+        kname = ("sdf_chain_tc_kernel (fused PE + 9-layer tcgen05 kind::tf32 chain, 1 launch per slab)"
+                 if args.precision == "tf32" else "gemm_nt_kernel (FFMA), 9 launches per slab")
         line.update({"metric": "sdf_grid_pts_per_s", "unit": "pts/s", "value": value, "ms_per_step": ms / args.steps,
                      "config": {"workload": "extract_fields SDF grid query, womsk_white SDF net, x-slabs per rank",
                                 "resolution": res, "l2": "256 MiB flush between timed iterations", "mode": args.precision},
                      "e2e": {"value": pts / e2e_t, "unit": "pts/s", "h2d_bytes_per_step": 3 * res * 4,
                              "d2h_bytes_per_step": int(local_pts * 4)},
-                     "roofline": {"bound": "tensor", "kernel": kname + ", 9 launches per slab",
+                     "roofline": {"bound": "tensor", "kernel": kname,
                                   "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                                   "frac": ach / pk["bf16_sustained"], "traffic": None,
                                   "peak_source": pk["source"] + " bf16 sustained (dense tf32 peak is half of it)",
