@@ -4,16 +4,19 @@
 // [32 points x 32 features] in the SWIZZLE_128B_BASE32B image (rows = points; the only layout tf32 supports for
 // MN-major operands), read by the tensor core with K = points.  One CTA owns 128 output rows (n) x up to 256 output columns (k) and a contiguous
 // split of the batch; its accumulator stays in TMEM for the whole split and is written once, as a partial slab
-// that reduce_partials_kernel sums deterministically.  Eight producer warps transform both operands (coalesced
-// loads -> prologue -> tf32 round -> swizzled store), one thread issues the MMAs, a 2-stage mbarrier ring
-// connects them, two CTAs share an SM.
+// that reduce_partials_kernel sums deterministically (or, in the training path, added straight into dW with fp32
+// atomics).  Sixteen producer warps transform both operands (coalesced loads two stages ahead in registers ->
+// prologue -> tf32 round -> swizzled store), one thread issues the MMAs, a 4-stage mbarrier ring connects them;
+// one CTA per SM, (output tiles x batch splits) sized to one wave over the 148 SMs.
 #pragma once
 #include "gemm_tc.cuh"
 
 namespace vdn {
 
-constexpr int TN_THREADS = 320;   // warps 0-7 producers + epilogue, warp 8 MMA issuer, warp 9 TMEM allocation
+constexpr int TN_PWARPS = 16;     // producer (+ epilogue) warps
+constexpr int TN_THREADS = TN_PWARPS * 32;         // warp 0 also allocates TMEM and issues the MMAs (one stage behind)
 constexpr int TN_P = 32;          // points per pipeline stage
+constexpr int TN_STAGES = 4;
 constexpr uint32_t TN_TILE = 4096;                 // bytes of one [32 x 32] tile
 constexpr uint32_t TN_STAGE = 12 * TN_TILE;        // 4 tiles of A (128 n) + 8 tiles of X (256 k)
 
@@ -27,12 +30,17 @@ __device__ __forceinline__ float4 tn_pro4(int kind, float scale, float4 a, float
   }
 }
 
-static __global__ void __launch_bounds__(TN_THREADS, 2)
+// Raw operand slices of one pipeline stage held by one producer thread (global loads run two stages ahead).
+struct TnRaw {
+  float4 a[2], b[2], x[4];
+};
+
+static __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__ P, int ldp, int rows_per_split,
                   int atomic_out, float* __restrict__ db, int* __restrict__ fault) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[2], bar_empty[2], bar_acc;
+  __shared__ uint64_t bar_full[TN_STAGES], bar_empty[TN_STAGES], bar_acc;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * 128;
@@ -47,53 +55,77 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 256);
+    for (int s = 0; s < TN_STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), TN_PWARPS * 32);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
     mbar_fence_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(&tmem_base_s), 256);
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   bool ok = true;
 
-  if (warp < 8) {
-    // ---- producers: warp w owns rows (points) 4w..4w+3 of every tile; a warp instruction covers 4 rows x 128 B ----
-    const int chunk = lane & 7;
-    const uint32_t r = (uint32_t)(warp * 4 + (lane >> 3));   // point row inside the stage, 0..31
+  {
+    // ---- producers: warp w owns rows (points) 4(w%8)..+3 of half (w/8) of the stage's tiles (A tiles 2h,2h+1; X tiles
+    // 4h..4h+3); a warp instruction covers 4 rows x 128 B.  Global loads run two stages ahead of their use. ----
+    const int chunk = lane & 7, hh = warp >> 3;
+    const uint32_t r = (uint32_t)((warp & 7) * 4 + (lane >> 3));   // point row inside the stage, 0..31
     // SWIZZLE_128B_BASE32B image: 4-row groups of 512 B, 32-byte blocks of row r permuted by (r % 4)
     const uint32_t soff = (r >> 2) * 512u + (r & 3u) * 128u + (((((uint32_t)chunk >> 1) ^ r) & 3u) << 5) +
                           (((uint32_t)chunk & 1u) << 4);
     const bool twoA = A.kind >= PRO_DSIG;   // the X side only takes single-operand prologues (none / softplus)
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ca0 = n0 + (2 * hh) * 32 + chunk * 4;     // first A column of this thread (tile t: + 32 t)
+    const int cx0 = k0 + (4 * hh) * 32 + chunk * 4;     // first X column
     // fused bias gradient: column sums of the A side (db[n] += sum_m A[m,n]) ride along for free
     const bool do_bias = db != nullptr && blockIdx.z == 0;
-    float4 bsum[4] = {zero4, zero4, zero4, zero4};
-    for (int st = 0; st < nst && ok; ++st) {
-      const int s = st & 1, ph = (st >> 1) & 1;
+    float4 bsum[2] = {zero4, zero4};
+    auto gload = [&](int st, TnRaw& R) {
       const int m = mbeg + st * TN_P + (int)r;
       const bool rok = m < mend;
-      float4 va[4], vx[8];
-      // A side: n columns n0 + 32 t + 4 chunk
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int c = n0 + t * 32 + chunk * 4;
-        float4 a = zero4, b = zero4;
-        if (rok && c < A.width) {
-          a = *reinterpret_cast<const float4*>(A.p + (size_t)m * A.ld + c);
-          if (twoA) b = *reinterpret_cast<const float4*>(A.p2 + (size_t)m * A.ld2 + c);
-        }
-        va[t] = a;
-        if (twoA) vx[t] = b;   // borrow vx as scratch for the second operand of the A side
+      for (int t = 0; t < 2; ++t) {
+        const int c = ca0 + t * 32;
+        const bool p = rok && c < A.width;
+        R.a[t] = p ? *reinterpret_cast<const float4*>(A.p + (size_t)m * A.ld + c) : zero4;
+        R.b[t] = (p && twoA) ? *reinterpret_cast<const float4*>(A.p2 + (size_t)m * A.ld2 + c) : zero4;
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const int c = n0 + t * 32 + chunk * 4;
-        float4 v = tn_pro4(A.kind, A.scale, va[t], vx[t]);
+        const int c = cx0 + t * 32;
+        const bool p = (4 * hh + t < nxt) && rok && c < X.width;
+        R.x[t] = p ? *reinterpret_cast<const float4*>(X.p + (size_t)m * X.ld + c) : zero4;
+      }
+    };
+    // MMA issue (warp 0 only, one stage behind its own production): 4 MMAs (8 points each) per stage, both operands
+    // MN-major
+    const uint32_t idesc = umma_idesc_tf32_mn(128, (uint32_t)k_mma);
+    auto issue = [&](int st) {
+      const int s = st % TN_STAGES, ph = (st / TN_STAGES) & 1;
+      ok = mbar_wait(smem_u32(&bar_full[s]), ph) && ok;
+      tc_fence_after();
+      if (lane == 0 && ok) {
+        const uint32_t a0 = smem0 + (uint32_t)s * TN_STAGE, x0 = a0 + 4 * TN_TILE;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          umma_tf32(tmem_base, umma_desc_sw128_mn(a0 + g * 1024, TN_TILE, 512), umma_desc_sw128_mn(x0 + g * 1024, TN_TILE, 512),
+                    idesc, (st | g) ? 1u : 0u);
+        umma_commit(smem_u32(&bar_empty[s]));
+      }
+      __syncwarp();
+    };
+    auto produce = [&](int st, TnRaw& R) {
+      const int s = st % TN_STAGES, ph = (st / TN_STAGES) & 1;
+      const bool rok = mbeg + st * TN_P + (int)r < mend;
+      float4 va[2], vx[4];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = ca0 + t * 32;
+        float4 v = tn_pro4(A.kind, A.scale, R.a[t], R.b[t]);
         if (!rok || c >= A.width) v = zero4;
         if (c + 0 >= A.kvalid) v.x = 0.f;
         if (c + 1 >= A.kvalid) v.y = 0.f;
@@ -102,44 +134,50 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
         bsum[t] = f4_add(bsum[t], v);
         va[t] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
       }
-      // X side: k columns k0 + 32 t + 4 chunk
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int c = k0 + t * 32 + chunk * 4;
-        float4 a = zero4;
-        if (t < nxt && rok && c < X.width) a = *reinterpret_cast<const float4*>(X.p + (size_t)m * X.ld + c);
-        vx[t] = a;
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int c = k0 + t * 32 + chunk * 4;
-        float4 v = (X.kind == PRO_SOFTPLUS) ? f4_map_sp(vx[t]) : vx[t];
-        if (!(t < nxt && rok && c < X.width)) v = zero4;
+      for (int t = 0; t < 4; ++t) {
+        const int c = cx0 + t * 32;
+        float4 v = (X.kind == PRO_SOFTPLUS) ? f4_map_sp(R.x[t]) : R.x[t];
+        if (!((4 * hh + t < nxt) && rok && c < X.width)) v = zero4;
         if (c + 0 >= X.kvalid) v.x = 0.f;
         if (c + 1 >= X.kvalid) v.y = 0.f;
         if (c + 2 >= X.kvalid) v.z = 0.f;
         if (c + 3 >= X.kvalid) v.w = 0.f;
         vx[t] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
       }
+      if (st + 2 < nst) gload(st + 2, R);              // refill the register buffer just consumed
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
       const uint32_t base = smem0 + (uint32_t)s * TN_STAGE + soff;
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)t * TN_TILE), "f"(va[t].x),
+      for (int t = 0; t < 2; ++t)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(2 * hh + t) * TN_TILE), "f"(va[t].x),
                      "f"(va[t].y), "f"(va[t].z), "f"(va[t].w)
                      : "memory");
 #pragma unroll
-      for (int t = 0; t < 8; ++t)
-        if (t < nxt)
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(4 + t) * TN_TILE),
+      for (int t = 0; t < 4; ++t)
+        if (4 * hh + t < nxt)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(4 + 4 * hh + t) * TN_TILE),
                        "f"(vx[t].x), "f"(vx[t].y), "f"(vx[t].z), "f"(vx[t].w)
                        : "memory");
       fence_proxy_async();
       mbar_arrive(smem_u32(&bar_full[s]));
+      if (warp == 0 && st > 0 && ok) issue(st - 1);
+    };
+    TnRaw R0, R1;
+    if (nst > 0) gload(0, R0);
+    if (nst > 1) gload(1, R1);
+    for (int st = 0; st < nst && ok; st += 2) {
+      produce(st, R0);
+      if (st + 1 < nst && ok) produce(st + 1, R1);
+    }
+    if (warp == 0) {
+      if (nst > 0 && ok) issue(nst - 1);
+      if (lane == 0) umma_commit(smem_u32(&bar_acc));
+      __syncwarp();
     }
     if (do_bias) {   // reduce over the 4 row lanes of the warp, then one atomic per column and warp
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < 2; ++t) {
         float4 v = bsum[t];
 #pragma unroll
         for (int off = 8; off <= 16; off <<= 1) {
@@ -148,7 +186,7 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
           v.z += __shfl_xor_sync(0xffffffffu, v.z, off);
           v.w += __shfl_xor_sync(0xffffffffu, v.w, off);
         }
-        const int n = n0 + t * 32 + chunk * 4;
+        const int n = ca0 + t * 32;
         if ((lane >> 3) == 0) {
           if (n + 0 < N) atomicAdd(db + n + 0, v.x);
           if (n + 1 < N) atomicAdd(db + n + 1, v.y);
@@ -157,25 +195,10 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
         }
       }
     }
-  } else if (tid == 8 * 32) {
-    // ---- MMA issuer: 4 MMAs (8 points each) per stage, both operands MN-major ------------------------------
-    const uint32_t idesc = umma_idesc_tf32_mn(128, (uint32_t)k_mma);
-    for (int st = 0; st < nst && ok; ++st) {
-      const int s = st & 1, ph = (st >> 1) & 1;
-      ok = mbar_wait(smem_u32(&bar_full[s]), ph);
-      tc_fence_after();
-      const uint32_t a0 = smem0 + (uint32_t)s * TN_STAGE, x0 = a0 + 4 * TN_TILE;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        umma_tf32(tmem_base, umma_desc_sw128_mn(a0 + g * 1024, TN_TILE, 512), umma_desc_sw128_mn(x0 + g * 1024, TN_TILE, 512),
-                  idesc, (st | g) ? 1u : 0u);
-      umma_commit(smem_u32(&bar_empty[s]));
-    }
-    umma_commit(smem_u32(&bar_acc));
   }
-  // ---- epilogue: the eight producer warps write the partial tile ----------------------------------------------
+  // ---- epilogue: the producer warps write the partial tile ----------------------------------------------
   __syncwarp();
-  if (warp < 8) {
+  {
     uint32_t spins = 0;
     while (!mbar_try_wait(smem_u32(&bar_acc), 0)) {
       __nanosleep(100);
@@ -183,7 +206,7 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
     }
     tc_fence_after();
     if (ok) {
-      const int q = warp & 3, half = warp >> 2;
+      const int q = warp & 3, cset = warp >> 2;
       const int nch = (kt + 31) >> 5;
       const uint32_t stg = smem0 + (uint32_t)warp * 4096u;
       const int g = lane & 7;
@@ -191,7 +214,7 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
       // atomic_out: every split adds its tile straight into the gradient matrix (red.global.add, no partial slabs)
       float* Ps = atomic_out ? P : P + (size_t)split * N * ldp;
       const bool skip_all = atomic_out && nst == 0;   // an empty split has nothing to add
-      for (int ch = half; ch < nch && !skip_all; ch += 2) {
+      for (int ch = cset; ch < nch && !skip_all; ch += TN_PWARPS / 4) {
         float v[32];
         if (nst > 0) {
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
@@ -246,14 +269,16 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-// Row splits of the batch for the tensor-core weight gradient (also sizes the partial slabs).
-inline int wgrad_splits_tc(int M) {
-  int s = (M + 511) / 512;
+// Row splits of the batch for the tensor-core weight gradient: one wave of (output tiles x splits) CTAs over the
+// 148 SMs, at least 128 points per split.  tiles = 1 gives the upper bound used to size the partial slabs.
+inline int wgrad_splits_tc(int M, int tiles = 1) {
+  int s = 148 / (tiles < 1 ? 1 : tiles);
+  const int cap = (M + 127) / 128;
+  if (s > cap) s = cap;
   if (s < 1) s = 1;
-  if (s > 256) s = 256;
   return s;
 }
 
@@ -262,11 +287,11 @@ inline int wgrad_splits_tc(int M) {
 // `accumulate` must be 1 (the packed gradient buffer is zero-initialised by the caller).
 static inline int launch_wgrad_tc(int M, int N, int K, const Operand& A0, const Operand& X0, float* partials, float* dW,
                                   int ldd, int accumulate, float* db, cudaStream_t st) {
-  const int S = wgrad_splits_tc(M);
+  const int S = wgrad_splits_tc(M, ((N + 127) / 128) * ((K + 255) / 256));
   int rows = (M + S - 1) / S;
   rows = (rows + TN_P - 1) / TN_P * TN_P;
   static bool attr_set = false;
-  const size_t smem = 2 * TN_STAGE + 1024;
+  const size_t smem = TN_STAGES * TN_STAGE + 1024;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
