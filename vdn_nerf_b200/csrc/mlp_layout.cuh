@@ -7,6 +7,8 @@
 //   IW_l   [ceil(in_dim/32)][out_ld][32]   W_l  as tcgen05 operand tiles: per 32-column K block, the rows in the
 //   IWT_l  [ceil(out_dim/32)][in_ld][32]   W_l^T  SWIZZLE_128B K-major shared-memory image (tc_common.cuh), values
 //                                          rounded to tf32 - one linear cp.async.bulk per tile, no tensor map
+//   IH_l   [ceil(in_dim/64)][out_ld][64 halfs]   W_l rounded to fp16 (10-bit mantissa like tf32), same K-major
+//                                          SWIZZLE_128B image with 64-element K blocks, for the kind::f16 chain kernel
 // with in_ld = round_up(in_dim, 16), out_ld = round_up(out_dim, 16).  The gradient buffer of a network uses
 // the W and b regions of the same layout, so weight-norm backward is one kernel over the whole network.
 // A layer may rotate its input columns (rot): packed column (c - rot) mod in_dim holds source column c; the
@@ -23,7 +25,7 @@ struct MlpLayout {
   int in_dim[VDN_MAX_LAYERS], out_dim[VDN_MAX_LAYERS];
   int in_ld[VDN_MAX_LAYERS], out_ld[VDN_MAX_LAYERS];
   long long off_w[VDN_MAX_LAYERS], off_wt[VDN_MAX_LAYERS], off_b[VDN_MAX_LAYERS];
-  long long off_iw[VDN_MAX_LAYERS], off_iwt[VDN_MAX_LAYERS];
+  long long off_iw[VDN_MAX_LAYERS], off_iwt[VDN_MAX_LAYERS], off_ih[VDN_MAX_LAYERS];
   long long total;  // floats
 };
 
@@ -50,6 +52,11 @@ inline int make_layout(int L, const int* in_dims, const int* out_dims, MlpLayout
     off += (long long)((in_dims[l] + 31) / 32) * ly->out_ld[l] * 32;
     ly->off_iwt[l] = off;
     off += (long long)((out_dims[l] + 31) / 32) * ly->in_ld[l] * 32;
+  }
+  for (int l = 0; l < L; ++l) {
+    off = (off + 255) / 256 * 256;
+    ly->off_ih[l] = off;
+    off += (long long)((in_dims[l] + 63) / 64) * ly->out_ld[l] * 32;   // 64 halfs = 32 floats per row and K block
   }
   ly->total = off;
   return 0;

@@ -4,22 +4,35 @@
 //   reference: SDFNetwork.sdf (dpt_models/fields.py:72-92) as used by the hierarchical sampler
 //   (renderer.py:369-370, 201) and by extract_fields (renderer.py:10-30, 446).
 //
-// Per CTA (persistent, one per SM, tiles of 128 points):
-//   * the activation tile A [128 x 256] lives in TENSOR MEMORY (columns 256..511; lane = point, one column per
-//     feature) and is the A operand of the MMAs - with tf32 a 128x256x8 MMA would otherwise read 4 KB of A plus 8 KB
-//     of B from shared memory every 128 cycles, i.e. 75 % of the shared-memory port, before any staging traffic;
-//   * weight tiles ([n x 32] pre-swizzled tf32 images, mlp_layout.cuh) stream through a 6-stage ring (192 KB),
-//     fetched by one thread with cp.async.bulk (TMA engine) running ahead across layers and tiles;
-//   * one thread issues tcgen05.mma kind::tf32 into the 256-column accumulator D (TMEM columns 0..255);
-//   * sixteen warps run the epilogue of layer l: drain D into registers (tcgen05.ld) and release it, then - all warps
-//     on the same 32-column chunk, chunk after chunk - +bias -> softplus -> tf32 -> tcgen05.st into A, signalling each
-//     finished K-block on its own mbarrier, so the MMAs of layer l+1 trail the epilogue of layer l by one chunk;
-//   * the skip connection cat[h, e]/sqrt2 (fields.py:82-83) is formed in the epilogue of the preceding layer, the
-//     embedding e is recomputed from the point (no extra buffer);
+// Operand precision: fp16 activations and weights (10-bit mantissa, the same as tf32; every magnitude on this path
+// sits well inside the fp16 range), exact products, fp32 accumulation: kind::f16 runs at twice the kind::tf32 rate,
+// halves the weight bytes per MMA and packs the activation tile into half the tensor-memory columns.
+//
+// The chain runs in "base-2 softplus units": with t = z * beta/ln2 the activation is a' = log2(1 + 2^t) =
+// max(t,0) + log2(1 + 2^-|t|) and the next layer's t' = W a' + (beta/ln2) b - the beta scaling cancels, so an element
+// costs one FFMA (bias), one MUFU.EX2, a degree-4 polynomial for log2(1+w)/w on [0,1] (|err| < 3.3e-5 in a', i.e.
+// 2e-7 in softplus units, an order of magnitude below the fp16 rounding of a'), FMNMX, FFMA and half a pack
+// instruction.  The embedding enters scaled by beta/ln2, the last layer scales back.
+//
+// Per CTA (persistent, one per SM), TWO tiles of 128 points (slots X and Y) are in flight and alternate phases:
+// while the tensor pipe runs layer l of one slot, the epilogue warps turn the other slot's accumulator into its
+// next operand, so neither the MMAs nor the element-wise work wait on each other's latencies.
+//   * the activation tiles A_X, A_Y [128 x 256] fp16 live in TENSOR MEMORY (columns 256..383 and 384..511; lane =
+//     point, two features per column) and are the A operands of the MMAs (no shared-memory traffic for A);
+//   * one 256-column fp32 accumulator D (TMEM columns 0..255) is shared by both slots: the epilogue warps drain it
+//     into registers (tcgen05.ld) as soon as a phase completes and release it for the other slot's MMAs;
+//   * weight tiles ([n x 64] pre-swizzled fp16 images, mlp_layout.cuh) stream through a 6-stage ring (192 KB),
+//     fetched by one thread with cp.async.bulk (TMA engine); a layer's tiles serve both slots before being released;
+//   * one thread issues tcgen05.mma kind::f16; sixteen warps run the epilogue (bias from shared memory, activation,
+//     fp16x2 pack, tcgen05.st into A_slot);
+//   * the skip connection cat[h, e]/sqrt2 (fields.py:82-83): the layer before it writes [a' | (beta/ln2) e] and the
+//     1/sqrt2 is applied to the skip layer's accumulator (same FFMA as the bias), the embedding e is recomputed from
+//     the point (no extra buffer);
 //   * in grid mode the lattice point is generated from its index (no point tensor in HBM).
 // Supported shape: d_in = 3, d_hidden = 256, d_e <= 64, one skip layer; anything else takes the layer-wise path.
 #pragma once
 #include "gemm_tc.cuh"
+#include <cuda_fp16.h>
 
 namespace vdn {
 
@@ -27,7 +40,7 @@ constexpr int CH_EPI_WARPS = 16;    // four warps per scheduler: the epilogue is
 constexpr int CH_THREADS = (CH_EPI_WARPS + 2) * 32;   // + warp 16: TMEM alloc + MMA issue; warp 17: weight stream
 constexpr int CH_WSTAGES = 6;
 constexpr uint32_t CH_W_STAGE = 32768;
-constexpr size_t CH_SMEM = CH_WSTAGES * CH_W_STAGE + 1024;
+constexpr size_t CH_SMEM = CH_WSTAGES * CH_W_STAGE + 1024 + VDN_MAX_LAYERS * 256 * sizeof(float);
 
 struct ChainLayer {
   long long img_off, bias_off;   // float offsets into the packed buffer
@@ -55,166 +68,233 @@ static __device__ __noinline__ float chain_embed_col(float y0, float y1, float y
   return rem < 3 ? sinf(y[rem] * f) : cosf(y[rem - 3] * f);
 }
 
+constexpr float kB2 = 144.26950408889634f;     // beta / ln 2 for beta = 100 (fields.py:50 Softplus(beta=100))
+constexpr float kInvB2 = 1.0f / 144.26950408889634f;
+
+// a' = log2(1 + 2^t) = max(t, 0) + w q(w), w = 2^-|t|; q = degree-4 fit of log2(1+w)/w on [0,1], |w q - log2(1+w)| < 3.3e-5
+__device__ __forceinline__ float softplus_base2(float t) {
+  float w;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(-fabsf(t)));
+  float q = fmaf(0.04008112847805023f, w, -0.1803952157497406f);
+  q = fmaf(q, w, 0.4036492109298706f);
+  q = fmaf(q, w, -0.7047332525253296f);
+  q = fmaf(q, w, 1.4414016008377075f);
+  return fmaf(w, q, fmaxf(t, 0.0f));
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // One output element of a chunk that is not entirely real outputs: the tail of the layer before the skip connection
-// carries the embedding (fields.py:82-83), anything beyond is zero padding.  Cold path.
-static __device__ __noinline__ float chain_ragged_elem(float acc, int nn, int out_dim, const float* bias, float osc,
-                                                       int d_e_tail, float y0, float y1, float y2) {
-  if (nn < out_dim) return softplus100_fast(acc + bias[nn]) * osc;
-  if (nn - out_dim < d_e_tail) return chain_embed_col(y0, y1, y2, nn - out_dim) * osc;
+// carries the embedding (fields.py:82-83), anything beyond is zero padding.  Cold path.  t = pre-activation in base-2
+// units (bias included).
+static __device__ __noinline__ float chain_ragged_elem(float t, int nn, int out_dim, int d_e_tail, float y0, float y1,
+                                                       float y2) {
+  if (nn < out_dim) return softplus_base2(t);
+  if (nn - out_dim < d_e_tail) return chain_embed_col(y0, y1, y2, nn - out_dim) * kB2;
   return 0.0f;
+}
+
+// Hot path: 8 consecutive real outputs of one row -> 4 packed fp16x2 words.  sb = bias * beta/ln2 in shared memory,
+// dsc = scale of the accumulator (1/sqrt2 on the skip layer, else 1).
+__device__ __forceinline__ void chain_epi8(const float (&v)[8], const float* sb, float dsc, uint32_t (&p)[4]) {
+  const float4 b0 = *reinterpret_cast<const float4*>(sb);
+  const float4 b1 = *reinterpret_cast<const float4*>(sb + 4);
+  float r[8];
+  r[0] = softplus_base2(fmaf(v[0], dsc, b0.x));
+  r[1] = softplus_base2(fmaf(v[1], dsc, b0.y));
+  r[2] = softplus_base2(fmaf(v[2], dsc, b0.z));
+  r[3] = softplus_base2(fmaf(v[3], dsc, b0.w));
+  r[4] = softplus_base2(fmaf(v[4], dsc, b1.x));
+  r[5] = softplus_base2(fmaf(v[5], dsc, b1.y));
+  r[6] = softplus_base2(fmaf(v[6], dsc, b1.z));
+  r[7] = softplus_base2(fmaf(v[7], dsc, b1.w));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = pack_half2(r[2 * i], r[2 * i + 1]);
 }
 
 static __global__ void __launch_bounds__(CH_THREADS, 1)
 sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t w_full[CH_WSTAGES], w_empty[CH_WSTAGES], a_ready[8], d_full, d_drained;
+  __shared__ uint64_t w_full[CH_WSTAGES], w_empty[CH_WSTAGES], a_ready[2], d_full, d_drained;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sW = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  float* sB = reinterpret_cast<float*>(smem_raw + (sW - smem_u32(smem_raw)) + CH_WSTAGES * CH_W_STAGE);
   const long long ntiles = (a.N + 127) / 128;
+  const long long G = gridDim.x;
 
   if (tid == 0) {
     for (int s = 0; s < CH_WSTAGES; ++s) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
-    for (int j = 0; j < 8; ++j) mbar_init(smem_u32(&a_ready[j]), CH_EPI_WARPS * 32);
+    for (int j = 0; j < 2; ++j) mbar_init(smem_u32(&a_ready[j]), CH_EPI_WARPS * 32);
     mbar_init(smem_u32(&d_full), 1);
     mbar_init(smem_u32(&d_drained), CH_EPI_WARPS * 32);
     mbar_fence_init();
+  }
+  for (int i = tid; i < a.L * 256; i += CH_THREADS) {   // biases in base-2 units
+    const int l = i >> 8, n = i & 255;
+    sB[i] = n < a.layer[l].out_dim ? a.packed[a.layer[l].bias_off + n] * kB2 : 0.0f;
   }
   if (warp == CH_EPI_WARPS) tmem_alloc(smem_u32(&tmem_base_s), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;   // accumulator D: columns [0,256); activation tile A: columns [256,512)
+  // accumulator D: columns [0,256); fp16 activation tiles: slot X columns [256,384), slot Y columns [384,512)
+  const uint32_t tmem_base = tmem_base_s;
   bool ok = true;
 
   if (warp < CH_EPI_WARPS) {
     // ================= embedding + epilogue warps =================
-    // warp (q, h): TMEM lane quarter q (rows 32q..32q+31), columns [32 ch + 8 h, +8) of every 32-column chunk ch.
-    // All sixteen warps work on the same chunk, chunk after chunk, so K-block ch of the next layer's operand is
-    // complete after 1/8 of the epilogue and the tensor pipe trails the epilogue by one chunk.
+    // warp (q, h): TMEM lane quarter q (rows 32q..32q+31), columns [32 ch + 8 h, +8) of every 32-column chunk ch of D,
+    // i.e. packed columns [16 ch + 4 h, +4) of the slot's A tile.
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t tD = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 8);
-    const uint32_t tA = tD + 256u;
+    const uint32_t tA0 = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(h * 4);
     uint32_t dcnt = 0;                                // completions of d_full consumed
-    for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+    float yX0 = 0.f, yX1 = 0.f, yX2 = 0.f, yY0 = 0.f, yY1 = 0.f, yY2 = 0.f;
+    auto load_point = [&](long long tile, float& y0, float& y1, float& y2) {
       const long long m = tile * 128 + row;
-      const bool valid = m < a.N;
-      float y[3] = {0.f, 0.f, 0.f};
-      if (valid) {
+      y0 = y1 = y2 = 0.f;
+      if (m < a.N) {
         if (a.x) {
-          y[0] = a.x[m * 3] * a.scale; y[1] = a.x[m * 3 + 1] * a.scale; y[2] = a.x[m * 3 + 2] * a.scale;
+          y0 = a.x[m * 3] * a.scale; y1 = a.x[m * 3 + 1] * a.scale; y2 = a.x[m * 3 + 2] * a.scale;
         } else {
           const int k = (int)(m % a.nz);
           const long long t = m / a.nz;
           const int j = (int)(t % a.ny);
           const int i = a.i0 + (int)(t / a.ny);
-          y[0] = a.xs[i] * a.scale; y[1] = a.ys[j] * a.scale; y[2] = a.zs[k] * a.scale;
+          y0 = a.xs[i] * a.scale; y1 = a.ys[j] * a.scale; y2 = a.zs[k] * a.scale;
         }
       }
-      // ---- positional encoding -> K-blocks 0 and 1 of A (activation tile in TMEM) ----
+    };
+    // positional encoding (times beta/ln2) -> chunks 0 and 1 of the slot's A tile, then signal the slot
+    auto write_pe = [&](int s, float y0, float y1, float y2) {
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = ch * 32 + h * 8 + j;
-          v[j] = c < a.d_e ? to_tf32(chain_embed_col(y[0], y[1], y[2], c)) : 0.0f;
+          v[j] = c < a.d_e ? chain_embed_col(y0, y1, y2, c) * kB2 : 0.0f;
         }
-        tmem_st8(tA + (uint32_t)(ch * 32), v);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&a_ready[ch]));
+        uint32_t p[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = pack_half2(v[2 * i], v[2 * i + 1]);
+        tmem_st4(tA0 + (uint32_t)(s * 128 + ch * 16), p);
       }
-      // ---- layer epilogues ----
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&a_ready[s]));
+    };
+    if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x, yX0, yX1, yX2); write_pe(0, yX0, yX1, yX2); }
+    if (blockIdx.x + G < ntiles) { load_point(blockIdx.x + G, yY0, yY1, yY2); write_pe(1, yY0, yY1, yY2); }
+    for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
+      const bool hasY = tX + G < ntiles;
       for (int l = 0; l < a.L && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
-        ok = mbar_wait(smem_u32(&d_full), dcnt & 1);
-        ++dcnt;
-        tc_fence_after();
-        const float* bias = a.packed + Ly.bias_off;
-        if (l == a.L - 1) {
-          if (h == 0) {
-            float v[8];
-            tmem_ld8(tD, v);
-            tmem_ld_wait();
-            if (valid) a.out[m * a.lds] = (v[0] + bias[0]) * (a.out_mul / a.scale);
+        const float* sb = sB + l * 256 + h * 8;
+        const float dsc = (l == a.skip) ? kInvSqrt2 : 1.0f;
+        for (int s = 0; s < 2 && ok; ++s) {
+          if (s && !hasY) break;
+          float y0 = s ? yY0 : yX0, y1 = s ? yY1 : yX1, y2 = s ? yY2 : yX2;
+          ok = mbar_wait(smem_u32(&d_full), dcnt & 1);
+          ++dcnt;
+          tc_fence_after();
+          if (l == a.L - 1) {
+            if (h == 0) {
+              float v[8];
+              tmem_ld8(tD, v);
+              tmem_ld_wait();
+              const long long m = (tX + s * G) * 128 + row;
+              if (m < a.N) a.out[m * a.lds] = fmaf(v[0] * dsc, kInvB2, a.packed[Ly.bias_off]) * (a.out_mul / a.scale);
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&d_drained));
+            const long long tn = tX + (2 + s) * G;     // the slot's next tile
+            if (tn < ntiles) {
+              load_point(tn, y0, y1, y2);
+              if (s) { yY0 = y0; yY1 = y1; yY2 = y2; } else { yX0 = y0; yX1 = y1; yX2 = y2; }
+              write_pe(s, y0, y1, y2);
+            }
+            continue;
           }
+          // drain this thread's 8 x 8 accumulator columns into registers, then release D for the other slot's MMAs
+          float v[8][8];
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) tmem_ld8(tD + (uint32_t)(ch * 32), v[ch]);
+          tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&d_drained));
-          continue;
-        }
-        // drain this thread's 8 x 8 accumulator columns into registers, then release D so the MMAs of the next layer
-        // may overwrite it while the activations are still being computed
-        float v[8][8];
+          const int d_e_tail = (l + 1 == a.skip) ? a.d_e : 0;
+          const uint32_t tA = tA0 + (uint32_t)(s * 128);
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) tmem_ld8(tD + (uint32_t)(ch * 32), v[ch]);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&d_drained));
-        const bool skip_next = (l + 1 == a.skip);
-        const float osc = skip_next ? kInvSqrt2 : 1.0f;
-        const int d_e_tail = skip_next ? a.d_e : 0;
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t p[4];
+            if (ch * 32 + 32 <= Ly.out_dim) {      // chunk of real outputs (uniform over the CTA)
+              chain_epi8(v[ch], sb + ch * 32, dsc, p);
+            } else {                                // tail of the layer before the skip connection / zero padding
+              const int n0 = ch * 32 + h * 8;
+              float r[8];
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const int n0 = ch * 32 + h * 8;
-          if (ch * 32 + 32 <= Ly.out_dim) {      // chunk of real outputs (uniform over the CTA)
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0) + 1);
-            v[ch][0] = to_tf32(softplus100_fast(v[ch][0] + b0.x) * osc);
-            v[ch][1] = to_tf32(softplus100_fast(v[ch][1] + b0.y) * osc);
-            v[ch][2] = to_tf32(softplus100_fast(v[ch][2] + b0.z) * osc);
-            v[ch][3] = to_tf32(softplus100_fast(v[ch][3] + b0.w) * osc);
-            v[ch][4] = to_tf32(softplus100_fast(v[ch][4] + b1.x) * osc);
-            v[ch][5] = to_tf32(softplus100_fast(v[ch][5] + b1.y) * osc);
-            v[ch][6] = to_tf32(softplus100_fast(v[ch][6] + b1.z) * osc);
-            v[ch][7] = to_tf32(softplus100_fast(v[ch][7] + b1.w) * osc);
-          } else {                                // tail of the layer before the skip connection / zero padding
+              for (int j = 0; j < 8; ++j)
+                r[j] = chain_ragged_elem(n0 + j < Ly.n_mma ? fmaf(v[ch][j], dsc, sb[ch * 32 + j]) : 0.0f, n0 + j, Ly.out_dim,
+                                         d_e_tail, y0, y1, y2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              v[ch][j] = to_tf32(chain_ragged_elem(n0 + j < Ly.n_mma ? v[ch][j] : 0.0f, n0 + j, Ly.out_dim, bias, osc,
-                                                   d_e_tail, y[0], y[1], y[2]));
+              for (int i = 0; i < 4; ++i) p[i] = pack_half2(r[2 * i], r[2 * i + 1]);
+            }
+            tmem_st4(tA + (uint32_t)(ch * 16), p);
           }
-          tmem_st8(tA + (uint32_t)(ch * 32), v[ch]);
           tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(smem_u32(&a_ready[ch]));
+          mbar_arrive(smem_u32(&a_ready[s]));
         }
       }
     }
   } else if (tid == CH_EPI_WARPS * 32) {
     // ================= MMA issuer: A from tensor memory, weights from shared memory =================
-    uint32_t acnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t acnt[2] = {0, 0};
     uint32_t wt = 0, drained = 0;
     const uint32_t tAcol = tmem_base + 256u;
-    for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+    for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
+      const bool hasY = tX + G < ntiles;
       for (int l = 0; l < a.L && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
-        const uint32_t idesc = umma_idesc_tf32(128, (uint32_t)Ly.n_mma);
-        // the accumulator of the previous layer must have been drained (first layer ever: passes immediately)
-        ok = mbar_wait(smem_u32(&d_drained), (drained & 1) ^ 1);
-        ++drained;
-        for (int kb = 0; kb < Ly.nkb && ok; ++kb, ++wt) {
-          const uint32_t ws = wt % CH_WSTAGES, wph = (wt / CH_WSTAGES) & 1;
-          ok = mbar_wait(smem_u32(&w_full[ws]), wph);
-          ok = ok && mbar_wait(smem_u32(&a_ready[kb]), acnt[kb] & 1);
-          ++acnt[kb];
+        const uint32_t idesc = umma_idesc_f16(128, (uint32_t)Ly.n_mma);
+        for (int s = 0; s < 2 && ok; ++s) {
+          if (s && !hasY) break;
+          // the accumulator of the previous phase must have been drained (first phase ever: passes immediately)
+          ok = mbar_wait(smem_u32(&d_drained), (drained & 1) ^ 1);
+          ++drained;
+          ok = ok && mbar_wait(smem_u32(&a_ready[s]), acnt[s] & 1);
+          ++acnt[s];
           tc_fence_after();
-          const uint32_t b0 = sW + ws * CH_W_STAGE;
+          for (int kb = 0; kb < Ly.nkb && ok; ++kb) {     // K blocks of 64
+            const uint32_t w = wt + (uint32_t)kb;
+            const uint32_t ws = w % CH_WSTAGES, wph = (w / CH_WSTAGES) & 1;
+            if (s == 0) {                                  // slot Y reuses the tiles slot X has already seen arrive
+              ok = mbar_wait(smem_u32(&w_full[ws]), wph);
+              tc_fence_after();
+            }
+            const uint32_t b0 = sW + ws * CH_W_STAGE;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32_ts(tmem_base, tAcol + (uint32_t)(kb * 32 + ks * 8), umma_desc_sw128(b0 + ks * 32), idesc,
-                         (kb | ks) ? 1u : 0u);
-          umma_commit(smem_u32(&w_empty[ws]));
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16_ts(tmem_base, tAcol + (uint32_t)(s * 128 + kb * 32 + ks * 8), umma_desc_sw128(b0 + ks * 32), idesc,
+                          (kb | ks) ? 1u : 0u);
+            if (s == 1 || !hasY) umma_commit(smem_u32(&w_empty[ws]));
+          }
+          umma_commit(smem_u32(&d_full));
         }
-        umma_commit(smem_u32(&d_full));
+        wt += (uint32_t)Ly.nkb;
       }
     }
   } else if (tid == (CH_EPI_WARPS + 1) * 32) {
-    // ================= weight stream (TMA engine) =================
+    // ================= weight stream (TMA engine): every layer once per pair of tiles =================
     uint32_t wt = 0;
-    for (long long tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+    for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
       for (int l = 0; l < a.L && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
         const uint32_t bytes = (uint32_t)Ly.n_mma * 128u;
@@ -247,10 +327,10 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
   a.packed = packed; a.x = x; a.xs = xs; a.ys = ys; a.zs = zs; a.ny = ny; a.nz = nz; a.i0 = i0; a.N = N; a.out = out; a.lds = lds;
   for (int l = 0; l < ly.L; ++l) {
     ChainLayer& c = a.layer[l];
-    c.img_off = ly.off_iw[l]; c.bias_off = ly.off_b[l]; c.out_ld = ly.out_ld[l]; c.out_dim = ly.out_dim[l];
+    c.img_off = ly.off_ih[l]; c.bias_off = ly.off_b[l]; c.out_ld = ly.out_ld[l]; c.out_dim = ly.out_dim[l];
     c.n_mma = (l == ly.L - 1) ? 16 : ((ly.out_dim[l] + 15) & ~15);
-    c.nkb = (ly.in_dim[l] + 31) / 32;
-    if (c.n_mma > 256 || c.nkb > 8) return -1;
+    c.nkb = (ly.in_dim[l] + 63) / 64;
+    if (c.n_mma > 256 || c.nkb > 4) return -1;
   }
   static int num_sms = 0;
   static bool attr_set = false;
@@ -266,7 +346,7 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
   const long long ntiles = (N + 127) / 128;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
   double flops = 0.0;
-  for (int l = 0; l < ly.L; ++l) flops += 2.0 * (double)N * a.layer[l].n_mma * a.layer[l].nkb * 32;
+  for (int l = 0; l < ly.L; ++l) flops += 2.0 * (double)N * a.layer[l].n_mma * a.layer[l].nkb * 64;
   prof_begin(PROF_TC, st, flops);
   VDN_LAUNCH(sdf_chain_tc_kernel, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault);
   prof_end(PROF_TC, st);

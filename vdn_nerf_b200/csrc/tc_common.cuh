@@ -20,6 +20,11 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t k
   return (r >> 3) * 1024u + (r & 7u) * 128u + ((((k >> 2) ^ r) & 7u) << 4) + ((k & 3u) << 2);
 }
 
+// byte offset of element (r, k) in a SWIZZLE_128B K-major tile with 64 16-bit columns
+__host__ __device__ __forceinline__ uint32_t sw128_offset_h(uint32_t r, uint32_t k) {
+  return (r >> 3) * 1024u + (r & 7u) * 128u + ((((k >> 3) ^ r) & 7u) << 4) + ((k & 7u) << 1);
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -106,6 +111,21 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32_mn(uint32_t M, uint
 __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate, both operands K-major
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T with fp16 operands: A in tensor memory holds two consecutive K elements per 32-bit
+// column (low half = even k), one MMA consumes K = 16 (8 columns)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -152,6 +172,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// four packed 32-bit words (e.g. 8 fp16 values) per lane
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

@@ -5,6 +5,7 @@
 // a packed gradient back into per-parameter gradients (weight-norm backward).
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 #include "../../include/vdn_b200.h"
 
 namespace vdn {
@@ -15,7 +16,7 @@ struct PackLayer {
   const float* b[2];
   int rows[2];
   int in_dim, in_ld, out_dim, out_ld, rot;
-  long long off_w, off_wt, off_b, off_iw, off_iwt;
+  long long off_w, off_wt, off_b, off_iw, off_iwt, off_ih;
 };
 struct PackArgs {
   int L;
@@ -59,6 +60,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
   }
   float* IW = packed + P.off_iw;
   float* IWT = packed + P.off_iwt;
+  __half* IH = reinterpret_cast<__half*>(packed + P.off_ih);
   for (int k = lane; k < P.in_ld; k += 32) {
     float w = 0.0f;
     if (k < P.in_dim) {
@@ -72,6 +74,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
       const float t = round_tf32(w);
       IW[(long long)(k >> 5) * P.out_ld * 32 + (tc::sw128_offset((uint32_t)r, (uint32_t)(k & 31)) >> 2)] = t;
       IWT[(long long)(r >> 5) * P.in_ld * 32 + (tc::sw128_offset((uint32_t)k, (uint32_t)(r & 31)) >> 2)] = t;
+      IH[(long long)(k >> 6) * P.out_ld * 64 + (tc::sw128_offset_h((uint32_t)r, (uint32_t)(k & 63)) >> 1)] = __float2half_rn(w);
     }
   }
   if (lane == 0) B[r] = P.b[src] ? P.b[src][rr] : 0.0f;
@@ -162,7 +165,7 @@ extern "C" int vdn_mlp_pack(int L, const int* in_dims, const int* out_dims, cons
     P.rot = rot ? rot[l] : 0;
     if (P.rot < 0 || P.rot >= P.in_dim) return (int)cudaErrorInvalidValue;
     P.off_w = ly.off_w[l]; P.off_wt = ly.off_wt[l]; P.off_b = ly.off_b[l];
-    P.off_iw = ly.off_iw[l]; P.off_iwt = ly.off_iwt[l];
+    P.off_iw = ly.off_iw[l]; P.off_iwt = ly.off_iwt[l]; P.off_ih = ly.off_ih[l];
   }
   a.row_start[L] = start;
   cudaStream_t st = (cudaStream_t)stream;
