@@ -276,7 +276,7 @@ def run_ours(args):
         lib.vdn_prof_enable(0)
         local_pts = float(hi - lo) * res * res
         ach = 2.0 * F_SDF1 * local_pts / (fam_ms * 1e-3) / 1e12
-        kname = ("sdf_chain_tc_kernel (fused PE + 9-layer tcgen05 kind::tf32 chain, 1 launch per slab)"
+        kname = ("sdf_chain_tc_kernel (fused PE + 9-layer tcgen05 kind::f16 chain, fp16 operands / fp32 accumulate, 1 launch per slab)"
                  if args.precision == "tf32" else "gemm_nt_kernel (FFMA), 9 launches per slab")
         line.update({"metric": "sdf_grid_pts_per_s", "unit": "pts/s", "value": value, "ms_per_step": ms / args.steps,
                      "config": {"workload": "extract_fields SDF grid query, womsk_white SDF net, x-slabs per rank",
@@ -286,8 +286,10 @@ def run_ours(args):
                      "roofline": {"bound": "tensor", "kernel": kname,
                                   "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                                   "frac": ach / pk["bf16_sustained"], "traffic": None,
-                                  "peak_source": pk["source"] + " bf16 sustained (dense tf32 peak is half of it)",
+                                  "peak_source": pk["source"] + " bf16 sustained (kind::f16 runs at the bf16 rate)",
                                   "launch_ms": fam_ms / max(1, fam_n)}})
+        if args.precision == "tf32":
+            line["dtype"] = "f16"
         cpu_kind = "grid"
     else:
         B = args.rays
@@ -369,7 +371,8 @@ def run_ours(args):
                                 "autograd (oracle port of the reference)"}
             line["cpu_baseline"] = cb
         line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-                     "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32",
+                     "scaling": "weak", "vs_baseline": None,
+                     "dtype": line.get("dtype", "tf32" if args.precision == "tf32" else "f32"),
                      "data": "synthetic", "gpu_launches": int(launches), "clocks": clocks})
         order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"]

@@ -22,7 +22,8 @@
 //   * one 256-column fp32 accumulator D (TMEM columns 0..255) is shared by both slots: the epilogue warps drain it
 //     into registers (tcgen05.ld) as soon as a phase completes and release it for the other slot's MMAs;
 //   * weight tiles ([n x 64] pre-swizzled fp16 images, mlp_layout.cuh) stream through a 6-stage ring (192 KB),
-//     fetched by one thread with cp.async.bulk (TMA engine); a layer's tiles serve both slots before being released;
+//     fetched by one thread with cp.async.bulk (TMA engine); the first two tiles of a layer serve both slots, the
+//     others are fetched once per slot so the ring can run ahead into the next layer;
 //   * one thread issues tcgen05.mma kind::f16; sixteen warps run the epilogue (bias from shared memory, activation,
 //     fp16x2 pack, tcgen05.st into A_slot);
 //   * the skip connection cat[h, e]/sqrt2 (fields.py:82-83): the layer before it writes [a' | (beta/ln2) e] and the
@@ -39,8 +40,9 @@ namespace vdn {
 constexpr int CH_EPI_WARPS = 16;    // four warps per scheduler: the epilogue is latency bound with fewer
 constexpr int CH_THREADS = (CH_EPI_WARPS + 2) * 32;   // + warp 16: TMEM alloc + MMA issue; warp 17: weight stream
 constexpr int CH_WSTAGES = 6;
+constexpr int CH_KEEP = 4;         // weight tiles of a layer kept in the ring for the second slot
 constexpr uint32_t CH_W_STAGE = 32768;
-constexpr size_t CH_SMEM = CH_WSTAGES * CH_W_STAGE + 1024 + VDN_MAX_LAYERS * 256 * sizeof(float);
+constexpr size_t CH_SMEM = CH_WSTAGES * CH_W_STAGE + 1024 + VDN_MAX_LAYERS * 256 * sizeof(float) + 64 * sizeof(float4);
 
 struct ChainLayer {
   long long img_off, bias_off;   // float offsets into the packed buffer
@@ -59,13 +61,13 @@ struct ChainArgs {
   ChainLayer layer[VDN_MAX_LAYERS];
 };
 
-// embedding column c (< d_e) of point y: [y | sin(2^k y) | cos(2^k y)]_k, d = 3 (embedder.py:15-36)
-static __device__ __noinline__ float chain_embed_col(float y0, float y1, float y2, int c) {
-  const float y[3] = {y0, y1, y2};
-  if (c < 3) return y[c];
-  const int k = (c - 3) / 6, rem = (c - 3) - 6 * k;
-  const float f = (float)(1 << k);
-  return rem < 3 ? sinf(y[rem] * f) : cosf(y[rem - 3] * f);
+// embedding column c (< d_e) of point y: [y | sin(2^k y) | cos(2^k y)]_k, d = 3 (embedder.py:15-36), through a
+// per-CTA table {frequency, phase, coordinate, identity flag} (cos x = sin(x + pi/2)).  MUFU sin: |2^k y| stays below
+// ~100 rad on this path, where sin.approx is good to ~1e-5 absolute - far below the fp16 rounding of the operand.
+__device__ __forceinline__ float chain_embed_col(const float4* lut, float y0, float y1, float y2, int c) {
+  const float4 e = lut[c];
+  const float y = e.z == 0.0f ? y0 : (e.z == 1.0f ? y1 : y2);
+  return e.w != 0.0f ? y : __sinf(fmaf(y, e.x, e.y));
 }
 
 constexpr float kB2 = 144.26950408889634f;     // beta / ln 2 for beta = 100 (fields.py:50 Softplus(beta=100))
@@ -88,12 +90,12 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 // One output element of a chunk that is not entirely real outputs: the tail of the layer before the skip connection
-// carries the embedding (fields.py:82-83), anything beyond is zero padding.  Cold path.  t = pre-activation in base-2
-// units (bias included).
-static __device__ __noinline__ float chain_ragged_elem(float t, int nn, int out_dim, int d_e_tail, float y0, float y1,
-                                                       float y2) {
+// carries the embedding (fields.py:82-83), anything beyond is zero padding.  t = pre-activation in base-2 units (bias
+// included).
+__device__ __forceinline__ float chain_ragged_elem(const float4* lut, float t, int nn, int out_dim, int d_e_tail, float y0,
+                                                   float y1, float y2) {
   if (nn < out_dim) return softplus_base2(t);
-  if (nn - out_dim < d_e_tail) return chain_embed_col(y0, y1, y2, nn - out_dim) * kB2;
+  if (nn - out_dim < d_e_tail) return chain_embed_col(lut, y0, y1, y2, nn - out_dim) * kB2;
   return 0.0f;
 }
 
@@ -116,14 +118,18 @@ __device__ __forceinline__ void chain_epi8(const float (&v)[8], const float* sb,
 }
 
 static __global__ void __launch_bounds__(CH_THREADS, 1)
-sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault) {
+sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault, long long* __restrict__ dbg) {
   using namespace tc;
+  // optional timeline of CTA 0 (debug, vdn_debug_timeline): dbg[role * 256 + 4 * phase + ev] = clock64()
+  const bool rec = dbg != nullptr && blockIdx.x == 0;
+#define CH_TL(role, ph, ev) do { if (rec && (ph) < 64) dbg[(role) * 256 + 4 * (ph) + (ev)] = clock64(); } while (0)
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full[CH_WSTAGES], w_empty[CH_WSTAGES], a_ready[2], d_full, d_drained;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sW = (smem_u32(smem_raw) + 1023u) & ~1023u;
   float* sB = reinterpret_cast<float*>(smem_raw + (sW - smem_u32(smem_raw)) + CH_WSTAGES * CH_W_STAGE);
+  const float4* sE = reinterpret_cast<const float4*>(sB + VDN_MAX_LAYERS * 256);
   const long long ntiles = (a.N + 127) / 128;
   const long long G = gridDim.x;
 
@@ -137,6 +143,17 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
   for (int i = tid; i < a.L * 256; i += CH_THREADS) {   // biases in base-2 units
     const int l = i >> 8, n = i & 255;
     sB[i] = n < a.layer[l].out_dim ? a.packed[a.layer[l].bias_off + n] * kB2 : 0.0f;
+  }
+  if (tid < 64) {                                        // embedding table (zero rows beyond d_e)
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = tid;
+    if (c < 3) {
+      e = make_float4(1.f, 0.f, (float)c, 1.f);
+    } else if (c < a.d_e) {
+      const int k = (c - 3) / 6, rem = (c - 3) - 6 * k;
+      e = make_float4((float)(1 << k), rem < 3 ? 0.f : 1.5707963267948966f, (float)(rem < 3 ? rem : rem - 3), 0.f);
+    }
+    const_cast<float4*>(sE)[c] = e;
   }
   if (warp == CH_EPI_WARPS) tmem_alloc(smem_u32(&tmem_base_s), 512);
   tc_fence_before();
@@ -163,10 +180,11 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
         if (a.x) {
           y0 = a.x[m * 3] * a.scale; y1 = a.x[m * 3 + 1] * a.scale; y2 = a.x[m * 3 + 2] * a.scale;
         } else {
-          const int k = (int)(m % a.nz);
-          const long long t = m / a.nz;
-          const int j = (int)(t % a.ny);
-          const int i = a.i0 + (int)(t / a.ny);
+          const unsigned mu = (unsigned)m, t = mu / (unsigned)a.nz;   // N < 2^31 (checked by the launcher)
+          const int k = (int)(mu - t * (unsigned)a.nz);
+          const unsigned ti = t / (unsigned)a.ny;
+          const int j = (int)(t - ti * (unsigned)a.ny);
+          const int i = a.i0 + (int)ti;
           y0 = a.xs[i] * a.scale; y1 = a.ys[j] * a.scale; y2 = a.zs[k] * a.scale;
         }
       }
@@ -179,7 +197,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = ch * 32 + h * 8 + j;
-          v[j] = c < a.d_e ? chain_embed_col(y0, y1, y2, c) * kB2 : 0.0f;
+          v[j] = c < a.d_e ? chain_embed_col(sE, y0, y1, y2, c) * kB2 : 0.0f;
         }
         uint32_t p[4];
 #pragma unroll
@@ -201,7 +219,9 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
         for (int s = 0; s < 2 && ok; ++s) {
           if (s && !hasY) break;
           float y0 = s ? yY0 : yX0, y1 = s ? yY1 : yX1, y2 = s ? yY2 : yX2;
+          if (tid == 0) CH_TL(0, dcnt, 0);
           ok = mbar_wait(smem_u32(&d_full), dcnt & 1);
+          if (tid == 0) CH_TL(0, dcnt, 1);
           ++dcnt;
           tc_fence_after();
           if (l == a.L - 1) {
@@ -229,6 +249,11 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&d_drained));
+          if (tid == 0) CH_TL(0, dcnt - 1, 2);
+          if (l == a.L - 2 && a.x) {                 // the slot's next point: pull its line towards L1 a phase early
+            const long long mn = (tX + (2 + s) * G) * 128 + row;
+            if (mn < a.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.x + mn * 3));
+          }
           const int d_e_tail = (l + 1 == a.skip) ? a.d_e : 0;
           const uint32_t tA = tA0 + (uint32_t)(s * 128);
 #pragma unroll
@@ -241,7 +266,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
               float r[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                r[j] = chain_ragged_elem(n0 + j < Ly.n_mma ? fmaf(v[ch][j], dsc, sb[ch * 32 + j]) : 0.0f, n0 + j, Ly.out_dim,
+                r[j] = chain_ragged_elem(sE, n0 + j < Ly.n_mma ? fmaf(v[ch][j], dsc, sb[ch * 32 + j]) : 0.0f, n0 + j, Ly.out_dim,
                                          d_e_tail, y0, y1, y2);
 #pragma unroll
               for (int i = 0; i < 4; ++i) p[i] = pack_half2(r[2 * i], r[2 * i + 1]);
@@ -251,6 +276,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&a_ready[s]));
+          if (tid == 0) CH_TL(0, dcnt - 1, 3);
         }
       }
     }
@@ -267,15 +293,23 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
         for (int s = 0; s < 2 && ok; ++s) {
           if (s && !hasY) break;
           // the accumulator of the previous phase must have been drained (first phase ever: passes immediately)
+          CH_TL(1, drained, 0);
           ok = mbar_wait(smem_u32(&d_drained), (drained & 1) ^ 1);
+          CH_TL(1, drained, 1);
           ++drained;
           ok = ok && mbar_wait(smem_u32(&a_ready[s]), acnt[s] & 1);
           ++acnt[s];
           tc_fence_after();
-          for (int kb = 0; kb < Ly.nkb && ok; ++kb) {     // K blocks of 64
-            const uint32_t w = wt + (uint32_t)kb;
+          CH_TL(1, drained - 1, 2);
+          // K blocks of 64.  Slot X streams all of the layer's weight tiles; the first `keep` stay in the ring for
+          // slot Y, the others are released at once and fetched again for Y, so that the ring always has room to run
+          // ahead into the next layer.
+          const int keep = Ly.nkb < CH_KEEP ? Ly.nkb : CH_KEEP;
+          for (int kb = 0; kb < Ly.nkb && ok; ++kb) {
+            const bool held = (s == 1 && kb < keep);       // tile slot X has already seen arrive
+            const uint32_t w = wt + (uint32_t)(s == 0 || held ? kb : Ly.nkb + kb - keep);
             const uint32_t ws = w % CH_WSTAGES, wph = (w / CH_WSTAGES) & 1;
-            if (s == 0) {                                  // slot Y reuses the tiles slot X has already seen arrive
+            if (!held) {
               ok = mbar_wait(smem_u32(&w_full[ws]), wph);
               tc_fence_after();
             }
@@ -284,23 +318,29 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
             for (int ks = 0; ks < 4; ++ks)
               umma_f16_ts(tmem_base, tAcol + (uint32_t)(s * 128 + kb * 32 + ks * 8), umma_desc_sw128(b0 + ks * 32), idesc,
                           (kb | ks) ? 1u : 0u);
-            if (s == 1 || !hasY) umma_commit(smem_u32(&w_empty[ws]));
+            if (s == 1 || !hasY || kb >= keep) umma_commit(smem_u32(&w_empty[ws]));
           }
           umma_commit(smem_u32(&d_full));
+          CH_TL(1, drained - 1, 3);
         }
-        wt += (uint32_t)Ly.nkb;
+        const int keep = Ly.nkb < CH_KEEP ? Ly.nkb : CH_KEEP;
+        wt += (uint32_t)(hasY ? 2 * Ly.nkb - keep : Ly.nkb);
       }
     }
   } else if (tid == (CH_EPI_WARPS + 1) * 32) {
-    // ================= weight stream (TMA engine): every layer once per pair of tiles =================
+    // ================= weight stream (TMA engine), in the order the MMA issuer consumes the tiles =================
     uint32_t wt = 0;
     for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
+      const bool hasY = tX + G < ntiles;
       for (int l = 0; l < a.L && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
         const uint32_t bytes = (uint32_t)Ly.n_mma * 128u;
-        for (int kb = 0; kb < Ly.nkb && ok; ++kb, ++wt) {
+        const int keep = Ly.nkb < CH_KEEP ? Ly.nkb : CH_KEEP;
+        const int nfetch = hasY ? 2 * Ly.nkb - keep : Ly.nkb;
+        for (int f = 0; f < nfetch && ok; ++f, ++wt) {
+          const int kb = f < Ly.nkb ? f : f - Ly.nkb + keep;
           const uint32_t ws = wt % CH_WSTAGES, wph = (wt / CH_WSTAGES) & 1;
-          ok = mbar_wait(smem_u32(&w_empty[ws]), wph ^ 1);
+          ok = mbar_wait_backoff(smem_u32(&w_empty[ws]), wph ^ 1, 256);
           mbar_arrive_expect_tx(smem_u32(&w_full[ws]), bytes);
           bulk_g2s(sW + ws * CH_W_STAGE, a.packed + Ly.img_off + (size_t)kb * Ly.out_ld * 32, bytes, smem_u32(&w_full[ws]));
         }
@@ -311,6 +351,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
   tc_fence_before();
   __syncthreads();
   if (warp == CH_EPI_WARPS) tmem_dealloc(tmem_base, 512);
+#undef CH_TL
 }
 
 // Returns -1 when the configuration is not supported by the fused chain (caller falls back to the layer-wise path).
@@ -322,6 +363,7 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
   if (d_in != 3 || d_hidden != 256 || d_e > 64 || ly.L < 2 || ly.L > VDN_MAX_LAYERS) return -1;
   for (int l = 1; l < ly.L; ++l)
     if (ly.in_dim[l] != 256) return -1;
+  if (N > 0x7fffffffLL) return (int)cudaErrorInvalidValue;   // 32-bit point indices inside the kernel
   ChainArgs a;
   a.L = ly.L; a.skip = skip; a.d_e = d_e; a.multires = multires; a.scale = scale; a.out_mul = out_mul;
   a.packed = packed; a.x = x; a.xs = xs; a.ys = ys; a.zs = zs; a.ny = ny; a.nz = nz; a.i0 = i0; a.N = N; a.out = out; a.lds = lds;
@@ -348,7 +390,7 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
   double flops = 0.0;
   for (int l = 0; l < ly.L; ++l) flops += 2.0 * (double)N * a.layer[l].n_mma * a.layer[l].nkb * 64;
   prof_begin(PROF_TC, st, flops);
-  VDN_LAUNCH(sdf_chain_tc_kernel, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault);
+  VDN_LAUNCH(sdf_chain_tc_kernel, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault, g_tc_dbg);
   prof_end(PROF_TC, st);
   return (int)cudaGetLastError();
 }

@@ -54,6 +54,15 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_
   }
   return false;
 }
+// Same, for long waits of single-thread roles (MMA issuer, weight stream): back off between polls so the spinning
+// thread does not take issue slots from the warps doing the element-wise work on its scheduler.
+__device__ __forceinline__ bool mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns = 64, uint32_t max_spins = 1u << 22) {
+  for (uint32_t i = 0; i < max_spins; ++i) {
+    if (mbar_try_wait(bar, parity)) return true;
+    __nanosleep(ns);
+  }
+  return false;
+}
 
 // ---- async proxy ------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
