@@ -1,0 +1,29 @@
+"""Device time of the SDF normals pass (9 layer-wise tcgen05 GEMM launches) versus the number of 128-point tiles."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vdn_nerf_b200 import configs, fields, ops
+dev = "cuda"
+conf = configs.CONFIGS["womsk_white"]
+mods = configs.build_networks(conf, fields, seed=0, device=dev)
+sdf = mods[1]
+ops.set_precision("tf32")
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+for waves in (0.25, 0.5, 1, 2, 4, 8):
+    n = int(148 * 2 * 128 * waves)
+    x = (torch.rand(n, 3, device=dev) * 2 - 1).requires_grad_(True)
+    t_f = timeit(lambda: sdf(x))
+    t_fn = timeit(lambda: (sdf(x), sdf.gradient(x)))
+    print(f"n={n:8d} ({waves} waves of 296 CTAs): forward {t_f*1e3:8.1f} us, normals {1e3*(t_fn - t_f):8.1f} us = {1e3*(t_fn-t_f)/9:6.1f} us per launch")

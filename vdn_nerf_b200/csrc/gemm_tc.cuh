@@ -74,11 +74,75 @@ __device__ __forceinline__ void tc_prologue4(const Operand& A, const RawLoad (&r
   }
 }
 
-// Slow path of the epilogue (ragged column ranges, unaligned or splitting epilogues): out of line.
-static __device__ __noinline__ void tc_epi_scalar4(const Epilogue& e, int m, int n, float4 v, int N) {
-  const float a[4] = {v.x, v.y, v.z, v.w};
-  for (int j = 0; j < 4; ++j)
-    if (n + j < N) epi_store(e, m, n + j, a[j]);
+// Element-wise path of the epilogue for 8 rows x 4 columns (ragged column ranges, unaligned or splitting epilogues):
+// same access pattern as the vector path (a warp instruction still covers four 128-byte row segments), scalar
+// loads / stores.  The kind switch sits outside the loops.
+__device__ __forceinline__ void tc_epilogue8_scalar(const Epilogue& e, int mbase, int M, int n, const float4 (&x)[8], int N) {
+  float bb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < N) bb[j] = e.bias[n + j];
+  }
+#define VDN_EPI_LOOP(BODY)                                                   \
+  _Pragma("unroll") for (int i = 0; i < 8; ++i) {                            \
+    const int m = mbase + 4 * i;                                             \
+    if (m < M) {                                                             \
+      const size_t mm = (size_t)m;                                           \
+      const float xv[4] = {x[i].x + bb[0], x[i].y + bb[1], x[i].z + bb[2], x[i].w + bb[3]}; \
+      _Pragma("unroll") for (int j = 0; j < 4; ++j) {                        \
+        const int nn = n + j;                                                \
+        const float v = xv[j];                                               \
+        if (nn < N) { BODY }                                                 \
+      }                                                                      \
+    }                                                                        \
+  }
+  switch (e.kind) {
+    case EPI_STORE: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = v;) break;
+    case EPI_RELU: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = fmaxf(v, 0.0f);) break;
+    case EPI_SIGMOID: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = sigmoidf_(v);) break;
+    case EPI_SOFTPLUS: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = softplus100(v);) break;
+    case EPI_SDF_SKIP:
+      VDN_EPI_LOOP(if (e.c) e.c[mm * e.ldc + nn] = v; e.c2[mm * e.ldc2 + nn] = softplus100(v) * e.scale;) break;
+    case EPI_SPLIT:
+      VDN_EPI_LOOP(if (nn < e.split) { if (e.c2) e.c2[mm * e.ldc2 + nn] = v * e.scale; }
+                   else if (e.c) e.c[mm * e.ldc + e.coff + (nn - e.split)] = v;) break;
+    case EPI_ADD_SCALED: VDN_EPI_LOOP(e.c[mm * e.ldc + nn] = v + e.scale * e.aux[mm * e.ldaux + e.split + nn];) break;
+    case EPI_GRAD_DUAL:
+      VDN_EPI_LOOP(const float z = e.aux[mm * e.ldaux + nn]; const float gin = e.aux2[mm * e.ldaux2 + nn] * e.scale2;
+                   e.c[mm * e.ldc + nn] = softplus100_d1(z) * v * e.scale;
+                   e.c2[mm * e.ldc2 + nn] = softplus100_d2(z) * gin * v;) break;
+    case EPI_BWD_INJECT:
+      VDN_EPI_LOOP(const float z = e.aux[mm * e.ldaux + nn]; float r = softplus100_d1(z) * v * e.scale;
+                   if (e.aux2) r += e.aux2[mm * e.ldaux2 + nn]; e.c[mm * e.ldc + nn] = r;) break;
+    case EPI_RELU_MASK: VDN_EPI_LOOP(e.c[mm * e.ldc + nn] = e.aux[mm * e.ldaux + e.split + nn] > 0.0f ? v : 0.0f;) break;
+    default: break;
+  }
+#undef VDN_EPI_LOOP
+}
+
+// Pull the lines of the epilogue's auxiliary operands (saved pre-activations, masks, injected cotangents) that this
+// thread will read for column chunk `n` into L2 well before the accumulator is complete: their DRAM latency would
+// otherwise be exposed once per chunk.
+__device__ __forceinline__ void tc_epilogue_prefetch(const Epilogue& e, int mbase, int M, int n, int N) {
+  if (n >= N) return;
+  const float* p1 = nullptr;
+  const float* p2 = nullptr;
+  int l1 = 0, l2 = 0;
+  switch (e.kind) {
+    case EPI_ADD_SCALED: case EPI_RELU_MASK: p1 = e.aux + e.split + n; l1 = e.ldaux; break;
+    case EPI_GRAD_DUAL: p1 = e.aux + n; l1 = e.ldaux; if (e.ldaux2) { p2 = e.aux2 + n; l2 = e.ldaux2; } break;
+    case EPI_BWD_INJECT: p1 = e.aux + n; l1 = e.ldaux; if (e.aux2) { p2 = e.aux2 + n; l2 = e.ldaux2; } break;
+    default: return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = mbase + 4 * i;
+    if (m < M) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + (size_t)m * l1));
+      if (p2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p2 + (size_t)m * l2));
+    }
+  }
 }
 
 // Vector epilogue for 8 rows x 4 columns (same columns for all rows); kind switched once.
@@ -109,6 +173,13 @@ __device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (mok_(i)) st4(e.c + (size_t)m_(i) * e.ldc + e.coff + n, f4_map_sp(x[i]));
+      break;
+    case EPI_SIGMOID:
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mok_(i))
+          st4(e.c + (size_t)m_(i) * e.ldc + e.coff + n,
+              make_float4(sigmoidf_(x[i].x), sigmoidf_(x[i].y), sigmoidf_(x[i].z), sigmoidf_(x[i].w)));
       break;
     case EPI_SDF_SKIP:
 #pragma unroll
@@ -157,7 +228,7 @@ inline bool epilogue_vec_ok(const Epilogue& e) {
   auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
   if (e.bias && !al(e.bias)) return false;
   switch (e.kind) {
-    case EPI_STORE: case EPI_RELU: case EPI_SOFTPLUS:
+    case EPI_STORE: case EPI_RELU: case EPI_SOFTPLUS: case EPI_SIGMOID:
       return al(e.c) && !(e.ldc & 3) && !(e.coff & 3);
     case EPI_SDF_SKIP:
       return (!e.c || (al(e.c) && !(e.ldc & 3))) && al(e.c2) && !(e.ldc2 & 3);
@@ -223,6 +294,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     const size_t stepa = (size_t)4 * A.ld, stepb = (size_t)4 * A.ld2;
     const int mlim = M - m0 - rbase;                              // group i is a valid row iff 4 i < mlim
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int pf_kb = nkb > 4 ? nkb - 4 : 0;
     RawLoad raw0[4], raw1[4];
     auto gload = [&](int kb, RawLoad (&raw)[4]) {
       const int col = kb * 32 + chunk * 4;
@@ -256,6 +328,11 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
       }
       if (tid == 0) VDN_TL(4, 2 * kb + 1);
       if (kb + 2 < nkb) gload(kb + 2, raw);          // refill the buffer just consumed
+      if (kb == pf_kb) {                             // epilogue operands of this thread -> L2, a few K blocks ahead
+        const int nch_e = (n_cta + 31) >> 5;
+        for (int ch = warp >> 2; ch < nch_e; ch += 2)
+          tc_epilogue_prefetch(E, m0 + (warp & 3) * 32 + (lane >> 3), M, n_base + ch * 32 + chunk * 4, N);
+      }
       if (tid == 0) VDN_TL(1, 3 * kb);
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
       if (tid == 0) VDN_TL(1, 3 * kb + 1);
@@ -351,8 +428,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
           if (vec_ok && n + 3 < N) {
             tc_epilogue8(E, mbase, M, n, x, bias4);
           } else if (n < N) {
-            for (int i = 0; i < 8; ++i)
-              if (mbase + 4 * i < M) tc_epi_scalar4(E, mbase + 4 * i, n, x[i], N);
+            tc_epilogue8_scalar(E, mbase, M, n, x, N);
           }
         }
       }

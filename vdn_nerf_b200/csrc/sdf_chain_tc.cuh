@@ -58,6 +58,12 @@ struct ChainArgs {
   long long N;
   float* out;
   int lds;
+  // training forward: Lrun < L layers are run (the multi-head last layer is left to the layer-wise kernel) and the
+  // pre-activations z_l (fields.py:79-87, in softplus units) are stored for the analytic gradient passes
+  int Lrun;
+  float* save_z[VDN_MAX_LAYERS];   // [N, ldz] per layer or null
+  float* save_u;                   // head of the skip layer's input, softplus(z_{skip-1}) / sqrt2, or null
+  int ldz;
   ChainLayer layer[VDN_MAX_LAYERS];
 };
 
@@ -100,23 +106,34 @@ __device__ __forceinline__ float chain_ragged_elem(const float4* lut, float t, i
 }
 
 // Hot path: 8 consecutive real outputs of one row -> 4 packed fp16x2 words.  sb = bias * beta/ln2 in shared memory,
-// dsc = scale of the accumulator (1/sqrt2 on the skip layer, else 1).
-__device__ __forceinline__ void chain_epi8(const float (&v)[8], const float* sb, float dsc, uint32_t (&p)[4]) {
+// dsc = scale of the accumulator (1/sqrt2 on the skip layer, else 1).  SAVE: also store the pre-activations (zrow) and,
+// on the layer before the skip connection, the scaled activations (urow), both in softplus units.
+template <bool SAVE>
+__device__ __forceinline__ void chain_epi8(const float (&v)[8], const float* sb, float dsc, uint32_t (&p)[4], float* zrow,
+                                           float* urow) {
   const float4 b0 = *reinterpret_cast<const float4*>(sb);
   const float4 b1 = *reinterpret_cast<const float4*>(sb + 4);
-  float r[8];
-  r[0] = softplus_base2(fmaf(v[0], dsc, b0.x));
-  r[1] = softplus_base2(fmaf(v[1], dsc, b0.y));
-  r[2] = softplus_base2(fmaf(v[2], dsc, b0.z));
-  r[3] = softplus_base2(fmaf(v[3], dsc, b0.w));
-  r[4] = softplus_base2(fmaf(v[4], dsc, b1.x));
-  r[5] = softplus_base2(fmaf(v[5], dsc, b1.y));
-  r[6] = softplus_base2(fmaf(v[6], dsc, b1.z));
-  r[7] = softplus_base2(fmaf(v[7], dsc, b1.w));
+  float t[8], r[8];
+  t[0] = fmaf(v[0], dsc, b0.x); t[1] = fmaf(v[1], dsc, b0.y); t[2] = fmaf(v[2], dsc, b0.z); t[3] = fmaf(v[3], dsc, b0.w);
+  t[4] = fmaf(v[4], dsc, b1.x); t[5] = fmaf(v[5], dsc, b1.y); t[6] = fmaf(v[6], dsc, b1.z); t[7] = fmaf(v[7], dsc, b1.w);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = softplus_base2(t[j]);
+  if (SAVE) {
+    if (zrow) {
+      reinterpret_cast<float4*>(zrow)[0] = make_float4(t[0] * kInvB2, t[1] * kInvB2, t[2] * kInvB2, t[3] * kInvB2);
+      reinterpret_cast<float4*>(zrow)[1] = make_float4(t[4] * kInvB2, t[5] * kInvB2, t[6] * kInvB2, t[7] * kInvB2);
+    }
+    if (urow) {
+      const float us = kInvB2 * kInvSqrt2;
+      reinterpret_cast<float4*>(urow)[0] = make_float4(r[0] * us, r[1] * us, r[2] * us, r[3] * us);
+      reinterpret_cast<float4*>(urow)[1] = make_float4(r[4] * us, r[5] * us, r[6] * us, r[7] * us);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) p[i] = pack_half2(r[2 * i], r[2 * i + 1]);
 }
 
+template <bool SAVE>
 static __global__ void __launch_bounds__(CH_THREADS, 1)
 sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault, long long* __restrict__ dbg) {
   using namespace tc;
@@ -212,7 +229,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
     if (blockIdx.x + G < ntiles) { load_point(blockIdx.x + G, yY0, yY1, yY2); write_pe(1, yY0, yY1, yY2); }
     for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
       const bool hasY = tX + G < ntiles;
-      for (int l = 0; l < a.L && ok; ++l) {
+      for (int l = 0; l < a.Lrun && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
         const float* sb = sB + l * 256 + h * 8;
         const float dsc = (l == a.skip) ? kInvSqrt2 : 1.0f;
@@ -224,59 +241,75 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
           if (tid == 0) CH_TL(0, dcnt, 1);
           ++dcnt;
           tc_fence_after();
-          if (l == a.L - 1) {
+          const bool last_run = (l == a.Lrun - 1);
+          const long long m = (tX + s * G) * 128 + row;
+          if (l == a.L - 1) {                          // sdf output layer (value-only mode)
             if (h == 0) {
               float v[8];
               tmem_ld8(tD, v);
               tmem_ld_wait();
-              const long long m = (tX + s * G) * 128 + row;
               if (m < a.N) a.out[m * a.lds] = fmaf(v[0] * dsc, kInvB2, a.packed[Ly.bias_off]) * (a.out_mul / a.scale);
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&d_drained));
-            const long long tn = tX + (2 + s) * G;     // the slot's next tile
+          } else {
+            // drain this thread's 8 x 8 accumulator columns into registers, then release D for the other slot's MMAs
+            float v[8][8];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) tmem_ld8(tD + (uint32_t)(ch * 32), v[ch]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&d_drained));
+            if (tid == 0) CH_TL(0, dcnt - 1, 2);
+            if (l == a.Lrun - 2 && a.x) {              // the slot's next point: pull its line towards L1 a phase early
+              const long long mn = (tX + (2 + s) * G) * 128 + row;
+              if (mn < a.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.x + mn * 3));
+            }
+            const int d_e_tail = (l + 1 == a.skip) ? a.d_e : 0;
+            const uint32_t tA = tA0 + (uint32_t)(s * 128);
+            float* zrow = nullptr;
+            float* urow = nullptr;
+            if (SAVE && m < a.N) {
+              if (a.save_z[l]) zrow = a.save_z[l] + m * a.ldz + h * 8;
+              if (a.save_u && l + 1 == a.skip) urow = a.save_u + m * a.ldz + h * 8;
+            }
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              uint32_t p[4];
+              if (ch * 32 + 32 <= Ly.out_dim) {      // chunk of real outputs (uniform over the CTA)
+                chain_epi8<SAVE>(v[ch], sb + ch * 32, dsc, p, zrow ? zrow + ch * 32 : nullptr, urow ? urow + ch * 32 : nullptr);
+              } else {                                // tail of the layer before the skip connection / zero padding
+                const int n0 = ch * 32 + h * 8;
+                float r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float t = n0 + j < Ly.n_mma ? fmaf(v[ch][j], dsc, sb[ch * 32 + j]) : 0.0f;
+                  r[j] = chain_ragged_elem(sE, t, n0 + j, Ly.out_dim, d_e_tail, y0, y1, y2);
+                  if (SAVE && n0 + j < Ly.out_dim) {
+                    if (zrow) zrow[ch * 32 + j] = t * kInvB2;
+                    if (urow) urow[ch * 32 + j] = r[j] * (kInvB2 * kInvSqrt2);
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) p[i] = pack_half2(r[2 * i], r[2 * i + 1]);
+              }
+              if (!last_run) tmem_st4(tA + (uint32_t)(ch * 16), p);
+            }
+            if (!last_run) {
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(smem_u32(&a_ready[s]));
+            }
+            if (tid == 0) CH_TL(0, dcnt - 1, 3);
+          }
+          if (last_run) {                              // the slot's next tile
+            const long long tn = tX + (2 + s) * G;
             if (tn < ntiles) {
               load_point(tn, y0, y1, y2);
               if (s) { yY0 = y0; yY1 = y1; yY2 = y2; } else { yX0 = y0; yX1 = y1; yX2 = y2; }
               write_pe(s, y0, y1, y2);
             }
-            continue;
           }
-          // drain this thread's 8 x 8 accumulator columns into registers, then release D for the other slot's MMAs
-          float v[8][8];
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) tmem_ld8(tD + (uint32_t)(ch * 32), v[ch]);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(smem_u32(&d_drained));
-          if (tid == 0) CH_TL(0, dcnt - 1, 2);
-          if (l == a.L - 2 && a.x) {                 // the slot's next point: pull its line towards L1 a phase early
-            const long long mn = (tX + (2 + s) * G) * 128 + row;
-            if (mn < a.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.x + mn * 3));
-          }
-          const int d_e_tail = (l + 1 == a.skip) ? a.d_e : 0;
-          const uint32_t tA = tA0 + (uint32_t)(s * 128);
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            uint32_t p[4];
-            if (ch * 32 + 32 <= Ly.out_dim) {      // chunk of real outputs (uniform over the CTA)
-              chain_epi8(v[ch], sb + ch * 32, dsc, p);
-            } else {                                // tail of the layer before the skip connection / zero padding
-              const int n0 = ch * 32 + h * 8;
-              float r[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                r[j] = chain_ragged_elem(sE, n0 + j < Ly.n_mma ? fmaf(v[ch][j], dsc, sb[ch * 32 + j]) : 0.0f, n0 + j, Ly.out_dim,
-                                         d_e_tail, y0, y1, y2);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) p[i] = pack_half2(r[2 * i], r[2 * i + 1]);
-            }
-            tmem_st4(tA + (uint32_t)(ch * 16), p);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(smem_u32(&a_ready[s]));
-          if (tid == 0) CH_TL(0, dcnt - 1, 3);
         }
       }
     }
@@ -287,7 +320,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
     const uint32_t tAcol = tmem_base + 256u;
     for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
       const bool hasY = tX + G < ntiles;
-      for (int l = 0; l < a.L && ok; ++l) {
+      for (int l = 0; l < a.Lrun && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
         const uint32_t idesc = umma_idesc_f16(128, (uint32_t)Ly.n_mma);
         for (int s = 0; s < 2 && ok; ++s) {
@@ -332,7 +365,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
     uint32_t wt = 0;
     for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
       const bool hasY = tX + G < ntiles;
-      for (int l = 0; l < a.L && ok; ++l) {
+      for (int l = 0; l < a.Lrun && ok; ++l) {
         const ChainLayer& Ly = a.layer[l];
         const uint32_t bytes = (uint32_t)Ly.n_mma * 128u;
         const int keep = Ly.nkb < CH_KEEP ? Ly.nkb : CH_KEEP;
@@ -358,7 +391,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
 static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, int d_hidden, int skip, float scale,
                                    const float* packed, const float* x, const float* xs, const float* ys,
                                    const float* zs, int ny, int nz, int i0, long long N, float* out, int lds, float out_mul,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, float* const* save_z = nullptr, float* save_u = nullptr, int ldz = 0) {
   const int d_e = d_in * (1 + 2 * multires);
   if (d_in != 3 || d_hidden != 256 || d_e > 64 || ly.L < 2 || ly.L > VDN_MAX_LAYERS) return -1;
   for (int l = 1; l < ly.L; ++l)
@@ -374,6 +407,12 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
     c.nkb = (ly.in_dim[l] + 63) / 64;
     if (c.n_mma > 256 || c.nkb > 4) return -1;
   }
+  // value-only: all L layers, sdf out.  Training forward (save_z given): layers 0..L-2 with stored pre-activations.
+  const bool save = save_z != nullptr;
+  a.Lrun = save ? ly.L - 1 : ly.L;
+  a.save_u = save ? save_u : nullptr;
+  a.ldz = ldz;
+  for (int l = 0; l < VDN_MAX_LAYERS; ++l) a.save_z[l] = (save && l < ly.L - 1) ? save_z[l] : nullptr;
   static int num_sms = 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -381,16 +420,22 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(sdf_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM);
+      e = cudaFuncSetAttribute(sdf_chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(sdf_chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const long long ntiles = (N + 127) / 128;
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
   double flops = 0.0;
-  for (int l = 0; l < ly.L; ++l) flops += 2.0 * (double)N * a.layer[l].n_mma * a.layer[l].nkb * 64;
+  for (int l = 0; l < a.Lrun; ++l) flops += 2.0 * (double)N * a.layer[l].n_mma * a.layer[l].nkb * 64;
   prof_begin(PROF_TC, st, flops);
-  VDN_LAUNCH(sdf_chain_tc_kernel, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault, g_tc_dbg);
+  if (save) {
+    VDN_LAUNCH(sdf_chain_tc_kernel<true>, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault, g_tc_dbg);
+  } else {
+    VDN_LAUNCH(sdf_chain_tc_kernel<false>, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault, g_tc_dbg);
+  }
   prof_end(PROF_TC, st);
   return (int)cudaGetLastError();
 }

@@ -149,7 +149,18 @@ static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x
   carve_blob(c, N, save, blob, &b);
   int e = launch_embed(c, x, N, b, st);
   if (e) return e;
-  for (int l = 0; l < c.L; ++l) {
+  int l0 = 0;
+  if (g_mode == 1) {
+    // tensor-core mode: layers 0..L-2 in the fused chain kernel, which stores the pre-activations the gradient passes
+    // need (all of them when saving, else only the last layer's input) and the head of the skip layer's input
+    float* zs[VDN_MAX_LAYERS];
+    for (int l = 0; l < c.L - 1; ++l) zs[l] = (save || l == c.L - 2) ? b.Z[l] : nullptr;
+    int r = launch_sdf_chain(c.ly, c.d_in, c.multires, c.d_hidden, c.skip, c.scale, packed, x, nullptr, nullptr, nullptr,
+                             0, 0, 0, N, nullptr, 0, 1.0f, st, zs, save ? b.U : nullptr, c.ldH);
+    if (r > 0) return r;
+    if (r == 0) l0 = c.L - 1;
+  }
+  for (int l = l0; l < c.L; ++l) {
     Operand A = input_operand(c, b, l);
     const float* bias = packed + c.ly.off_b[l];
     Epilogue E;
