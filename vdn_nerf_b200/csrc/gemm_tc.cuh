@@ -244,7 +244,8 @@ inline bool epilogue_vec_ok(const Epilogue& e) {
 
 static __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bimg, int img_rows, int row0,
-                  Epilogue E, int vec_ok, int* __restrict__ fault, long long* __restrict__ dbg) {
+                  Epilogue E, int vec_ok, const float* __restrict__ wextra, int* __restrict__ fault,
+                  long long* __restrict__ dbg) {
   using namespace tc;
   // optional timeline of CTA 0 (debug): dbg[role*64 + event] = clock64()
   const bool rec = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
@@ -295,6 +296,10 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     const int mlim = M - m0 - rbase;                              // group i is a valid row iff 4 i < mlim
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int pf_kb = nkb > 4 ? nkb - 4 : 0;
+    // optional output column N (one past the MMA tile, e.g. the 257th output of the stacked sdf|feature and
+    // alpha|feature heads): a plain fp32 dot product accumulated by the producers from the operand values they hold,
+    // instead of a second N tile that would re-read the whole operand for a single column
+    float ext[4] = {0.f, 0.f, 0.f, 0.f};
     RawLoad raw0[4], raw1[4];
     auto gload = [&](int kb, RawLoad (&raw)[4]) {
       const int col = kb * 32 + chunk * 4;
@@ -327,6 +332,12 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
         v[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
       }
       if (tid == 0) VDN_TL(4, 2 * kb + 1);
+      if (wextra) {
+        const float4 w4 = col < A.width ? __ldg(reinterpret_cast<const float4*>(wextra + col)) : zero4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          ext[i] = fmaf(v[i].x, w4.x, fmaf(v[i].y, w4.y, fmaf(v[i].z, w4.z, fmaf(v[i].w, w4.w, ext[i]))));
+      }
       if (kb + 2 < nkb) gload(kb + 2, raw);          // refill the buffer just consumed
       if (kb == pf_kb) {                             // epilogue operands of this thread -> L2, a few K blocks ahead
         const int nch_e = (n_cta + 31) >> 5;
@@ -359,6 +370,16 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     for (int kb = 0; kb < nkb && ok; kb += 2) {
       produce(kb, raw0);
       if (kb + 1 < nkb && ok) produce(kb + 1, raw1);
+    }
+    if (wextra) {                                   // reduce over the 8 lanes that share a row, lane 0 of them stores
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float e = ext[i];
+        e += __shfl_xor_sync(0xffffffffu, e, 1);
+        e += __shfl_xor_sync(0xffffffffu, e, 2);
+        e += __shfl_xor_sync(0xffffffffu, e, 4);
+        if (chunk == 0 && 4 * i < mlim) epi_store(E, m0 + rbase + 4 * i, N, e);
+      }
     }
   } else if (tid == 8 * 32) {
     // ---- MMA issuer ------------------------------------------------------------------------------
@@ -478,10 +499,17 @@ static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((M + TC_BM - 1) / TC_BM, (N + 255) / 256);
+  // N = 257 (a 256-wide head stacked with a scalar one): the last column rides along in the producers
+  const float* wextra = nullptr;
+  int n_main = N;
+  if (N == 257 && B.row0 == 0 && B.w && (B.ld & 3) == 0 && ((uintptr_t)B.w & 15) == 0) {
+    wextra = B.w + (size_t)256 * B.ld;
+    n_main = 256;
+  }
+  dim3 grid((M + TC_BM - 1) / TC_BM, (n_main + 255) / 256);
   prof_begin(PROF_TC, st, 2.0 * M * N * K);
-  VDN_LAUNCH(gemm_nt_tc_kernel, grid, TC_THREADS, smem, st, M, N, nkb, A, B.img, B.img_rows, B.row0, E,
-             epilogue_vec_ok(E) ? 1 : 0, g_tc_fault, g_tc_dbg);
+  VDN_LAUNCH(gemm_nt_tc_kernel, grid, TC_THREADS, smem, st, M, n_main, nkb, A, B.img, B.img_rows, B.row0, E,
+             epilogue_vec_ok(E) ? 1 : 0, wextra, g_tc_fault, g_tc_dbg);
   prof_end(PROF_TC, st);
   return (int)cudaGetLastError();
 }

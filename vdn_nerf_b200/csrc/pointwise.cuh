@@ -17,8 +17,16 @@ static __global__ void embed_rows_kernel(const float* __restrict__ x, int ldx, l
   const int wt = we + wu;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * wt) return;
-  const long long m = idx / wt;
-  int c = (int)(idx - m * wt);
+  long long m;
+  int c;
+  if (N * wt < 0x7fffffffLL) {   // 32-bit division where it fits (the 64-bit one costs more than the sin/cos)
+    const unsigned mi = (unsigned)idx / (unsigned)wt;
+    m = mi;
+    c = (int)((unsigned)idx - mi * (unsigned)wt);
+  } else {
+    m = idx / wt;
+    c = (int)(idx - m * wt);
+  }
   const bool to_u = c >= we;
   if (to_u) c -= we;
   const int d_e = d * (1 + 2 * L);
