@@ -268,7 +268,7 @@ def run_ours(args):
         fn(0)
         import ctypes
         fam_ms, fam_n = 0.0, 0
-        for f in (0, 2):
+        for f in (0, 2, 3):
             msn, sp, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
             lib.vdn_prof_read(f, ctypes.byref(msn), ctypes.byref(sp), ctypes.byref(fl))
             fam_ms += msn.value
@@ -328,14 +328,40 @@ def run_ours(args):
         lib.vdn_prof_enable(1)
         fn(0)
         fam = {}
-        for f, nm in ((0, "gemm_nt"), (1, "wgrad"), (2, "tc")):
-            msn, sp, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        for f, nm in ((0, "gemm_nt"), (1, "wgrad"), (2, "tc"), (3, "chain")):
+            msn, sp, fl, by = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_double()
             lib.vdn_prof_read(f, ctypes.byref(msn), ctypes.byref(sp), ctypes.byref(fl))
-            fam[nm] = (msn.value, sp.value, fl.value)
+            lib.vdn_prof_read_bytes(f, ctypes.byref(by))
+            fam[nm] = (msn.value, sp.value, fl.value, by.value)
         lib.vdn_prof_enable(0)
-        gemm_ms = fam["gemm_nt"][0] + fam["wgrad"][0] + fam["tc"][0]
+        gemm_ms = sum(v[0] for v in fam.values())
         alg = alg_flops_per_ray(depth) * B
         ach = alg / (gemm_ms * 1e-3) / 1e12
+        tensor_view = {"achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                       "algorithmic_flops_per_step": alg, "executed_flops_per_step": sum(v[2] for v in fam.values()),
+                       "peak_source": pk["source"] + " bf16 sustained (dense tf32 peak is half of it)"}
+        common = {"launches_by_family": {k: v[1] for k, v in fam.items()}, "ms_by_family": {k: v[0] for k, v in fam.items()},
+                  "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps)}
+        if args.precision == "tf32":
+            # the layer-wise tcgen05 GEMMs stream every activation through HBM once per layer: they are bandwidth bound
+            dom = "tc" if fam["tc"][0] >= fam["wgrad"][0] else "wgrad"
+            gbs = fam[dom][3] / (fam[dom][0] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "%s (layer-wise tcgen05 kind::tf32 GEMM with fused prologue/epilogue), %d launches "
+                    "per step; algorithmic bytes = every operand / output / auxiliary element once"
+                    % ("gemm_nt_tc_kernel" if dom == "tc" else "gemm_tn_tc_kernel", fam[dom][1]),
+                    "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                    "algorithmic_bytes_per_step": fam[dom][3], "kernel_ms": fam[dom][0],
+                    "peak_source": pk["source"] + " hbm (copy)",
+                    "all_gemm_families": {k: {"ms": v[0], "launches": v[1], "GB/s": (v[3] / (v[0] * 1e-3) / 1e9) if v[0] else 0.0,
+                                              "TFLOP/s": (v[2] / (v[0] * 1e-3) / 1e12) if v[0] else 0.0}
+                                          for k, v in fam.items()},
+                    "tensor_view": tensor_view}
+        else:
+            roof = dict(tensor_view)
+            roof.update({"bound": "tensor", "traffic": None,
+                         "kernel": "all MLP contractions of one step: gemm_nt_kernel (FFMA) x%d, gemm_tn_kernel (wgrad) x%d"
+                         % (fam["gemm_nt"][1], fam["wgrad"][1])})
+        roof.update(common)
         line.update({"metric": "train_rays_per_s", "unit": "rays/s", "value": value, "ms_per_step": ms / args.steps,
                      "config": {"workload": "womsk_white%s training step (BASELINE configs[%d]): render fwd + driver "
                                             "loss + bwd%s" % ("_wdepth" if depth else "", 2 if depth else 1,
@@ -345,16 +371,7 @@ def run_ours(args):
                                 "l2": "256 MiB flush between timed iterations"},
                      "e2e": {"value": B * world / e2e_t, "unit": "rays/s",
                              "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)), "d2h_bytes_per_step": 4},
-                     "roofline": {"bound": "tensor", "kernel": "all MLP contractions of one step: gemm_nt_tc_kernel (tcgen05) x%d, "
-                                  "gemm_nt_kernel (FFMA) x%d, gemm_tn_kernel (wgrad) x%d"
-                                  % (fam["tc"][1], fam["gemm_nt"][1], fam["wgrad"][1]),
-                                  "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                                  "frac": ach / pk["bf16_sustained"], "traffic": None,
-                                  "algorithmic_flops_per_step": alg,
-                                  "executed_flops_per_step": fam["gemm_nt"][2] + fam["wgrad"][2] + fam["tc"][2],
-                                  "ms_by_family": {k: v[0] for k, v in fam.items()},
-                                  "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps),
-                                  "peak_source": pk["source"] + " bf16 sustained (dense tf32 peak is half of it)"}})
+                     "roofline": roof})
         cpu_kind = "train"
 
     clocks = cs.summary()

@@ -46,10 +46,13 @@ int vdn_tc_fault(void);
 int vdn_debug_timeline(long long* device_buf);
 
 /* Measurement aid for bench.py: when enabled, CUDA events bracket every launch of a kernel family on its
- * stream (0 = gemm_nt, 1 = weight-gradient gemm_tn + reduce, 2 = tcgen05 chain kernels); vdn_prof_read sums the
- * recorded durations (ms), the number of spans and the executed FLOPs.  Enabling/disabling clears the record. */
+ * stream (0 = FFMA gemm_nt, 1 = weight-gradient gemm_tn (+ reduce), 2 = layer-wise tcgen05 gemm_nt, 3 = fused SDF chain
+ * kernel); vdn_prof_read sums the recorded durations (ms), the number of spans and the executed FLOPs,
+ * vdn_prof_read_bytes the algorithmic HBM bytes (every operand / output element once).  Enabling/disabling clears
+ * the record. */
 int vdn_prof_enable(int on);
 int vdn_prof_read(int family, double* ms /*host*/, long long* spans /*host*/, double* flops /*host*/);
+int vdn_prof_read_bytes(int family, double* bytes /*host*/);
 
 /* ---- packed parameters (weight_norm: fields.py:65-66, 141-142; nn.Linear: fields.py:303-318) ------------ */
 long long vdn_mlp_layout(int L, const int* in_dims /*host*/, const int* out_dims /*host*/, long long* off_w /*host*/,

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdn_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 
@@ -23,6 +23,7 @@ SIGNATURES = {
     "vdn_error_string": (c_char_p, [I]),
     "vdn_prof_enable": (I, [I]),
     "vdn_prof_read": (I, [I, P, P, P]),
+    "vdn_prof_read_bytes": (I, [I, P]),
     "vdn_mlp_layout": (L, [I, P, P, P, P, P]),
     "vdn_mlp_pack": (I, [I, P, P, P, P, P, P, P, P, P]),
     "vdn_mlp_unpack_grads": (I, [I, P, P, P, P, P, P, P, P, P, P, P]),

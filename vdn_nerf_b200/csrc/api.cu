@@ -16,15 +16,17 @@ static bool g_prof_on = false;
 struct ProfSpan { cudaEvent_t a, b; };
 static std::vector<ProfSpan> g_spans[PROF_FAMILIES];
 static double g_flops[PROF_FAMILIES];
+static double g_bytes[PROF_FAMILIES];
 static cudaEvent_t g_open[PROF_FAMILIES];
 
-void prof_begin(int family, cudaStream_t st, double flops) {
+void prof_begin(int family, cudaStream_t st, double flops, double bytes) {
   if (!g_prof_on) return;
   cudaEvent_t a;
   cudaEventCreate(&a);
   cudaEventRecord(a, st);
   g_open[family] = a;
   g_flops[family] += flops;
+  g_bytes[family] += bytes;
 }
 void prof_end(int family, cudaStream_t st) {
   if (!g_prof_on) return;
@@ -36,7 +38,7 @@ void prof_end(int family, cudaStream_t st) {
 }  // namespace vdn
 using namespace vdn;
 
-extern "C" int vdn_abi_version(void) { return 2; }
+extern "C" int vdn_abi_version(void) { return 3; }
 extern "C" long long vdn_launch_count(void) { return g_launches.load(); }
 extern "C" const char* vdn_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
@@ -70,6 +72,7 @@ extern "C" int vdn_prof_enable(int on) {
     for (auto& s : g_spans[f]) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     g_spans[f].clear();
     g_flops[f] = 0.0;
+    g_bytes[f] = 0.0;
   }
   return 0;
 }
@@ -87,6 +90,12 @@ extern "C" int vdn_prof_read(int family, double* ms, long long* spans, double* f
   *ms = total;
   *spans = (long long)g_spans[family].size();
   *flops = g_flops[family];
+  return 0;
+}
+
+extern "C" int vdn_prof_read_bytes(int family, double* bytes) {
+  if (family < 0 || family >= PROF_FAMILIES) return (int)cudaErrorInvalidValue;
+  *bytes = g_bytes[family];
   return 0;
 }
 

@@ -396,16 +396,32 @@ inline bool operand_ok(const Operand& o) {
 }
 
 // Optional per-family timing (vdn_prof_enable): CUDA events around the GEMM launches on the launching stream.
-void prof_begin(int family, cudaStream_t st, double flops);
+void prof_begin(int family, cudaStream_t st, double flops, double bytes = 0.0);
 void prof_end(int family, cudaStream_t st);
-enum { PROF_GEMM_NT = 0, PROF_WGRAD = 1, PROF_TC = 2, PROF_FAMILIES = 3 };
+enum { PROF_GEMM_NT = 0, PROF_WGRAD = 1, PROF_TC = 2, PROF_CHAIN = 3, PROF_FAMILIES = 4 };
+
+// Algorithmic HBM bytes of one GEMM launch: every operand / output element moved once (weights are L2 resident).
+inline double operand_bytes(const Operand& A, double M) {
+  return 4.0 * M * (A.kvalid < A.width ? A.kvalid : A.width) * (A.kind >= PRO_DSIG ? 2.0 : 1.0);
+}
+inline double epilogue_bytes(const Epilogue& E, double M, double N) {
+  double per = 1.0;
+  switch (E.kind) {
+    case EPI_SDF_SKIP: per = E.c ? 2.0 : 1.0; break;
+    case EPI_ADD_SCALED: case EPI_RELU_MASK: per = 2.0; break;
+    case EPI_GRAD_DUAL: per = (E.ldaux2 ? 4.0 : 3.0); break;
+    case EPI_BWD_INJECT: per = E.aux2 ? 3.0 : 2.0; break;
+    default: break;
+  }
+  return 4.0 * M * N * per;
+}
 
 inline int launch_gemm_nt_simt(int M, int N, int K, const Operand& A, const float* B, int ldb, const Epilogue& E,
                           cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   if (K % GEMM_BK != 0 || !operand_ok(A) || ((uintptr_t)B & 15) || (ldb & 3)) return (int)cudaErrorInvalidValue;
   dim3 grid((M + GEMM_BM - 1) / GEMM_BM, (N + GEMM_BN - 1) / GEMM_BN);
-  prof_begin(PROF_GEMM_NT, st, 2.0 * M * N * K);
+  prof_begin(PROF_GEMM_NT, st, 2.0 * M * N * K, operand_bytes(A, M) + epilogue_bytes(E, M, N));
   VDN_LAUNCH(gemm_nt_kernel, grid, GEMM_THREADS, 0, st, M, N, K, A, B, ldb, E);
   prof_end(PROF_GEMM_NT, st);
   return (int)cudaGetLastError();
@@ -430,7 +446,7 @@ inline int launch_wgrad(int M, int N, int K, const Operand& A0, const Operand& X
   const int rows_per_split = (rows + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
   const int ldp = K;
   dim3 grid((K + GEMM_BN - 1) / GEMM_BN, (N + GEMM_BM - 1) / GEMM_BM, S);
-  prof_begin(PROF_WGRAD, st, 2.0 * M * N * K * (A1 ? 2 : 1));
+  prof_begin(PROF_WGRAD, st, 2.0 * M * N * K * (A1 ? 2 : 1), operand_bytes(A0, M) + operand_bytes(X0, M));
   VDN_LAUNCH(gemm_tn_kernel, grid, GEMM_THREADS, 0, st, M, N, K, A0, X0, A1 ? *A1 : A0, X1 ? *X1 : X0, A1 ? 2 : 1,
                                                 partials, ldp, rows_per_split);
   int e = (int)cudaGetLastError();

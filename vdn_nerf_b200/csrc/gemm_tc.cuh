@@ -507,7 +507,7 @@ static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const
     n_main = 256;
   }
   dim3 grid((M + TC_BM - 1) / TC_BM, (n_main + 255) / 256);
-  prof_begin(PROF_TC, st, 2.0 * M * N * K);
+  prof_begin(PROF_TC, st, 2.0 * M * N * K, operand_bytes(A, M) + epilogue_bytes(E, M, N));
   VDN_LAUNCH(gemm_nt_tc_kernel, grid, TC_THREADS, smem, st, M, n_main, nkb, A, B.img, B.img_rows, B.row0, E,
              epilogue_vec_ok(E) ? 1 : 0, wextra, g_tc_fault, g_tc_dbg);
   prof_end(PROF_TC, st);

@@ -298,7 +298,7 @@ static inline int launch_wgrad_tc(int M, int N, int K, const Operand& A0, const 
     attr_set = true;
   }
   dim3 grid((N + 127) / 128, S, (K + 255) / 256);
-  prof_begin(PROF_WGRAD, st, 2.0 * M * N * K);
+  prof_begin(PROF_WGRAD, st, 2.0 * M * N * K, operand_bytes(A0, M) + operand_bytes(X0, M));
   if (accumulate) {
     VDN_LAUNCH(gemm_tn_tc_kernel, grid, TN_THREADS, smem, st, M, N, K, A0, X0, dW, ldd, rows, 1, db, g_tc_fault);
   } else {

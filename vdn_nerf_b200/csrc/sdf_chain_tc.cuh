@@ -430,13 +430,19 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
   const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
   double flops = 0.0;
   for (int l = 0; l < a.Lrun; ++l) flops += 2.0 * (double)N * a.layer[l].n_mma * a.layer[l].nkb * 64;
-  prof_begin(PROF_TC, st, flops);
+  double bytes = (double)N * (x ? 16.0 : 4.0);
+  if (save) {
+    bytes = (double)N * 12.0;
+    for (int l = 0; l < a.Lrun; ++l) bytes += a.save_z[l] ? 4.0 * N * a.layer[l].out_dim : 0.0;
+    if (a.save_u && skip >= 1) bytes += 4.0 * N * a.layer[skip - 1].out_dim;
+  }
+  prof_begin(PROF_CHAIN, st, flops, bytes);
   if (save) {
     VDN_LAUNCH(sdf_chain_tc_kernel<true>, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault, g_tc_dbg);
   } else {
     VDN_LAUNCH(sdf_chain_tc_kernel<false>, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault, g_tc_dbg);
   }
-  prof_end(PROF_TC, st);
+  prof_end(PROF_CHAIN, st);
   return (int)cudaGetLastError();
 }
 
