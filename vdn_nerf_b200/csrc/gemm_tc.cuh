@@ -244,13 +244,19 @@ inline bool epilogue_vec_ok(const Epilogue& e) {
 
 static __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bimg, int img_rows, int row0,
-                  Epilogue E, int vec_ok, const float* __restrict__ wextra, int* __restrict__ fault,
+                  Epilogue E, int vec_ok, const float* __restrict__ wextra, int async_a, int* __restrict__ fault,
                   long long* __restrict__ dbg) {
   using namespace tc;
   // optional timeline of CTA 0 (debug): dbg[role*64 + event] = clock64()
   const bool rec = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 #define VDN_TL(role, ev) do { if (rec) dbg[(role) * 64 + (ev)] = clock64(); } while (0)
   if (threadIdx.x == 0) VDN_TL(0, 0);
+  if (dbg && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 1500) {   // per-CTA start / SM id (debug)
+    unsigned long long g; unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    dbg[1024 + 4 * blockIdx.x] = (long long)g; dbg[1024 + 4 * blockIdx.x + 2] = sm;
+  }
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc;
   __shared__ uint32_t tmem_base_s;
@@ -266,7 +272,7 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
 
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 256 + 1);   // 256 producer threads + the expect_tx arrival of the weight tile
+      mbar_init(smem_u32(&bar_full[s]), 8 + 1);     // one arrival per producer warp + the expect_tx arrival of the weight tile
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
@@ -360,16 +366,81 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
                      "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
                      : "memory");
       if (tid == 0) VDN_TL(5, 2 * kb);
-      fence_proxy_async();
+      fence_proxy_async();                           // own stores -> visible to the tensor core's (async proxy) reads
       if (tid == 0) VDN_TL(5, 2 * kb + 1);
-      mbar_arrive(smem_u32(&bar_full[s]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
       if (tid == 0) VDN_TL(1, 3 * kb + 2);
     };
+    if (async_a) {
+      // ---- plain operand (no prologue): the rows go global -> shared memory with cp.async, 16 bytes per thread and
+      // instruction straight into their swizzled positions (zero fill outside the operand), no registers, ~20
+      // instead of ~300 instructions per thread and K block.  One K block later the same thread rounds its own four
+      // chunks to tf32 in place (and clears the columns past the logical width), fences them for the tensor core and
+      // signals the stage. ----
+      auto finish = [&](int kb) {
+        const int s = kb & 1;
+        const int col = kb * 32 + chunk * 4;
+        const uint32_t base = smem0 + (uint32_t)s * stage_stride;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t addr = base + ((i & 1) ? soff_o : soff_e) + (uint32_t)(i >> 1) * 1024u;
+          uint32_t x, y, z, w;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr));
+          // round to nearest (ties away) on the 13 dropped mantissa bits: the operands of this path are finite
+          x = (x + 0x1000u) & 0xffffe000u; y = (y + 0x1000u) & 0xffffe000u;
+          z = (z + 0x1000u) & 0xffffe000u; w = (w + 0x1000u) & 0xffffe000u;
+          if (col + 0 >= A.kvalid) x = 0u;
+          if (col + 1 >= A.kvalid) y = 0u;
+          if (col + 2 >= A.kvalid) z = 0u;
+          if (col + 3 >= A.kvalid) w = 0u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+      };
+      for (int kb = 0; kb < nkb && ok; ++kb) {
+        const int s = kb & 1, ph = (kb >> 1) & 1;
+        ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+        const uint32_t base = smem0 + (uint32_t)s * stage_stride;
+        if (tid == 0) {                              // the stage is free: stream its weight tile (TMA engine)
+          const uint32_t bytes = (uint32_t)n_mma * 128u;
+          mbar_arrive_expect_tx(smem_u32(&bar_full[s]), bytes);
+          bulk_g2s(base + 16384u, Bimg + ((size_t)kb * img_rows + row0 + n_base) * 32, bytes, smem_u32(&bar_full[s]));
+        }
+        const bool cok = kb * 32 + chunk * 4 < A.width;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool p = cok && (4 * i < mlim);
+          const float* src = p ? pa0 + i * stepa + kb * 32 : A.p;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + ((i & 1) ? soff_o : soff_e) +
+                                                                              (uint32_t)(i >> 1) * 1024u),
+                       "l"(src), "r"(p ? 16 : 0)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (kb == pf_kb) {
+          const int nch_e = (n_cta + 31) >> 5;
+          for (int ch = warp >> 2; ch < nch_e; ch += 2)
+            tc_epilogue_prefetch(E, m0 + (warp & 3) * 32 + (lane >> 3), M, n_base + ch * 32 + chunk * 4, N);
+        }
+        if (kb > 0) {
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          finish(kb - 1);
+        }
+      }
+      if (ok && nkb > 0) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        finish(nkb - 1);
+      }
+    } else {
     gload(0, raw0);
     if (nkb > 1) gload(1, raw1);
     for (int kb = 0; kb < nkb && ok; kb += 2) {
       produce(kb, raw0);
       if (kb + 1 < nkb && ok) produce(kb + 1, raw1);
+    }
     }
     if (wextra) {                                   // reduce over the 8 lanes that share a row, lane 0 of them stores
 #pragma unroll
@@ -462,6 +533,11 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, ncols);
   if (threadIdx.x == 0) VDN_TL(0, 4);
+  if (dbg && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 1500) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    dbg[1024 + 4 * blockIdx.x + 1] = (long long)g;
+  }
 #undef VDN_TL
 }
 
@@ -487,15 +563,24 @@ extern int g_mode;           // 0: exact fp32 (FFMA kernels), 1: tf32 tensor cor
 extern int* g_tc_fault;      // device flag raised by a timed-out barrier wait in a tcgen05 kernel
 extern long long* g_tc_dbg;  // optional device buffer (256 int64) receiving CTA 0's timeline (vdn_debug_timeline)
 
+static inline bool nt_async_enabled() {
+  static int f = -1;
+  if (f < 0) { const char* e = getenv("VDN_NT_SYNC"); f = (e && atoi(e)) ? 0 : 1; }
+  return f != 0;
+}
+
 static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const WeightRef& B, const Epilogue& E,
                                     cudaStream_t st) {
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int n_mma_max = ((N < 256 ? N : 256) + 15) & ~15;
   const size_t stage = ((size_t)16384 + (size_t)n_mma_max * 128 + 1023) & ~(size_t)1023;
-  const size_t smem = TC_STAGES * stage + 1024;
+  size_t smem = TC_STAGES * stage + 1024;
+  static int one = -1;
+  if (one < 0) { const char* ev = getenv("VDN_NT_ONE"); one = ev ? atoi(ev) : 0; }
+  if (one) smem = 130 * 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -508,8 +593,18 @@ static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const
   }
   dim3 grid((M + TC_BM - 1) / TC_BM, (n_main + 255) / 256);
   prof_begin(PROF_TC, st, 2.0 * M * N * K, operand_bytes(A, M) + epilogue_bytes(E, M, N));
+  // debug timeline: record only the launch selected by VDN_DBG_LAUNCH (index since the buffer was installed)
+  long long* dbg = g_tc_dbg;
+  if (dbg) {
+    static int sel = -2;
+    static int count = 0;
+    static long long* last = nullptr;
+    if (sel == -2) { const char* ev = getenv("VDN_DBG_LAUNCH"); sel = ev ? atoi(ev) : -1; }
+    if (last != dbg) { last = dbg; count = 0; }
+    if (sel >= 0 && count++ != sel) dbg = nullptr;
+  }
   VDN_LAUNCH(gemm_nt_tc_kernel, grid, TC_THREADS, smem, st, M, n_main, nkb, A, B.img, B.img_rows, B.row0, E,
-             epilogue_vec_ok(E) ? 1 : 0, wextra, g_tc_fault, g_tc_dbg);
+             epilogue_vec_ok(E) ? 1 : 0, wextra, (A.kind == PRO_NONE && !wextra && nt_async_enabled()) ? 1 : 0, g_tc_fault, dbg);
   prof_end(PROF_TC, st);
   return (int)cudaGetLastError();
 }

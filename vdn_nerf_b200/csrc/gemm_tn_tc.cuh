@@ -56,7 +56,7 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
 
   if (tid == 0) {
     for (int s = 0; s < TN_STAGES; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), TN_PWARPS * 32);
+      mbar_init(smem_u32(&bar_full[s]), TN_PWARPS);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_acc), 1);
@@ -160,7 +160,8 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
                        "f"(vx[t].x), "f"(vx[t].y), "f"(vx[t].z), "f"(vx[t].w)
                        : "memory");
       fence_proxy_async();
-      mbar_arrive(smem_u32(&bar_full[s]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
       if (warp == 0 && st > 0 && ok) issue(st - 1);
     };
     TnRaw R0, R1;
