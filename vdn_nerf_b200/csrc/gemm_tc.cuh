@@ -244,7 +244,7 @@ inline bool epilogue_vec_ok(const Epilogue& e) {
 
 static __global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bimg, int img_rows, int row0,
-                  Epilogue E, int vec_ok, const float* __restrict__ wextra, int async_a, int* __restrict__ fault,
+                  Epilogue E, int vec_ok, const float* __restrict__ wextra, int* __restrict__ fault,
                   long long* __restrict__ dbg) {
   using namespace tc;
   // optional timeline of CTA 0 (debug): dbg[role*64 + event] = clock64()
@@ -306,50 +306,14 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
     // alpha|feature heads): a plain fp32 dot product accumulated by the producers from the operand values they hold,
     // instead of a second N tile that would re-read the whole operand for a single column
     float ext[4] = {0.f, 0.f, 0.f, 0.f};
-    RawLoad raw0[4], raw1[4];
-    auto gload = [&](int kb, RawLoad (&raw)[4]) {
-      const int col = kb * 32 + chunk * 4;
-      const bool cok = col < A.width;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bool p = cok && (4 * i < mlim);
-        raw[i].a = p ? *reinterpret_cast<const float4*>(pa0 + i * stepa + kb * 32) : zero4;
-        raw[i].b = (p && two) ? *reinterpret_cast<const float4*>(pb0 + i * stepb + kb * 32) : zero4;
-      }
-    };
-    auto produce = [&](int kb, RawLoad (&raw)[4]) {
+    // The rows go global -> shared memory with cp.async, 16 bytes per thread and instruction straight into their
+    // swizzled positions (zero fill outside the operand): no staging registers, no per-element address arithmetic.
+    // The second operand of the two-operand prologues travels through registers (one K block in flight).  One K block
+    // later the same thread applies the prologue to its own four chunks in place, rounds them to tf32, clears what
+    // lies outside the logical extent, fences the stores for the tensor core and signals the stage.
+    float4 b0[4], b1[4];
+    auto issue = [&](int kb, float4 (&bq)[4]) {
       const int s = kb & 1, ph = (kb >> 1) & 1;
-      const int col = kb * 32 + chunk * 4;
-      float4 v[4];
-      if (tid == 0) VDN_TL(4, 2 * kb);
-      tc_prologue4(A, raw, v);
-      if (col + 3 >= A.kvalid || col >= A.width) {  // ragged K edge: zero the columns beyond the logical extent
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (col + 0 >= A.kvalid) v[i].x = 0.f;
-          if (col + 1 >= A.kvalid) v[i].y = 0.f;
-          if (col + 2 >= A.kvalid) v[i].z = 0.f;
-          if (col + 3 >= A.kvalid) v[i].w = 0.f;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (!(4 * i < mlim)) v[i] = zero4;
-        v[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
-      }
-      if (tid == 0) VDN_TL(4, 2 * kb + 1);
-      if (wextra) {
-        const float4 w4 = col < A.width ? __ldg(reinterpret_cast<const float4*>(wextra + col)) : zero4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          ext[i] = fmaf(v[i].x, w4.x, fmaf(v[i].y, w4.y, fmaf(v[i].z, w4.z, fmaf(v[i].w, w4.w, ext[i]))));
-      }
-      if (kb + 2 < nkb) gload(kb + 2, raw);          // refill the buffer just consumed
-      if (kb == pf_kb) {                             // epilogue operands of this thread -> L2, a few K blocks ahead
-        const int nch_e = (n_cta + 31) >> 5;
-        for (int ch = warp >> 2; ch < nch_e; ch += 2)
-          tc_epilogue_prefetch(E, m0 + (warp & 3) * 32 + (lane >> 3), M, n_base + ch * 32 + chunk * 4, N);
-      }
       if (tid == 0) VDN_TL(1, 3 * kb);
       ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
       if (tid == 0) VDN_TL(1, 3 * kb + 1);
@@ -359,88 +323,88 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
         mbar_arrive_expect_tx(smem_u32(&bar_full[s]), bytes);
         bulk_g2s(base + 16384u, Bimg + ((size_t)kb * img_rows + row0 + n_base) * 32, bytes, smem_u32(&bar_full[s]));
       }
+      const bool cok = kb * 32 + chunk * 4 < A.width;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool p = cok && (4 * i < mlim);
+        const float* src = p ? pa0 + i * stepa + kb * 32 : A.p;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + ((i & 1) ? soff_o : soff_e) +
+                                                                            (uint32_t)(i >> 1) * 1024u),
+                     "l"(src), "r"(p ? 16 : 0)
+                     : "memory");
+        if (two) bq[i] = p ? *reinterpret_cast<const float4*>(pb0 + i * stepb + kb * 32) : zero4;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (kb == pf_kb) {                             // epilogue operands of this thread -> L2, a few K blocks ahead
+        const int nch_e = (n_cta + 31) >> 5;
+        for (int ch = warp >> 2; ch < nch_e; ch += 2)
+          tc_epilogue_prefetch(E, m0 + (warp & 3) * 32 + (lane >> 3), M, n_base + ch * 32 + chunk * 4, N);
+      }
+    };
+    auto finish = [&](int kb, const float4 (&bq)[4]) {
+      const int s = kb & 1;
+      const int col = kb * 32 + chunk * 4;
+      const uint32_t base = smem0 + (uint32_t)s * stage_stride;
+      RawLoad raw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t addr = base + ((i & 1) ? soff_o : soff_e) + (uint32_t)(i >> 1) * 1024u;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(raw[i].a.x), "=f"(raw[i].a.y), "=f"(raw[i].a.z), "=f"(raw[i].a.w)
+                     : "r"(addr));
+        raw[i].b = bq[i];
+      }
+      float4 v[4];
+      tc_prologue4(A, raw, v);
+      if (A.kind == PRO_SOFTPLUS) {                  // the only prologue that does not map 0 to 0: re-clear the padding
+        const bool cok = col < A.width;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (!(cok && 4 * i < mlim)) v[i] = zero4;
+      }
+      if (col + 3 >= A.kvalid) {                     // ragged K edge: zero the columns beyond the logical extent
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (col + 0 >= A.kvalid) v[i].x = 0.f;
+          if (col + 1 >= A.kvalid) v[i].y = 0.f;
+          if (col + 2 >= A.kvalid) v[i].z = 0.f;
+          if (col + 3 >= A.kvalid) v[i].w = 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = make_float4(to_tf32(v[i].x), to_tf32(v[i].y), to_tf32(v[i].z), to_tf32(v[i].w));
+      if (wextra) {
+        const float4 w4 = col < A.width ? __ldg(reinterpret_cast<const float4*>(wextra + col)) : zero4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          ext[i] = fmaf(v[i].x, w4.x, fmaf(v[i].y, w4.y, fmaf(v[i].z, w4.z, fmaf(v[i].w, w4.w, ext[i]))));
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((i & 1) ? soff_o : soff_e) +
                                                                      (uint32_t)(i >> 1) * 1024u),
                      "f"(v[i].x), "f"(v[i].y), "f"(v[i].z), "f"(v[i].w)
                      : "memory");
-      if (tid == 0) VDN_TL(5, 2 * kb);
       fence_proxy_async();                           // own stores -> visible to the tensor core's (async proxy) reads
-      if (tid == 0) VDN_TL(5, 2 * kb + 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
       if (tid == 0) VDN_TL(1, 3 * kb + 2);
     };
-    if (async_a) {
-      // ---- plain operand (no prologue): the rows go global -> shared memory with cp.async, 16 bytes per thread and
-      // instruction straight into their swizzled positions (zero fill outside the operand), no registers, ~20
-      // instead of ~300 instructions per thread and K block.  One K block later the same thread rounds its own four
-      // chunks to tf32 in place (and clears the columns past the logical width), fences them for the tensor core and
-      // signals the stage. ----
-      auto finish = [&](int kb) {
-        const int s = kb & 1;
-        const int col = kb * 32 + chunk * 4;
-        const uint32_t base = smem0 + (uint32_t)s * stage_stride;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t addr = base + ((i & 1) ? soff_o : soff_e) + (uint32_t)(i >> 1) * 1024u;
-          uint32_t x, y, z, w;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(addr));
-          // round to nearest (ties away) on the 13 dropped mantissa bits: the operands of this path are finite
-          x = (x + 0x1000u) & 0xffffe000u; y = (y + 0x1000u) & 0xffffe000u;
-          z = (z + 0x1000u) & 0xffffe000u; w = (w + 0x1000u) & 0xffffe000u;
-          if (col + 0 >= A.kvalid) x = 0u;
-          if (col + 1 >= A.kvalid) y = 0u;
-          if (col + 2 >= A.kvalid) z = 0u;
-          if (col + 3 >= A.kvalid) w = 0u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
-      };
-      for (int kb = 0; kb < nkb && ok; ++kb) {
-        const int s = kb & 1, ph = (kb >> 1) & 1;
-        ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
-        const uint32_t base = smem0 + (uint32_t)s * stage_stride;
-        if (tid == 0) {                              // the stage is free: stream its weight tile (TMA engine)
-          const uint32_t bytes = (uint32_t)n_mma * 128u;
-          mbar_arrive_expect_tx(smem_u32(&bar_full[s]), bytes);
-          bulk_g2s(base + 16384u, Bimg + ((size_t)kb * img_rows + row0 + n_base) * 32, bytes, smem_u32(&bar_full[s]));
-        }
-        const bool cok = kb * 32 + chunk * 4 < A.width;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool p = cok && (4 * i < mlim);
-          const float* src = p ? pa0 + i * stepa + kb * 32 : A.p;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + ((i & 1) ? soff_o : soff_e) +
-                                                                              (uint32_t)(i >> 1) * 1024u),
-                       "l"(src), "r"(p ? 16 : 0)
-                       : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (kb == pf_kb) {
-          const int nch_e = (n_cta + 31) >> 5;
-          for (int ch = warp >> 2; ch < nch_e; ch += 2)
-            tc_epilogue_prefetch(E, m0 + (warp & 3) * 32 + (lane >> 3), M, n_base + ch * 32 + chunk * 4, N);
-        }
-        if (kb > 0) {
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-          finish(kb - 1);
-        }
-      }
-      if (ok && nkb > 0) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        finish(nkb - 1);
-      }
-    } else {
-    gload(0, raw0);
-    if (nkb > 1) gload(1, raw1);
     for (int kb = 0; kb < nkb && ok; kb += 2) {
-      produce(kb, raw0);
-      if (kb + 1 < nkb && ok) produce(kb + 1, raw1);
+      issue(kb, b0);
+      if (kb > 0) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        finish(kb - 1, b1);
+      }
+      if (kb + 1 < nkb && ok) {
+        issue(kb + 1, b1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        finish(kb, b0);
+      }
     }
+    if (ok && nkb > 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (nkb & 1) finish(nkb - 1, b0); else finish(nkb - 1, b1);
     }
     if (wextra) {                                   // reduce over the 8 lanes that share a row, lane 0 of them stores
 #pragma unroll
@@ -563,24 +527,15 @@ extern int g_mode;           // 0: exact fp32 (FFMA kernels), 1: tf32 tensor cor
 extern int* g_tc_fault;      // device flag raised by a timed-out barrier wait in a tcgen05 kernel
 extern long long* g_tc_dbg;  // optional device buffer (256 int64) receiving CTA 0's timeline (vdn_debug_timeline)
 
-static inline bool nt_async_enabled() {
-  static int f = -1;
-  if (f < 0) { const char* e = getenv("VDN_NT_SYNC"); f = (e && atoi(e)) ? 0 : 1; }
-  return f != 0;
-}
-
 static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const WeightRef& B, const Epilogue& E,
                                     cudaStream_t st) {
   const int nkb = (K + TC_BK - 1) / TC_BK;
   const int n_mma_max = ((N < 256 ? N : 256) + 15) & ~15;
   const size_t stage = ((size_t)16384 + (size_t)n_mma_max * 128 + 1023) & ~(size_t)1023;
-  size_t smem = TC_STAGES * stage + 1024;
-  static int one = -1;
-  if (one < 0) { const char* ev = getenv("VDN_NT_ONE"); one = ev ? atoi(ev) : 0; }
-  if (one) smem = 130 * 1024;
+  const size_t smem = TC_STAGES * stage + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -604,7 +559,7 @@ static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const
     if (sel >= 0 && count++ != sel) dbg = nullptr;
   }
   VDN_LAUNCH(gemm_nt_tc_kernel, grid, TC_THREADS, smem, st, M, n_main, nkb, A, B.img, B.img_rows, B.row0, E,
-             epilogue_vec_ok(E) ? 1 : 0, wextra, (A.kind == PRO_NONE && !wextra && nt_async_enabled()) ? 1 : 0, g_tc_fault, dbg);
+             epilogue_vec_ok(E) ? 1 : 0, wextra, g_tc_fault, dbg);
   prof_end(PROF_TC, st);
   return (int)cudaGetLastError();
 }
