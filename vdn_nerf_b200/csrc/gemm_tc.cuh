@@ -4,14 +4,19 @@
 //   gemm_nt_tc : C[M,N] = epi( pro(A)[M,K] * W[N,K]^T + bias )
 //
 // One CTA owns a 128-row tile and up to 256 output columns; two CTAs are co-resident per SM so one tile's
-// epilogue overlaps the other's MMAs.  Warp roles: warps 0-7 transform the A operand (coalesced global loads two
-// K blocks ahead -> prologue -> tf32 round -> SWIZZLE_128B shared-memory image) and thread 0 streams the
-// pre-swizzled weight tile of each stage with cp.async.bulk (TMA engine); one thread of warp 8 issues tcgen05.mma
-// kind::tf32 into a TMEM accumulator; then the eight warps drain TMEM with tcgen05.ld, transpose through shared
-// memory and run the epilogue with coalesced global accesses.  A 2-stage mbarrier ring (full / empty) connects the roles; every wait is bounded and raises a
-// device fault flag instead of hanging.  The prologue / epilogue kind is switched once per tile-row group, outside
-// the per-element loops, so the executed instruction footprint stays small (the first version, with the switch
-// inlined per element, was instruction-fetch bound).
+// epilogue overlaps the other's MMAs.  Warp roles: warps 0-7 bring the A operand in with cp.async (16 bytes per
+// thread and instruction, straight into the SWIZZLE_128B shared-memory image, zero fill outside the operand) and,
+// one K block later, apply the fused prologue to their own chunks in place and round them to tf32; thread 0 streams
+// the pre-swizzled weight tile of each stage with cp.async.bulk (TMA engine); one thread of warp 8 issues
+// tcgen05.mma kind::tf32 into a TMEM accumulator; then the eight warps drain TMEM with tcgen05.ld, transpose
+// through shared memory and run the epilogue with coalesced global accesses (its auxiliary operands are pulled
+// into L2 a few K blocks ahead).  A 2-stage mbarrier ring (full / empty) connects the roles; every wait is bounded
+// and raises a device fault flag instead of hanging.  The prologue / epilogue kind is switched once per tile-row
+// group, outside the per-element loops.  History that shaped this: with the kind switch inlined per element the
+// kernel was instruction-fetch bound; with register-staged operand loads (address arithmetic, predicates and
+// conversion per element, ~300 instructions per thread and K block) it was issue bound in the producers - the
+// cp.async form needs ~60.  An output width of 257 (a 256-wide head stacked with a scalar one) is served by the
+// producers accumulating the extra column as an fp32 dot product instead of a second N tile.
 #pragma once
 #include "gemm_simt.cuh"
 #include "mlp_layout.cuh"
