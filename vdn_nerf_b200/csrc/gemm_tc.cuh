@@ -27,10 +27,11 @@ namespace vdn {
 constexpr int TC_BM = 128, TC_BK = 32, TC_STAGES = 2;
 constexpr int TC_THREADS = 288;   // warps 0-7: operand producers, then epilogue; warp 8: TMEM allocation + MMA issue
 
+// Round to tf32 (nearest, ties away from zero - what cvt.rna.tf32.f32 does) in two integer instructions instead of
+// the three (+ predicate) the conversion compiles to; differs from it only for Inf / NaN inputs, which the MLP
+// operands never hold.
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ float4 f4_map_sp(float4 a) {
   return make_float4(softplus100_fast(a.x), softplus100_fast(a.y), softplus100_fast(a.z), softplus100_fast(a.w));

@@ -84,6 +84,13 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
     // fused bias gradient: column sums of the A side (db[n] += sum_m A[m,n]) ride along for free
     const bool do_bias = db != nullptr && blockIdx.z == 0;
     float4 bsum[2] = {zero4, zero4};
+    // column groups of this thread that touch the ragged edge of an operand (loop invariant; the common case is none)
+    bool a_edge[2], x_edge[4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) a_edge[t] = ca0 + t * 32 + 3 >= (A.kvalid < A.width ? A.kvalid : A.width);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      x_edge[t] = (4 * hh + t >= nxt) || cx0 + t * 32 + 3 >= (X.kvalid < X.width ? X.kvalid : X.width);
     auto gload = [&](int st, TnRaw& R) {
       const int m = mbeg + st * TN_P + (int)r;
       const bool rok = m < mend;
@@ -121,28 +128,33 @@ gemm_tn_tc_kernel(int M, int N, int K, Operand A, Operand X, float* __restrict__
     auto produce = [&](int st, TnRaw& R) {
       const int s = st % TN_STAGES, ph = (st / TN_STAGES) & 1;
       const bool rok = mbeg + st * TN_P + (int)r < mend;
+      const bool tail = mbeg + (st + 1) * TN_P > mend;     // uniform: only the split's last stage can hold invalid rows
       float4 va[2], vx[4];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int c = ca0 + t * 32;
         float4 v = tn_pro4(A.kind, A.scale, R.a[t], R.b[t]);
-        if (!rok || c >= A.width) v = zero4;
-        if (c + 0 >= A.kvalid) v.x = 0.f;
-        if (c + 1 >= A.kvalid) v.y = 0.f;
-        if (c + 2 >= A.kvalid) v.z = 0.f;
-        if (c + 3 >= A.kvalid) v.w = 0.f;
+        if (a_edge[t] | tail) {                        // ragged column edge of the operand or the split's last rows
+          const int c = ca0 + t * 32;
+          if (!rok || c >= A.width) v = zero4;
+          if (c + 0 >= A.kvalid) v.x = 0.f;
+          if (c + 1 >= A.kvalid) v.y = 0.f;
+          if (c + 2 >= A.kvalid) v.z = 0.f;
+          if (c + 3 >= A.kvalid) v.w = 0.f;
+        }
         bsum[t] = f4_add(bsum[t], v);
         va[t] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const int c = cx0 + t * 32;
         float4 v = (X.kind == PRO_SOFTPLUS) ? f4_map_sp(R.x[t]) : R.x[t];
-        if (!((4 * hh + t < nxt) && rok && c < X.width)) v = zero4;
-        if (c + 0 >= X.kvalid) v.x = 0.f;
-        if (c + 1 >= X.kvalid) v.y = 0.f;
-        if (c + 2 >= X.kvalid) v.z = 0.f;
-        if (c + 3 >= X.kvalid) v.w = 0.f;
+        if (x_edge[t] | tail) {
+          const int c = cx0 + t * 32;
+          if (!((4 * hh + t < nxt) && rok && c < X.width)) v = zero4;
+          if (c + 0 >= X.kvalid) v.x = 0.f;
+          if (c + 1 >= X.kvalid) v.y = 0.f;
+          if (c + 2 >= X.kvalid) v.z = 0.f;
+          if (c + 3 >= X.kvalid) v.w = 0.f;
+        }
         vx[t] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
       }
       if (st + 2 < nst) gload(st + 2, R);              // refill the register buffer just consumed
