@@ -30,12 +30,14 @@ struct Operand {
   int kvalid;  // logical columns; columns >= kvalid read as 0
   int kind;
   float scale;
+  int rounded;  // values are already tf32-representable (written by an epilogue with round_c): the tensor-core
+                // kernels may feed them to the MMA without their own rounding pass
 };
 
 __host__ __device__ inline Operand make_operand(const float* p, int ld, int width, int kvalid, int kind = PRO_NONE,
                                                 const float* p2 = nullptr, int ld2 = 0, float scale = 1.0f) {
   Operand o;
-  o.p = p; o.p2 = p2; o.ld = ld; o.ld2 = ld2; o.width = width; o.kvalid = kvalid; o.kind = kind; o.scale = scale;
+  o.p = p; o.p2 = p2; o.ld = ld; o.ld2 = ld2; o.width = width; o.kvalid = kvalid; o.kind = kind; o.scale = scale; o.rounded = 0;
   return o;
 }
 
@@ -118,12 +120,14 @@ struct Epilogue {
   int ldc, ldc2, ldaux, ldaux2;
   int split, coff;
   float scale, scale2;
+  int round_c;  // tensor-core mode: store c rounded to tf32 (intermediates that only ever feed GEMM operands; the
+                // consumer would round them anyway, so the numerics are unchanged and its rounding pass is saved)
 };
 
 __host__ __device__ inline Epilogue make_epilogue(int kind, const float* bias, float* c, int ldc) {
   Epilogue e;
   e.kind = kind; e.bias = bias; e.c = c; e.c2 = nullptr; e.aux = nullptr; e.aux2 = nullptr;
-  e.ldc = ldc; e.ldc2 = 0; e.ldaux = 0; e.ldaux2 = 0; e.split = 0; e.coff = 0; e.scale = 1.0f; e.scale2 = 1.0f;
+  e.ldc = ldc; e.ldc2 = 0; e.ldaux = 0; e.ldaux2 = 0; e.split = 0; e.coff = 0; e.scale = 1.0f; e.scale2 = 1.0f; e.round_c = 0;
   return e;
 }
 

@@ -84,6 +84,8 @@ __device__ __forceinline__ void tc_prologue4(const Operand& A, const RawLoad (&r
 // same access pattern as the vector path (a warp instruction still covers four 128-byte row segments), scalar
 // loads / stores.  The kind switch sits outside the loops.
 __device__ __forceinline__ void tc_epilogue8_scalar(const Epilogue& e, int mbase, int M, int n, const float4 (&x)[8], int N) {
+  const bool rc = e.round_c != 0;
+  auto rnd = [rc](float v) { return rc ? to_tf32(v) : v; };
   float bb[4] = {0.f, 0.f, 0.f, 0.f};
   if (e.bias) {
 #pragma unroll
@@ -105,7 +107,7 @@ __device__ __forceinline__ void tc_epilogue8_scalar(const Epilogue& e, int mbase
   }
   switch (e.kind) {
     case EPI_STORE: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = v;) break;
-    case EPI_RELU: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = fmaxf(v, 0.0f);) break;
+    case EPI_RELU: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = rnd(fmaxf(v, 0.0f));) break;
     case EPI_SIGMOID: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = sigmoidf_(v);) break;
     case EPI_SOFTPLUS: VDN_EPI_LOOP(e.c[mm * e.ldc + e.coff + nn] = softplus100(v);) break;
     case EPI_SDF_SKIP:
@@ -116,12 +118,12 @@ __device__ __forceinline__ void tc_epilogue8_scalar(const Epilogue& e, int mbase
     case EPI_ADD_SCALED: VDN_EPI_LOOP(e.c[mm * e.ldc + nn] = v + e.scale * e.aux[mm * e.ldaux + e.split + nn];) break;
     case EPI_GRAD_DUAL:
       VDN_EPI_LOOP(const float z = e.aux[mm * e.ldaux + nn]; const float gin = e.aux2[mm * e.ldaux2 + nn] * e.scale2;
-                   e.c[mm * e.ldc + nn] = softplus100_d1(z) * v * e.scale;
+                   e.c[mm * e.ldc + nn] = rnd(softplus100_d1(z) * v * e.scale);
                    e.c2[mm * e.ldc2 + nn] = softplus100_d2(z) * gin * v;) break;
     case EPI_BWD_INJECT:
       VDN_EPI_LOOP(const float z = e.aux[mm * e.ldaux + nn]; float r = softplus100_d1(z) * v * e.scale;
-                   if (e.aux2) r += e.aux2[mm * e.ldaux2 + nn]; e.c[mm * e.ldc + nn] = r;) break;
-    case EPI_RELU_MASK: VDN_EPI_LOOP(e.c[mm * e.ldc + nn] = e.aux[mm * e.ldaux + e.split + nn] > 0.0f ? v : 0.0f;) break;
+                   if (e.aux2) r += e.aux2[mm * e.ldaux2 + nn]; e.c[mm * e.ldc + nn] = rnd(r);) break;
+    case EPI_RELU_MASK: VDN_EPI_LOOP(e.c[mm * e.ldc + nn] = rnd(e.aux[mm * e.ldaux + e.split + nn] > 0.0f ? v : 0.0f);) break;
     default: break;
   }
 #undef VDN_EPI_LOOP
@@ -157,6 +159,11 @@ __device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M
 #define m_(i) (mbase + 4 * (i))
 #define mok_(i) (mbase + 4 * (i) < M)
   auto st4 = [](float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; };
+  const bool rc = e.round_c != 0;
+  auto st4c = [rc](float* p, float4 v) {   // store to c, optionally rounded to tf32
+    if (rc) v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    *reinterpret_cast<float4*>(p) = v;
+  };
   auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
   if (e.bias) {   // b = bias[n .. n+3], fetched by the caller ahead of time
 #pragma unroll
@@ -172,8 +179,8 @@ __device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (mok_(i))
-          st4(e.c + (size_t)m_(i) * e.ldc + e.coff + n,
-              make_float4(fmaxf(x[i].x, 0.f), fmaxf(x[i].y, 0.f), fmaxf(x[i].z, 0.f), fmaxf(x[i].w, 0.f)));
+          st4c(e.c + (size_t)m_(i) * e.ldc + e.coff + n,
+               make_float4(fmaxf(x[i].x, 0.f), fmaxf(x[i].y, 0.f), fmaxf(x[i].z, 0.f), fmaxf(x[i].w, 0.f)));
       break;
     case EPI_SOFTPLUS:
 #pragma unroll
@@ -201,7 +208,7 @@ __device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M
         if (mok_(i)) {
           const float4 z = ld4(e.aux + (size_t)m_(i) * e.ldaux + n);
           const float4 g = f4_scale(ld4(e.aux2 + (size_t)m_(i) * e.ldaux2 + n), e.scale2);
-          st4(e.c + (size_t)m_(i) * e.ldc + n, f4_scale(f4_mul(f4_map_sp1(z), x[i]), e.scale));
+          st4c(e.c + (size_t)m_(i) * e.ldc + n, f4_scale(f4_mul(f4_map_sp1(z), x[i]), e.scale));
           st4(e.c2 + (size_t)m_(i) * e.ldc2 + n, f4_mul(f4_mul(f4_map_sp2(z), g), x[i]));
         }
       break;
@@ -212,7 +219,7 @@ __device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M
           const float4 z = ld4(e.aux + (size_t)m_(i) * e.ldaux + n);
           float4 r = f4_scale(f4_mul(f4_map_sp1(z), x[i]), e.scale);
           if (e.aux2) r = f4_add(r, ld4(e.aux2 + (size_t)m_(i) * e.ldaux2 + n));
-          st4(e.c + (size_t)m_(i) * e.ldc + n, r);
+          st4c(e.c + (size_t)m_(i) * e.ldc + n, r);
         }
       break;
     case EPI_RELU_MASK:
@@ -220,8 +227,8 @@ __device__ __forceinline__ void tc_epilogue8(const Epilogue& e, int mbase, int M
       for (int i = 0; i < 8; ++i)
         if (mok_(i)) {
           const float4 h = ld4(e.aux + (size_t)m_(i) * e.ldaux + e.split + n);
-          st4(e.c + (size_t)m_(i) * e.ldc + n, make_float4(h.x > 0.f ? x[i].x : 0.f, h.y > 0.f ? x[i].y : 0.f,
-                                                         h.z > 0.f ? x[i].z : 0.f, h.w > 0.f ? x[i].w : 0.f));
+          st4c(e.c + (size_t)m_(i) * e.ldc + n, make_float4(h.x > 0.f ? x[i].x : 0.f, h.y > 0.f ? x[i].y : 0.f,
+                                                          h.z > 0.f ? x[i].z : 0.f, h.w > 0.f ? x[i].w : 0.f));
         }
       break;
     default: break;
@@ -347,10 +354,18 @@ gemm_nt_tc_kernel(int M, int N, int nkb, Operand A, const float* __restrict__ Bi
           tc_epilogue_prefetch(E, m0 + (warp & 3) * 32 + (lane >> 3), M, n_base + ch * 32 + chunk * 4, N);
       }
     };
+    const bool plain = A.kind == PRO_NONE && A.rounded && !wextra;
     auto finish = [&](int kb, const float4 (&bq)[4]) {
       const int s = kb & 1;
       const int col = kb * 32 + chunk * 4;
       const uint32_t base = smem0 + (uint32_t)s * stage_stride;
+      if (plain && kb * 32 + 31 < A.kvalid) {        // tf32-representable already, nothing to clear: publish as it landed
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));
+        if (tid == 0) VDN_TL(1, 3 * kb + 2);
+        return;
+      }
       RawLoad raw[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {

@@ -71,11 +71,12 @@ extern "C" int vdn_rendernet_forward(const int* cfg, const float* packed, const 
   for (int l = 0; l < c.L; ++l) {
     Operand A = (l == 0) ? make_operand(CIN, c.ldIn, c.ldIn, c.in0)
                          : make_operand(H + (long long)(l - 1) * N * c.ldH, c.ldH, c.ly.in_ld[l], c.ly.in_dim[l]);
+    if (l > 0) A.rounded = 1;
     Epilogue E;
     if (l == c.L - 1)
       E = make_epilogue(c.squeeze_out ? EPI_SIGMOID : EPI_RELU, packed + c.ly.off_b[l], out, c.d_out);
     else
-      E = make_epilogue(EPI_RELU, packed + c.ly.off_b[l], H + (long long)l * N * c.ldH, c.ldH);
+      E = make_epilogue(EPI_RELU, packed + c.ly.off_b[l], H + (long long)l * N * c.ldH, c.ldH), E.round_c = 1;
     e = launch_gemm_nt((int)N, c.ly.out_dim[l], c.ly.in_ld[l], A, wref(c.ly, packed, l), E, st);
     if (e) return e;
   }
@@ -124,11 +125,14 @@ extern "C" int vdn_rendernet_backward(const int* cfg, const float* packed, long 
                                 : make_operand(ZB[l & 1], c.ldH, ly.out_ld[l], ly.out_dim[l]);
     Operand u = (l == 0) ? make_operand(CIN, c.ldIn, c.ldIn, c.in0)
                          : make_operand(H + (long long)(l - 1) * N * c.ldH, c.ldH, ly.in_ld[l], ly.in_dim[l]);
+    if (l < L - 1) zbar.rounded = 1;
+    if (l > 0) u.rounded = 1;
     int e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l], ly.in_ld[l], 1,
                              dpacked + ly.off_b[l], st);
     if (e) return e;
     if (l > 0) {
       Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(l - 1) & 1], c.ldH);
+      E.round_c = 1;
       E.aux = H + (long long)(l - 1) * N * c.ldH; E.ldaux = c.ldH; E.split = 0;
       e = launch_gemm_nt(M, ly.in_dim[l], ly.out_ld[l], zbar, wtref(ly, packed, l), E, st);
       if (e) return e;
@@ -197,7 +201,9 @@ static void carve_nerf(const NerfCfg& c, long long N, float* p, NerfBlob* b) {
 static Operand nerf_input(const NerfCfg& c, const NerfBlob& b, int i) {
   if (i == 0) return make_operand(b.E, c.ldE, c.ldE, c.d_e);
   if (i - 1 == c.skip) return make_operand(b.U, c.ldU, c.ldU, c.W + c.d_e);
-  return make_operand(b.H[i - 1], c.ldH, c.ly.in_ld[i], c.W);
+  Operand o = make_operand(b.H[i - 1], c.ldH, c.ly.in_ld[i], c.W);
+  o.rounded = 1;   // written by an EPI_RELU epilogue with round_c
+  return o;
 }
 }  // namespace vdn
 
@@ -235,6 +241,7 @@ extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float
   for (int i = 0; i < D; ++i) {
     Operand A = nerf_input(c, b, i);
     Epilogue E = make_epilogue(EPI_RELU, packed + ly.off_b[i], b.H[i], c.ldH);
+    E.round_c = 1;
     if (i == c.skip) { E.c = b.U; E.ldc = c.ldU; E.coff = 0; }
     e = launch_gemm_nt(M, c.W, ly.in_ld[i], A, wref(ly, packed, i), E, st);
     if (e) return e;
@@ -250,11 +257,13 @@ extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float
   {
     Operand A = make_operand(b.VIN, c.ldV, c.ldV, c.vin);
     Epilogue E = make_epilogue(EPI_RELU, packed + ly.off_b[D + 1], b.HV, c.ldHV);
+    E.round_c = 1;
     e = launch_gemm_nt(M, c.W / 2, ly.in_ld[D + 1], A, wref(ly, packed, D + 1), E, st);
     if (e) return e;
   }
   {
     Operand A = make_operand(b.HV, c.ldHV, c.ldHV, c.W / 2);
+    A.rounded = 1;
     Epilogue E = make_epilogue(EPI_SPLIT, packed + ly.off_b[D + 2], dpt, c.dpt_dim);
     E.c2 = rgb; E.ldc2 = c.rgb_dims; E.split = c.rgb_dims; E.scale = 1.0f;
     e = launch_gemm_nt(M, c.rgb_dims + c.dpt_dim, ly.in_ld[D + 2], A, wref(ly, packed, D + 2), E, st);
@@ -323,9 +332,11 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
     if (e) return e;
     Operand zo = make_operand(ZO, ldo, ldo, ly.out_dim[D + 2]);
     Operand hv = make_operand(b.HV, c.ldHV, c.ldHV, c.W / 2);
+    hv.rounded = 1;
     e = wg(D + 2, zo, hv);
     if (e) return e;
     Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZV, c.ldHV);
+    E.round_c = 1;
     E.aux = b.HV; E.ldaux = c.ldHV;
     e = launch_gemm_nt(M, c.W / 2, ldo, zo, wtref(ly, packed, D + 2), E, st);
     if (e) return e;
@@ -333,6 +344,7 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
   // view layer
   {
     Operand zv = make_operand(ZV, c.ldHV, c.ldHV, c.W / 2);
+    zv.rounded = 1;
     Operand vin = make_operand(b.VIN, c.ldV, c.ldV, c.vin);
     e = wg(D + 1, zv, vin);
     if (e) return e;
@@ -361,18 +373,21 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
     e = wg(D, zh, nerf_input(c, b, D));
     if (e) return e;
     Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(D - 1) & 1], c.ldH);
+    E.round_c = 1;
     E.aux = b.H[D - 1]; E.ldaux = c.ldH;
     e = launch_gemm_nt(M, c.W, ldh, zh, wtref(ly, packed, D), E, st);
     if (e) return e;
   }
   for (int i = D - 1; i >= 0; --i) {
     Operand zbar = make_operand(ZB[i & 1], c.ldH, c.ldH, c.W);
+    zbar.rounded = 1;
     e = wg(i, zbar, nerf_input(c, b, i));
     if (e) return e;
     if (i > 0) {
       // hidden part of the input cotangent, masked by the sign of h_{i-1}
       const bool after_skip = (i - 1 == c.skip);
       Epilogue E = make_epilogue(EPI_RELU_MASK, nullptr, ZB[(i - 1) & 1], c.ldH);
+      E.round_c = 1;
       if (after_skip) { E.aux = b.U; E.ldaux = c.ldU; E.split = 0; }
       else { E.aux = b.H[i - 1]; E.ldaux = c.ldH; E.split = 0; }
       e = launch_gemm_nt(M, c.W, c.ldH, zbar, wtref(ly, packed, i), E, st);

@@ -317,9 +317,11 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
     for (int l = 0; l <= L - 2; ++l) {
       Operand qbar = (l == 0) ? make_operand(DEB, c.ldE, c.ldE, c.d_e)
                               : make_operand(l == c.skip ? QS : Q[l & 1], c.ldH, ly.in_ld[l], ly.in_dim[l]);
+      if (l > 0 && l != c.skip) qbar.rounded = 1;   // written by the previous layer's EPI_GRAD_DUAL with round_c
       GinRef gi = gin_of(c, packed, g, l);
       // dbar_l = qbar_l * W_l^T ; epilogue splits it into qbar_{l+1} and the injected pre-activation cotangent
       Epilogue E = make_epilogue(EPI_GRAD_DUAL, nullptr, (l + 1 == c.skip) ? QS : Q[(l + 1) & 1], c.ldH);
+      E.round_c = 1;
       E.scale = (l + 1 == c.skip) ? kInvSqrt2 : 1.0f;
       E.c2 = ZG[l]; E.ldc2 = c.ldH;
       E.aux = b.Z[l]; E.ldaux = c.ldH;
@@ -358,6 +360,7 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
   for (int l = L - 1; l >= 0; --l) {
     Operand zbar = (l == L - 1) ? make_operand(ZL, ly.out_ld[l], ly.out_ld[l], ly.out_dim[l])
                                 : make_operand(ZG[l], c.ldH, ly.out_ld[l], ly.out_dim[l]);
+    if (l < L - 1) zbar.rounded = 1;   // written by EPI_BWD_INJECT with round_c
     Operand u = input_operand(c, b, l);
     e = launch_wgrad_any(M, ly.out_dim[l], ly.in_dim[l], zbar, u, partials, dpacked + ly.off_w[l], ly.in_ld[l], 1,
                          dpacked + ly.off_b[l], st);
@@ -365,6 +368,7 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
     if (l > 0) {
       // ubar = zbar_l W_l restricted to the hidden part; epilogue -> zbar_{l-1}
       Epilogue E = make_epilogue(EPI_BWD_INJECT, nullptr, ZG[l - 1], c.ldH);
+      E.round_c = 1;
       E.aux = b.Z[l - 1]; E.ldaux = c.ldH;
       E.aux2 = have_n ? ZG[l - 1] : nullptr; E.ldaux2 = c.ldH;
       E.scale = (l == c.skip) ? kInvSqrt2 : 1.0f;
