@@ -319,7 +319,7 @@ static int run_gemm_ts(int N, int K) {
 }
 
 // Issue `iters` x 4 back-to-back MMAs (N=256, K=8 each) on fixed operands and report cycles per MMA.
-__global__ void __launch_bounds__(128) probe_rate(int iters, long long* cycles, int* status) {
+__global__ void __launch_bounds__(128) probe_rate(int iters, long long* cycles, int* status, int mn) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_mma;
@@ -337,12 +337,17 @@ __global__ void __launch_bounds__(128) probe_rate(int iters, long long* cycles, 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (tid == 0) {
-    const uint32_t idesc = umma_idesc_tf32(128, 256);
+    const uint32_t idesc = mn ? umma_idesc_tf32_mn(128, 256) : umma_idesc_tf32(128, 256);
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it)
-      for (int ks = 0; ks < 4; ++ks)
-        umma_tf32(tmem_base + (it & 1) * 256, umma_desc_sw128(smem_u32(smem) + ks * 32),
-                  umma_desc_sw128(smem_u32(smem + 16384) + ks * 32), idesc, 1u);
+      for (int ks = 0; ks < 4; ++ks) {
+        if (mn)   // both operands MN-major (SWIZZLE_128B_BASE32B tiles of 32 points x 32 features): the wgrad layout
+          umma_tf32(tmem_base + (it & 1) * 256, umma_desc_sw128_mn(smem_u32(smem) + ks * 1024, 4096, 512),
+                    umma_desc_sw128_mn(smem_u32(smem + 16384) + ks * 1024, 4096, 512), idesc, 1u);
+        else
+          umma_tf32(tmem_base + (it & 1) * 256, umma_desc_sw128(smem_u32(smem) + ks * 32),
+                    umma_desc_sw128(smem_u32(smem + 16384) + ks * 32), idesc, 1u);
+      }
     umma_commit(smem_u32(&bar_mma));
     bool ok = mbar_wait(smem_u32(&bar_mma), 0);
     long long t1 = clock64();
@@ -435,17 +440,18 @@ int main() {
     CK(cudaMalloc(&dC, 148 * 8)); CK(cudaMalloc(&dS, 4)); CK(cudaMemset(dS, 0, 4));
     const int smem = 16384 + 32768 + 1024;
     CK(cudaFuncSetAttribute(probe_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int mn = 0; mn < 2; ++mn)
     for (int grid : {1, 148}) {
       const int iters = 2048;
-      probe_rate<<<grid, 128, smem>>>(iters, dC, dS);
+      probe_rate<<<grid, 128, smem>>>(iters, dC, dS, mn);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("probe_rate: LAUNCH FAILED %s\n", cudaGetErrorString(e)); ++fails; break; }
       long long c[148];
       CK(cudaMemcpy(c, dC, grid * 8, cudaMemcpyDeviceToHost));
       long long mx = 0;
       for (int i = 0; i < grid; ++i) if (c[i] > mx) mx = c[i];
-      printf("probe_rate grid=%d: %.1f cycles per 128x256x8 tf32 MMA (max over CTAs)\n", grid,
-             (double)mx / (iters * 4));
+      printf("probe_rate grid=%d %s: %.1f cycles per 128x256x8 tf32 MMA (max over CTAs)\n", grid,
+             mn ? "MN-major operands" : "K-major operands", (double)mx / (iters * 4));
     }
   }
   printf("probe_tc: %s (%d failing)\n", fails ? "FAIL" : "ALL PASS", fails);

@@ -49,6 +49,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded wait: returns false (and the caller bails out) instead of hanging the GPU if a barrier never flips.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t max_spins = 1u << 24) {
+#pragma unroll 1
   for (uint32_t i = 0; i < max_spins; ++i) {
     if (mbar_try_wait(bar, parity)) return true;
   }
@@ -57,6 +58,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_
 // Same, for long waits of single-thread roles (MMA issuer, weight stream): back off between polls so the spinning
 // thread does not take issue slots from the warps doing the element-wise work on its scheduler.
 __device__ __forceinline__ bool mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns = 64, uint32_t max_spins = 1u << 22) {
+#pragma unroll 1
   for (uint32_t i = 0; i < max_spins; ++i) {
     if (mbar_try_wait(bar, parity)) return true;
     __nanosleep(ns);
