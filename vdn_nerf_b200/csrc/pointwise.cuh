@@ -145,6 +145,48 @@ static __global__ void copy_pad_rows_kernel(const float* __restrict__ src, int l
   dst[m * ldd + dcol + c] = (c < w && src) ? src[m * lds + c] * scale : 0.0f;
 }
 
+// dst[m, :] = [ a[m, 0..wa) * sa | b[m, 0..wb) * sb | 0 ... ] up to ldd columns (null source = zeros): the cotangent of
+// a stacked pair of heads assembled in ONE pass (it used to take a zero fill plus one strided copy per head).
+static __global__ void gather2_rows_kernel(const float* __restrict__ a, int lda, int wa, float sa, const float* __restrict__ b,
+                                           int ldb, int wb, float sb, long long N, float* __restrict__ dst, int ldd) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * ldd) return;
+  long long m;
+  int c;
+  if (N * ldd < 0x7fffffffLL) {
+    const unsigned mi = (unsigned)idx / (unsigned)ldd;
+    m = mi;
+    c = (int)((unsigned)idx - mi * (unsigned)ldd);
+  } else {
+    m = idx / ldd;
+    c = (int)(idx - m * ldd);
+  }
+  float v = 0.0f;
+  if (c < wa) { if (a) v = a[m * lda + c] * sa; }
+  else if (c < wa + wb) { if (b) v = b[m * ldb + (c - wa)] * sb; }
+  dst[idx] = v;
+}
+inline int launch_gather2_rows(const float* a, int lda, int wa, float sa, const float* b, int ldb, int wb, float sb,
+                               long long N, float* dst, int ldd, cudaStream_t st) {
+  const long long tot = N * ldd;
+  if (tot <= 0) return 0;
+  VDN_LAUNCH(gather2_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, a, lda, wa, sa, b, ldb, wb, sb, N, dst, ldd);
+  return (int)cudaGetLastError();
+}
+
+// dst[m, 0] = a ? a[m] : 0 and dst[m, wreal..ldd) = 0: the columns of a stacked-head cotangent that the following GEMM
+// epilogue (which fills columns 1..wreal-1) does not write.
+static __global__ void head_edges_kernel(const float* __restrict__ a, long long N, float* __restrict__ dst, int ldd,
+                                         int wreal) {
+  const int ne = 1 + (ldd - wreal);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * ne) return;
+  const long long m = idx / ne;
+  const int j = (int)(idx - m * ne);
+  if (j == 0) dst[m * ldd] = a ? a[m] : 0.0f;
+  else dst[m * ldd + wreal + j - 1] = 0.0f;
+}
+
 // Rendering-network input row (reference fields.py:148-158):
 //   idr:          [points(3) | PE_L(view)(3+6L) | normals(3) | feats(F)]
 //   no_view_dir:  [points | normals | feats]         no_normal: [points | PE(view) | feats]

@@ -316,19 +316,8 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
   // output heads
   {
     int ldo = ly.out_ld[D + 2];
-    long long tot = N * ldo;
-    VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, nullptr, 0, 0, N, ZO, ldo, 0, ldo, 0.0f);
-    if (d_rgb) {
-      long long t = N * c.rgb_dims;
-      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((t + 255) / 256), 256, 0, st, d_rgb, c.rgb_dims, c.rgb_dims, N, ZO, ldo, 0,
-                                                                       c.rgb_dims, 1.0f);
-    }
-    if (d_dpt && c.dpt_dim > 0) {
-      long long t = N * c.dpt_dim;
-      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((t + 255) / 256), 256, 0, st, d_dpt, c.dpt_dim, c.dpt_dim, N, ZO, ldo,
-                                                                       c.rgb_dims, c.rgb_dims + c.dpt_dim, 1.0f);
-    }
-    e = (int)cudaGetLastError();
+    e = launch_gather2_rows(d_rgb, c.rgb_dims, c.rgb_dims, 1.0f, c.dpt_dim > 0 ? d_dpt : nullptr, c.dpt_dim, c.dpt_dim, 1.0f,
+                            N, ZO, ldo, st);
     if (e) return e;
     Operand zo = make_operand(ZO, ldo, ldo, ly.out_dim[D + 2]);
     Operand hv = make_operand(b.HV, c.ldHV, c.ldHV, c.W / 2);
@@ -350,10 +339,10 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
     if (e) return e;
     // cotangent of the feature -> columns 1..W of ZHEAD; column 0 = d_sigma
     int ldh = ly.out_ld[D];
-    long long tot = N * ldh;
-    VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, nullptr, 0, 0, N, ZHEAD, ldh, 0, ldh, 0.0f);
-    if (d_sigma)
-      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((N + 255) / 256), 256, 0, st, d_sigma, 1, 1, N, ZHEAD, ldh, 0, 1, 1.0f);
+    {
+      const long long tot = N * (1 + ldh - (1 + c.W));
+      VDN_LAUNCH(head_edges_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, d_sigma, N, ZHEAD, ldh, 1 + c.W);
+    }
     e = (int)cudaGetLastError();
     if (e) return e;
     Epilogue E = make_epilogue(EPI_STORE, nullptr, ZHEAD, ldh);

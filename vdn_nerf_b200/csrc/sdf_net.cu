@@ -342,19 +342,8 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
 
   // ---- phase 2: ordinary backward with the injected cotangents ------------------------------------
   {
-    long long tot = N * ly.out_ld[L - 1];
-    VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, nullptr, 0, 0, N, ZL, ly.out_ld[L - 1], 0,
-                                                                       ly.out_ld[L - 1], 0.0f);
-    if (d_sdf) {
-      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((N + 255) / 256), 256, 0, st, d_sdf, lds, 1, N, ZL, ly.out_ld[L - 1], 0, 1,
-                                                                       1.0f / c.scale);
-    }
-    if (d_feat) {
-      long long t2 = N * (c.d_out - 1);
-      VDN_LAUNCH(copy_pad_rows_kernel, (unsigned)((t2 + 255) / 256), 256, 0, st, d_feat, ldf, c.d_out - 1, N, ZL,
-                                                                        ly.out_ld[L - 1], 1, c.d_out, 1.0f);
-    }
-    e = (int)cudaGetLastError();
+    // cotangent of the last layer's stacked [sdf | feature] output
+    e = launch_gather2_rows(d_sdf, lds, 1, 1.0f / c.scale, d_feat, ldf, c.d_out - 1, 1.0f, N, ZL, ly.out_ld[L - 1], st);
     if (e) return e;
   }
   for (int l = L - 1; l >= 0; --l) {
