@@ -8,47 +8,53 @@ namespace vdn {
 // e(y) = [y | sin(2^0 y) | cos(2^0 y) | ... ]  with y = x * scale  (reference embedder.py:15-36).
 // Writes row m of `e` (ld lde; columns >= d_e zeroed up to lde) and, when u != nullptr, the same values
 // times uscale into u[m, ucol ... ucol+d_e) (zero up to u_pad_to): the skip-connection tail of the SDF net
-// (fields.py:82-83) or of the NeRF field.  One thread per output element, so stores are coalesced.
+// (fields.py:82-83) or of the NeRF field.  One thread per (row, frequency, coordinate): a single sincosf feeds the
+// sin and the cos column of both destinations; further threads of the row write the identity and padding columns.
 static __global__ void embed_rows_kernel(const float* __restrict__ x, int ldx, long long N, int d, int L, float scale,
                                   float* __restrict__ e, int lde, float* __restrict__ u, int ldu, int ucol,
                                   float uscale, int u_pad_to) {
-  const int we = e ? lde : 0;
-  const int wu = u ? (u_pad_to - ucol) : 0;
-  const int wt = we + wu;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * wt) return;
-  long long m;
-  int c;
-  if (N * wt < 0x7fffffffLL) {   // 32-bit division where it fits (the 64-bit one costs more than the sin/cos)
-    const unsigned mi = (unsigned)idx / (unsigned)wt;
-    m = mi;
-    c = (int)((unsigned)idx - mi * (unsigned)wt);
-  } else {
-    m = idx / wt;
-    c = (int)(idx - m * wt);
-  }
-  const bool to_u = c >= we;
-  if (to_u) c -= we;
   const int d_e = d * (1 + 2 * L);
-  float v = 0.0f;
-  if (c < d_e) {
-    if (c < d) {
-      v = x[m * ldx + c] * scale;
-    } else {
-      const int t = c - d, k = t / (2 * d), rem = t - k * 2 * d;
-      const float f = (float)(1 << k);
-      const float y = x[m * ldx + (rem < d ? rem : rem - d)] * scale;
-      v = rem < d ? sinf(y * f) : cosf(y * f);
-    }
+  const int pe = e ? lde - d_e : 0;                   // padding columns of e
+  const int pu = u ? u_pad_to - ucol - d_e : 0;       // padding columns of u
+  const int T = d + d * L + pe + pu;                  // work items per row
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * T) return;
+  long long m;
+  int t;
+  if (N * T < 0x7fffffffLL) {
+    const unsigned mi = (unsigned)idx / (unsigned)T;
+    m = mi;
+    t = (int)((unsigned)idx - mi * (unsigned)T);
+  } else {
+    m = idx / T;
+    t = (int)(idx - m * T);
   }
-  if (to_u) u[m * ldu + ucol + c] = v * uscale;
-  else e[m * lde + c] = v;
+  float* er = e ? e + m * lde : nullptr;
+  float* ur = u ? u + m * ldu + ucol : nullptr;
+  if (t < d) {
+    const float y = x[m * ldx + t] * scale;
+    if (er) er[t] = y;
+    if (ur) ur[t] = y * uscale;
+  } else if (t < d + d * L) {
+    const int q = t - d, k = q / d, j = q - k * d;
+    const float y = x[m * ldx + j] * scale;
+    float sn, cs;
+    sincosf(y * (float)(1 << k), &sn, &cs);
+    const int c0 = d + 2 * k * d + j, c1 = c0 + d;
+    if (er) { er[c0] = sn; er[c1] = cs; }
+    if (ur) { ur[c0] = sn * uscale; ur[c1] = cs * uscale; }
+  } else {
+    const int p = t - d - d * L;
+    if (p < pe) er[d_e + p] = 0.0f;
+    else ur[d_e + (p - pe)] = 0.0f;
+  }
 }
 
 inline int launch_embed_rows(const float* x, int ldx, long long N, int d, int L, float scale, float* e, int lde, float* u,
                              int ldu, int ucol, float uscale, int u_pad_to, cudaStream_t st) {
-  const long long wt = (e ? lde : 0) + (u ? (u_pad_to - ucol) : 0);
-  const long long total = N * wt;
+  const int d_e = d * (1 + 2 * L);
+  const long long T = d + d * L + (e ? lde - d_e : 0) + (u ? u_pad_to - ucol - d_e : 0);
+  const long long total = N * T;
   if (total <= 0) return 0;
   VDN_LAUNCH(embed_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, st, x, ldx, N, d, L, scale, e, lde, u, ldu, ucol,
              uscale, u_pad_to);
