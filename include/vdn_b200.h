@@ -41,8 +41,12 @@ int vdn_set_mode(int mode);
 int vdn_get_mode(void);
 int vdn_tc_fault(void);
 
-/* Debug aid: when device_buf (256 int64, device memory) is non-null, CTA 0 of every tcgen05 GEMM launch records
- * clock64() time stamps of its pipeline events there (csrc/gemm_tc.cuh).  Pass null to switch it off. */
+/* Debug aid: when device_buf (8192 int64 of device memory) is non-null, the tcgen05 kernels record time stamps there:
+ * CTA 0 of a layer-wise GEMM launch its pipeline events as clock64() in entries [0, 512) and every CTA (first 1500)
+ * its %globaltimer start / end and SM id in entries [1024, 7024) (csrc/gemm_tc.cuh; the environment variable
+ * VDN_DBG_LAUNCH=n restricts the recording to the n-th launch after the buffer was installed); CTA 0 of the fused
+ * chain kernel its per-phase events in entries [0, 512) (csrc/sdf_chain_tc.cuh).  Pass null to switch it off.
+ * Readers: tools/diag_timeline.py, tools/diag_ctas.py, tools/diag_chain.py. */
 int vdn_debug_timeline(long long* device_buf);
 
 /* Measurement aid for bench.py: when enabled, CUDA events bracket every launch of a kernel family on its

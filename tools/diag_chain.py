@@ -15,7 +15,7 @@ x = torch.rand(n, 3, device=dev) * 2 - 1
 torch.set_grad_enabled(False)
 for _ in range(2):
     sdf.sdf(x)
-buf = torch.zeros(512, dtype=torch.int64, device=dev)
+buf = torch.zeros(8192, dtype=torch.int64, device=dev)
 lib.vdn_debug_timeline(ctypes.c_void_p(buf.data_ptr()))
 torch.cuda.synchronize()
 sdf.sdf(x)

@@ -12,11 +12,11 @@ lib = _lib.load()
 for n in (128, 148 * 2 * 128, 1 << 21):
     x = torch.rand(n, 3, device=dev) * 2 - 1
     for _ in range(2):
-        sdf.sdf(x)
-    buf = torch.zeros(512, dtype=torch.int64, device=dev)
+        sdf(x)
+    buf = torch.zeros(8192, dtype=torch.int64, device=dev)
     lib.vdn_debug_timeline(ctypes.c_void_p(buf.data_ptr()))
     torch.cuda.synchronize()
-    sdf.sdf(x)
+    sdf(x)
     torch.cuda.synchronize()
     lib.vdn_debug_timeline(None)
     t = buf.cpu().tolist()
@@ -25,5 +25,5 @@ for n in (128, 148 * 2 * 128, 1 << 21):
     print(f"--- n={n} (last launch of the chain; cycles since CTA start)")
     print("  alloc+sync done", r(0, 1), " acc ready", r(0, 2), " epilogue done", r(0, 3), " dealloc", r(0, 4))
     for kb in range(8):
-        print(f"  kb{kb}: start {r(4,2*kb)} math-done {r(4,2*kb+1)} sts-done {r(5,2*kb)} fence-done {r(5,2*kb+1)}")
-        print(f"  kb{kb}: prod loads-ready {r(1,3*kb)} empty-ok {r(1,3*kb+1)} arrived {r(1,3*kb+2)} | B issued {r(3,kb)} | mma wait {r(2,2*kb)} full-ok {r(2,2*kb+1)}")
+        print(f"  kb{kb}: producer wait-empty {r(1,3*kb)} empty-ok/cp.async issued {r(1,3*kb+1)} finished+arrived {r(1,3*kb+2)} | "
+              f"mma wait {r(2,2*kb)} full-ok {r(2,2*kb+1)}")

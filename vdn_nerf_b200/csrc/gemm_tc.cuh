@@ -546,7 +546,7 @@ inline WeightRef wtref(const MlpLayout& ly, const float* packed, int l, int row0
 
 extern int g_mode;           // 0: exact fp32 (FFMA kernels), 1: tf32 tensor cores (tcgen05); set by vdn_set_mode
 extern int* g_tc_fault;      // device flag raised by a timed-out barrier wait in a tcgen05 kernel
-extern long long* g_tc_dbg;  // optional device buffer (256 int64) receiving CTA 0's timeline (vdn_debug_timeline)
+extern long long* g_tc_dbg;  // optional device buffer (8192 int64) receiving debug time stamps (vdn_debug_timeline)
 
 static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const WeightRef& B, const Epilogue& E,
                                     cudaStream_t st) {
