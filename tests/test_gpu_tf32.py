@@ -59,7 +59,7 @@ def test_tf32_mode_is_active():
     assert ops.get_precision() == "tf32"
 
 
-@pytest.mark.parametrize("n", [1, 127, 128, 1000, 4133])
+@pytest.mark.parametrize("n", [1, 127, 128, 1000, 4133, 40001])
 def test_tf32_sdf_forward_normals(white, n):
     fx, mods, conf = white
     cpu_mods, _ = util.build("womsk_white")
