@@ -118,6 +118,11 @@ class SDFNetwork(nn.Module):
         """Fused (forward(x), gradient(x).squeeze(1)): one forward pass instead of the reference's two."""
         return ops.sdf_eval(self.handle(), x, want_normals=True, want_feature=True)
 
+    def forward_split(self, x):
+        """(sdf [N,1], feature [N,d_out-1], normals [N,3]) as separate tensors - what render_core consumes; saves the
+        slicing of a concatenated output and the zero-filled concatenated cotangent autograd would build for it."""
+        return ops.sdf_eval_split(self.handle(), x, want_normals=True, want_feature=True)
+
 
 class RenderingNetwork(nn.Module):
     """View-dependent colour / depth-feature head (reference fields.py:112-176)."""

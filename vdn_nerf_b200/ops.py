@@ -236,7 +236,10 @@ def sdf_value(h: SdfHandle, x: torch.Tensor) -> torch.Tensor:
 
 
 class _SdfFn(torch.autograd.Function):
-    """(x, params...) -> (out [N, d_out] = [sdf | feature], normals [N, d_in] or None)."""
+    """(x, params...) -> (sdf [N,1], feature [N, d_out-1] or None, normals [N, d_in] or None).
+
+    The value and the feature are separate outputs (the C ABI takes separate pointers and leading dimensions), so
+    autograd hands their cotangents over as they are instead of scattering both into a zero-filled [N, d_out]."""
 
     @staticmethod
     def forward(ctx, h: SdfHandle, x, want_normals: bool, want_feature: bool, *params):
@@ -247,11 +250,10 @@ class _SdfFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[4:]) or ctx.needs_input_grad[1]
         save = 1 if (need_grad or want_normals) else 0
         dev = x.device
-        width = h.d_out if want_feature else 1
-        out = torch.empty(N, width, device=dev, dtype=torch.float32)
+        sdf = torch.empty(N, 1, device=dev, dtype=torch.float32)
+        feat = torch.empty(N, h.d_out - 1, device=dev, dtype=torch.float32) if want_feature else None
         blob = torch.empty(int(lib.vdn_sdf_blob_floats(h.cfg, N, save)), device=dev, dtype=torch.float32)
-        feat_ptr = ctypes.c_void_p(out.data_ptr() + 4) if want_feature else None
-        check(lib.vdn_sdf_forward(h.cfg, h.scale, _p(packed), _p(x), N, _p(out), width, feat_ptr, width, _p(blob),
+        check(lib.vdn_sdf_forward(h.cfg, h.scale, _p(packed), _p(x), N, _p(sdf), 1, _p(feat), h.d_out - 1, _p(blob),
                                   save, _stream()), "vdn_sdf_forward")
         normals = None
         blobg = None
@@ -265,33 +267,44 @@ class _SdfFn(torch.autograd.Function):
         ctx.want_feature = want_feature
         if need_grad:
             ctx.save_for_backward(x, packed, blob, blobg)
-        if normals is None:
-            return out, None
-        return out, normals
+        return sdf, feat, normals
 
     @staticmethod
-    def backward(ctx, d_out, d_normals):
+    def backward(ctx, d_sdf, d_feat, d_normals):
         lib = _lib.load()
         h = ctx.h
         x, packed, blob, blobg = ctx.saved_tensors
         N = x.shape[0]
         dev = x.device
-        width = h.d_out if ctx.want_feature else 1
-        d_out = _prep(d_out) if d_out is not None else None
+        d_sdf = _prep(d_sdf) if d_sdf is not None else None
+        ldf = h.d_out - 1
+        if d_feat is None or not ctx.want_feature:
+            d_feat = None
+        elif d_feat.is_cuda and d_feat.dtype == torch.float32 and d_feat.dim() == 2 and d_feat.stride(1) == 1:
+            ldf = d_feat.stride(0)        # e.g. a column slice of the colour network's input cotangent: read in place
+        else:
+            d_feat = _prep(d_feat)
         d_normals = _prep(d_normals) if (d_normals is not None and ctx.want_normals) else None
         dpacked = torch.zeros(h.mlp.total, device=dev, dtype=torch.float32)
         ws = torch.empty(int(lib.vdn_sdf_bwd_ws_floats(h.cfg, N)), device=dev, dtype=torch.float32)
         d_x = torch.empty_like(x) if ctx.needs_input_grad[1] else None
-        d_sdf = _p(d_out)
-        d_feat = ctypes.c_void_p(d_out.data_ptr() + 4) if (d_out is not None and ctx.want_feature) else None
-        check(lib.vdn_sdf_backward(h.cfg, h.scale, _p(packed), _p(x), N, _p(blob), _p(blobg), d_sdf, width, d_feat,
-                                   width, _p(d_normals), _p(dpacked), _p(d_x), _p(ws), _stream()), "vdn_sdf_backward")
+        check(lib.vdn_sdf_backward(h.cfg, h.scale, _p(packed), _p(x), N, _p(blob), _p(blobg), _p(d_sdf), 1, _p(d_feat),
+                                   ldf, _p(d_normals), _p(dpacked), _p(d_x), _p(ws), _stream()),
+              "vdn_sdf_backward")
         grads = h.mlp.unpack_grads(dpacked, ctx.needs_input_grad[4:])
         return (None, d_x, None, None, *grads)
 
 
-def sdf_eval(h: SdfHandle, x: torch.Tensor, want_normals: bool, want_feature: bool = True):
+def sdf_eval_split(h: SdfHandle, x: torch.Tensor, want_normals: bool, want_feature: bool = True):
+    """(sdf [N,1], feature [N, d_out-1] | None, normals [N, d_in] | None)."""
     return _SdfFn.apply(h, x, want_normals, want_feature, *h.mlp.params)
+
+
+def sdf_eval(h: SdfHandle, x: torch.Tensor, want_normals: bool, want_feature: bool = True):
+    """Reference-shaped result: (out [N, d_out] = [sdf | feature] (or [N,1]), normals | None)."""
+    sdf, feat, normals = sdf_eval_split(h, x, want_normals, want_feature)
+    out = torch.cat([sdf, feat], dim=1) if want_feature else sdf
+    return out, normals
 
 
 # ----------------------------------------------------------------------------------------------------

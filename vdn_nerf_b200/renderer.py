@@ -149,9 +149,12 @@ class NeuSRenderer:
             dists, mid_z, pts = ops.fine_prep(rays_o, rays_d, z_vals, sample_dist)
         dirs = rays_d[:, None, :].expand(B, n, 3).reshape(-1, 3)
 
-        out, gradients = sdf_network.forward_with_gradient(pts)
-        sdf = out[:, :1]
-        feature_vector = out[:, 1:]
+        if hasattr(sdf_network, "forward_split"):
+            sdf, feature_vector, gradients = sdf_network.forward_split(pts)
+        else:   # any module with the reference's interface (fields.py:72-108)
+            out = sdf_network(pts)
+            gradients = sdf_network.gradient(pts).squeeze(1)
+            sdf, feature_vector = out[:, :1], out[:, 1:]
         sampled_feat = None
         if depth_network is not None:
             sampled_feat = depth_network(pts, gradients, dirs, feature_vector)
