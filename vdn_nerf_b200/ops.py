@@ -61,6 +61,17 @@ def tc_fault() -> int:
 # ----------------------------------------------------------------------------------------------------
 # Packed parameters
 # ----------------------------------------------------------------------------------------------------
+_FORCE_REPACK = False
+
+
+def force_repack(on: bool) -> None:
+    """While on, PackedMLP.packed() re-materialises the weights on every call instead of trusting its version-keyed
+    cache: used while a training step is captured into a CUDA graph, so that the pack launch is part of the graph and
+    every replay sees the parameters the optimiser has written since."""
+    global _FORCE_REPACK
+    _FORCE_REPACK = bool(on)
+
+
 class PackedMLP:
     """Effective (weight-normed, padded, transposed) weights of one network in one device buffer.
 
@@ -115,7 +126,7 @@ class PackedMLP:
 
     def packed(self) -> torch.Tensor:
         key = tuple((p.data_ptr(), p._version) for p in self.params)
-        if key != self._key or self._packed is None:
+        if key != self._key or self._packed is None or _FORCE_REPACK:
             dev = self.params[0].device
             for p in self.params:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():

@@ -61,3 +61,46 @@ def train_step(renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=N
     if grad_sync is not None:
         grad_sync()
     return loss.detach(), out
+
+
+class GraphedTrainStep:
+    """`train_step` captured once into a CUDA graph and replayed: the ~250 launches of a step (a good third of them
+    few-microsecond PyTorch element-wise kernels of the sampler and the loss) are issued by one graph launch, which
+    removes the gaps between them.  Single-process only (no collective inside the graph); shapes are fixed at capture.
+
+    The inputs of every call are copied into static device buffers; parameter tensors must keep their storage
+    (in-place optimiser updates); `param.grad` tensors are allocated once, inside the graph's memory pool, and
+    overwritten by each replay.  The weight packing launches are part of the graph (`ops.force_repack`)."""
+
+    def __init__(self, renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None,
+                 cos_anneal_ratio=1.0, perturb_overwrite=-1, igr_weight=0.1, warmup=3):
+        from . import ops
+        self.params = list(params)
+        self._static = [None if t is None else t.detach().clone()
+                        for t in (rays_o, rays_d, near, far, true_rgb, gt_feats, background_rgb)]
+        kw = dict(cos_anneal_ratio=cos_anneal_ratio, perturb_overwrite=perturb_overwrite, igr_weight=igr_weight)
+
+        def run():
+            o, d, n, f, rgb, gt, bg = self._static
+            return train_step(renderer, self.params, o, d, n, f, rgb, gt_feats=gt, background_rgb=bg, **kw)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                run()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        ops.force_repack(True)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss, self.out = run()
+        finally:
+            ops.force_repack(False)
+
+    def __call__(self, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None):
+        for dst, src in zip(self._static, (rays_o, rays_d, near, far, true_rgb, gt_feats, background_rgb)):
+            if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.out
