@@ -31,14 +31,14 @@ if [ "${1:-}" != "quick" ]; then
   echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "exit $?"; tail -c 900 $OUT/bench_ref.json
   echo "== ncu launch list"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_train.csv \
-      python bench.py --precision tf32 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_train.log 2>&1; echo "ncu exit $?"
+      python bench.py --precision tf32 --steps 1 --warmup 3 --no-cpu-baseline --no-cuda-graph > $OUT/ncu_train.log 2>&1; echo "ncu exit $?"
   wc -l $OUT/launches_train.csv
   echo "== ncu full captures (one launch of each tcgen05 kernel)"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:sdf_chain_tc -c 1 -f -o $OUT/prof_chain \
       python bench.py --precision tf32 --workload grid --resolution 256 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_chain.log 2>&1; echo "ncu chain exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_nt_tc -s 100 -c 2 -f -o $OUT/prof_nt \
-      python bench.py --precision tf32 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_nt.log 2>&1; echo "ncu nt exit $?"
+      python bench.py --precision tf32 --steps 1 --warmup 3 --no-cpu-baseline --no-cuda-graph > $OUT/ncu_nt.log 2>&1; echo "ncu nt exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_tc -s 40 -c 2 -f -o $OUT/prof_tn \
-      python bench.py --precision tf32 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_tn.log 2>&1; echo "ncu tn exit $?"
+      python bench.py --precision tf32 --steps 1 --warmup 3 --no-cpu-baseline --no-cuda-graph > $OUT/ncu_tn.log 2>&1; echo "ncu tn exit $?"
 fi
 echo "== done"

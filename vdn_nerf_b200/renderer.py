@@ -179,14 +179,23 @@ class NeuSRenderer:
                 "_eik_num": eik_num, "_eik_den": eik_den}
 
     # ------------------------------------------------------------------------------------------------
+    def _lin(self, a, b, n, dev):
+        """torch.linspace evaluated on the host as in the reference (renderer.py:337, 343; the CPU and CUDA linspace
+        differ in the last bit), cached on the device: no host->device copy per step (CUDA-graph capturable)."""
+        cache = self.__dict__.setdefault("_lin_cache", {})
+        key = (float(a), float(b), int(n), str(dev))
+        if key not in cache:
+            cache[key] = torch.linspace(a, b, n).to(dev)
+        return cache[key]
+
     def _coarse_z(self, near, far, batch_size, perturb):
         """Coarse and outside sample depths (renderer.py:333-359); RNG draws in the reference's order."""
         dev = near.device
-        z_vals = torch.linspace(0.0, 1.0, self.n_samples).to(dev)
+        z_vals = self._lin(0.0, 1.0, self.n_samples, dev)
         z_vals = near + (far - near) * z_vals[None, :]
         z_out = None
         if self.n_outside > 0:
-            z_out = torch.linspace(1e-3, 1.0 - 1.0 / (self.n_outside + 1.0), self.n_outside).to(dev)
+            z_out = self._lin(1e-3, 1.0 - 1.0 / (self.n_outside + 1.0), self.n_outside, dev)
         if perturb > 0:
             t_rand = torch.rand([batch_size, 1], device=dev) - 0.5
             z_vals = z_vals + t_rand * 2.0 / self.n_samples

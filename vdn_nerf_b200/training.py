@@ -26,7 +26,7 @@ def driver_loss(render_out, true_rgb, mask=None, igr_weight=0.1, mask_weight=0.0
     if mask is None:
         mask = torch.ones_like(render_out["weight_sum"])
     if data_parallel and global_batch is not None:
-        mask_sum = mask.new_tensor(float(global_batch)) + 1e-5      # use_mask=False: mask == 1 (dpt_runner.py:209)
+        mask_sum = float(global_batch) + 1e-5      # use_mask=False: mask == 1 (dpt_runner.py:209); host scalar
     else:
         mask_sum = mask.sum() + 1e-5
     color_error = (color - true_rgb) * mask
@@ -66,19 +66,22 @@ def train_step(renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=N
 class GraphedTrainStep:
     """`train_step` captured once into a CUDA graph and replayed: the ~250 launches of a step (a good third of them
     few-microsecond PyTorch element-wise kernels of the sampler and the loss) are issued by one graph launch, which
-    removes the gaps between them.  Single-process only (no collective inside the graph); shapes are fixed at capture.
+    removes the gaps between them.  Shapes are fixed at capture.  With `grad_sync` (data parallel) the two NCCL
+    all-reduces of the step are captured as well (NCCL >= 2.9 supports stream capture); every rank must construct and
+    replay its graph in lock step.
 
     The inputs of every call are copied into static device buffers; parameter tensors must keep their storage
     (in-place optimiser updates); `param.grad` tensors are allocated once, inside the graph's memory pool, and
     overwritten by each replay.  The weight packing launches are part of the graph (`ops.force_repack`)."""
 
     def __init__(self, renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None,
-                 cos_anneal_ratio=1.0, perturb_overwrite=-1, igr_weight=0.1, warmup=3):
+                 cos_anneal_ratio=1.0, perturb_overwrite=-1, igr_weight=0.1, warmup=3, grad_sync=None, global_batch=None):
         from . import ops
         self.params = list(params)
         self._static = [None if t is None else t.detach().clone()
                         for t in (rays_o, rays_d, near, far, true_rgb, gt_feats, background_rgb)]
-        kw = dict(cos_anneal_ratio=cos_anneal_ratio, perturb_overwrite=perturb_overwrite, igr_weight=igr_weight)
+        kw = dict(cos_anneal_ratio=cos_anneal_ratio, perturb_overwrite=perturb_overwrite, igr_weight=igr_weight,
+                  grad_sync=grad_sync, global_batch=global_batch)
 
         def run():
             o, d, n, f, rgb, gt, bg = self._static
@@ -92,11 +95,13 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         ops.force_repack(True)
+        c0 = ops.launch_count()
         try:
             with torch.cuda.graph(self.graph):
                 self.loss, self.out = run()
         finally:
             ops.force_repack(False)
+        self.launches_per_replay = ops.launch_count() - c0     # kernels of this library inside the graph
 
     def __call__(self, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None):
         for dst, src in zip(self._static, (rays_o, rays_d, near, far, true_rgb, gt_feats, background_rgb)):
