@@ -207,14 +207,17 @@ def run_reference(args):
         vals = []
         v, threads, times = cpu_reference_grid(sample, args.warmup + args.steps)
         value, unit, metric, ms = v, "pts/s", "sdf_grid_pts_per_s", 1e3 * sum(times) / len(times)
-        cfg = {"workload": "extract_fields 512^3 SDF grid query (womsk_white SDF net)", "resolution": 512}
+        cfg = {"workload": "extract_fields SDF grid query, womsk_white SDF net, x-slabs per rank", "resolution": 512,
+               "mode": "reference algorithm, PyTorch CPU fp32"}
         sample_s = f"{sample} lattice-like points per step, PyTorch CPU fp32"
     else:
         sample = 64
         v, threads, times = cpu_reference_step(sample, depth, args.steps, warm=args.warmup)
         value, unit, metric, ms = v, "rays/s", "train_rays_per_s", 1e3 * sum(times) / len(times)
-        cfg = {"workload": "womsk_white%s training step: render fwd + loss + bwd, 64+64 samples + 32 outside"
-                           % ("_wdepth" if depth else ""), "rays_per_step_per_gpu": args.rays}
+        cfg = {"workload": "womsk_white%s training step (BASELINE configs[%d]): render fwd + driver loss + bwd"
+                           % ("_wdepth" if depth else "", 2 if depth else 1), "rays_per_step_per_gpu": args.rays,
+               "global_batch": args.rays, "n_samples": 64, "n_importance": 64, "n_outside": 32,
+               "mode": "reference algorithm, PyTorch CPU fp32 autograd"}
         sample_s = f"{sample} rays per step (bounded sample of the {args.rays}-ray batch), PyTorch CPU fp32, autograd"
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
