@@ -287,3 +287,52 @@ def composite_backward(o, d, mid_z, dists, sdf, nrm, col, feat, sigma_bg, rgb_bg
         else:
             out["d_sigma_bg"] = abar_bg.reshape(sigma_bg.shape)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Arithmetic of the fused tcgen05 chain kernel (csrc/sdf_chain_tc.cuh), emulated on the CPU
+# ---------------------------------------------------------------------------------------------------------
+B2 = 144.26950408889634          # beta / ln 2 for beta = 100
+# degree-4 fit of log2(1+w)/w on [0,1] - the constants of softplus_base2() in csrc/sdf_chain_tc.cuh
+_Q = (0.04008112847805023, -0.1803952157497406, 0.4036492109298706, -0.7047332525253296, 1.4414016008377075)
+
+
+def to_tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest, ties away from zero, on the 13 dropped mantissa bits: the two-instruction form the kernels
+    use (csrc/gemm_tc.cuh), equal to cvt.rna.tf32.f32 for finite inputs."""
+    i = x.detach().to(torch.float32).contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def softplus_base2(t: torch.Tensor) -> torch.Tensor:
+    """a' = log2(1 + 2^t) = max(t, 0) + w q(w), w = 2^-|t|, in fp32 as the kernel evaluates it."""
+    t = t.to(torch.float32)
+    w = torch.exp2(-t.abs())
+    q = torch.full_like(w, _Q[0])
+    for c in _Q[1:]:
+        q = q * w + c
+    return w * q + torch.clamp(t, min=0.0)
+
+
+def sdf_chain_emulated(p, x, spec: vo.SDFSpec) -> torch.Tensor:
+    """SDF value through the chain kernel's arithmetic: fp16 operands (weights and activations rounded to nearest),
+    exact products, fp32 accumulation, base-2 softplus units (t = z * beta/ln2; the beta scaling cancels between
+    layers), skip 1/sqrt2 applied to the skip layer's accumulator.  Returns sdf [N,1] in fp32."""
+    f16 = lambda a: a.to(torch.float16).to(torch.float32)
+    L = spec.n_lin
+    skip = spec.skip_in[0] if len(spec.skip_in) else -1
+    y = (x * spec.scale).to(torch.float32)
+    e = vo.embed(y, spec.multires).to(torch.float32) * B2
+    h = f16(e)
+    for l in range(L):
+        W = f16(vo.effective_weight(p, f"lin{l}").to(torch.float32))
+        b = p[f"lin{l}.bias"].to(torch.float32) * B2
+        dsc = INV_SQRT2 if l == skip else 1.0
+        if l == skip:
+            h = torch.cat([h, f16(e)], dim=1)
+        acc = h @ W.t()                                    # fp16-representable operands: fp32 products are exact
+        t = acc * dsc + b
+        if l == L - 1:
+            return (t[:, :1] / B2) / spec.scale
+        h = f16(softplus_base2(t))
+    raise AssertionError("unreachable")

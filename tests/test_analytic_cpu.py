@@ -116,3 +116,46 @@ def test_composite_closed_form_backward(with_bg, with_feat, alpha_mode):
             # the kernel returns only the true_cos path of d (pts_norm masks are detached in the reference)
             pass
         assert torch.allclose(got[k], want, rtol=1e-8, atol=1e-10 * (1 + want.abs().max())), k
+
+
+def test_tf32_rounding_trick_matches_round_to_nearest_ties_away():
+    """The two-instruction rounding of the tensor-core operands equals round-to-nearest (ties away) on 10 mantissa bits."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.cat([torch.randn(20000, generator=g) * 10 ** torch.randint(-6, 6, (20000,), generator=g).float(),
+                   torch.tensor([0.0, -0.0, 1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -1.0 - 2 ** -11, 3.4e38 * 0.5, 1e-38])])
+    got = ar.to_tf32(x).double()
+    xd = x.double()
+    ex = torch.floor(torch.log2(xd.abs().clamp(min=1e-300)))
+    ulp = torch.pow(torch.tensor(2.0, dtype=torch.float64), ex - 10)
+    want = torch.sign(xd) * torch.floor(xd.abs() / ulp + 0.5) * ulp
+    normal = xd.abs() >= 2.0 ** -126
+    assert torch.equal(got[normal], want[normal])
+    assert bool((got[~normal].abs() <= xd[~normal].abs() + 2.0 ** -136).all())
+    assert bool(((ar.to_tf32(x).view(torch.int32) & 0x1FFF) == 0).all())
+
+
+def test_base2_softplus_polynomial_error_budget():
+    """a' = log2(1+2^t) through the kernel's degree-4 polynomial: |err| < 3.3e-5 in a' (2.3e-7 in softplus units), an
+    order of magnitude below the fp16 rounding of a' - and the base-2 form is softplus(beta=100) exactly."""
+    t = torch.linspace(-40.0, 40.0, 400001, dtype=torch.float64)
+    want = torch.log2(1.0 + torch.exp2(-t.abs())) + t.clamp(min=0.0)
+    got = ar.softplus_base2(t.float()).double()
+    assert float((got - want).abs().max()) < 3.4e-5
+    z = t / ar.B2
+    assert float((want / ar.B2 - vo.softplus100(z)).abs().max()) < 1e-9      # threshold branch differs by < 3e-9
+
+
+def test_chain_kernel_arithmetic_within_tensor_core_tolerance():
+    """fp16 operands + fp32 accumulation + base-2 softplus, emulated on the CPU for the reference's geometric
+    initialisation (womsk_white widths): the SDF value stays within the 2e-3 tensor-core tolerance of the fp64 oracle."""
+    from tests import util
+    mods, conf = util.build("womsk_white")
+    nets64 = util.oracle_nets(mods, conf, dtype=torch.float64)
+    nets32 = util.oracle_nets(mods, conf, dtype=torch.float32)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(4096, 3, generator=g) * 2.4 - 1.2
+    want = vo.sdf_value(nets64.sdf, x.double(), nets64.sdf_spec)
+    got = ar.sdf_chain_emulated(nets32.sdf, x, nets32.sdf_spec).double()
+    err = float((got - want).abs().max() / want.abs().max())
+    print(f"chain arithmetic (CPU emulation) rel err {err:.2e}")
+    assert err < 2e-3
