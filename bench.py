@@ -315,16 +315,15 @@ def run_ours(args):
             # capture is refused.  Multi-GPU runs stay eager: capturing the step together with its two NCCL all-reduces
             # hung in the round-1 trial (2 GPUs), see DESIGN.md section 5.
             from vdn_nerf_b200.training import GraphedTrainStep
-            fn(0)                                       # eager warm-up: library / NCCL initialisation outside the capture
+            fn(0)                                       # eager warm-up: one-time library initialisation outside the capture
             torch.manual_seed(2)
             try:
                 gstep = GraphedTrainStep(rend, params, o, d, near, far, rgb, gt_feats=gt, background_rgb=bg,
                                          cos_anneal_ratio=1.0, warmup=2, grad_sync=sync, global_batch=B * world)
                 per_replay = int(gstep.launches_per_replay)
-                good = 1.0
             except Exception as ex:                     # noqa: BLE001 - any capture failure means "run eagerly"
                 print("CUDA graph capture failed, running eagerly: %r" % (ex,), file=sys.stderr)
-                gstep, good = None, 0.0
+                gstep = None
                 torch.cuda.synchronize()
 
             def gfn(i):
