@@ -130,6 +130,23 @@ def max_over_ranks(x, world, dev):
     return float(t[0])
 
 
+def ncu_traffic(name):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches) from the
+    committed `ncu --set full` summary profiles/r01_ncu_full_<name>.txt; None when the file is missing."""
+    units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_%s.txt" % name)
+        tot, n = 0.0, 0
+        for ln in open(path):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * units.get(f[2], 1.0)
+                n += f[0] == "dram__bytes_read.sum"
+        return tot / n if n else None
+    except Exception:   # noqa: BLE001 - a missing or malformed summary only means "no traffic figure"
+        return None
+
+
 def timed_steps(fn, steps, warmup, world, dev, flush, lib):
     """W untimed + K timed calls of fn(i); every timed call is bracketed by CUDA events on the current stream,
     an L2 flush (a 256 MiB write) runs untimed between calls.  Returns total milliseconds (max over ranks)."""
@@ -288,7 +305,10 @@ def run_ours(args):
                              "d2h_bytes_per_step": int(local_pts * 4)},
                      "roofline": {"bound": "tensor", "kernel": kname,
                                   "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                                  "frac": ach / pk["bf16_sustained"], "traffic": None,
+                                  "frac": ach / pk["bf16_sustained"],
+                                  "traffic": ncu_traffic("chain") if args.precision == "tf32" else None,
+                                  "traffic_note": "DRAM bytes per launch of a 2 M-point slab (ncu --set full, "
+                                                  "profiles/r01_ncu_full_chain.txt); algorithmic: 8 MB written",
                                   "peak_source": pk["source"] + " bf16 sustained (kind::f16 runs at the bf16 rate)",
                                   "launch_ms": fam_ms / max(1, fam_n)}})
         if args.precision == "tf32":
@@ -377,7 +397,12 @@ def run_ours(args):
             roof = {"bound": "hbm", "kernel": "%s (layer-wise tcgen05 kind::tf32 GEMM with fused prologue/epilogue), %d launches "
                     "per step; algorithmic bytes = every operand / output / auxiliary element once"
                     % ("gemm_nt_tc_kernel" if dom == "tc" else "gemm_tn_tc_kernel", fam[dom][1]),
-                    "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                    "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                    "traffic": ncu_traffic("nt" if dom == "tc" else "tn"),
+                    "traffic_note": "DRAM bytes per launch, mean of the two launches captured with ncu --set full "
+                                    "(profiles/r01_ncu_full_%s.txt); compare algorithmic_bytes_per_launch"
+                                    % ("nt" if dom == "tc" else "tn"),
+                    "algorithmic_bytes_per_launch": fam[dom][3] / max(1, fam[dom][1]),
                     "algorithmic_bytes_per_step": fam[dom][3], "kernel_ms": fam[dom][0],
                     "peak_source": pk["source"] + " hbm (copy)",
                     "all_gemm_families": {k: {"ms": v[0], "launches": v[1], "GB/s": (v[3] / (v[0] * 1e-3) / 1e9) if v[0] else 0.0,
