@@ -105,3 +105,23 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_helpers_of_the_graph_capturable_step():
+    """No host->device traffic per step: the sampler's host-evaluated linspace is cached on the device, the packed
+    weight cache can be forced to re-materialise (what a CUDA-graph capture needs), the split SDF entry point fails as
+    loudly as the reference-shaped one on CPU tensors."""
+    from vdn_nerf_b200.renderer import NeuSRenderer
+    mods, conf = util.build("womsk_white")
+    rend = NeuSRenderer(*mods, **conf["neus_renderer"])
+    a = rend._lin(0.0, 1.0, 64, torch.device("cpu"))
+    assert a is rend._lin(0.0, 1.0, 64, torch.device("cpu"))
+    assert torch.equal(a, torch.linspace(0.0, 1.0, 64))
+    assert rend._lin(1e-3, 1.0 - 1.0 / 33.0, 32, torch.device("cpu")) is not a
+    assert ops._FORCE_REPACK is False
+    ops.force_repack(True)
+    assert ops._FORCE_REPACK is True
+    ops.force_repack(False)
+    assert ops._FORCE_REPACK is False
+    with pytest.raises(_lib.VdnLibraryError):
+        mods[1].forward_split(torch.zeros(4, 3))
