@@ -314,16 +314,18 @@ def softplus_base2(t: torch.Tensor) -> torch.Tensor:
     return w * q + torch.clamp(t, min=0.0)
 
 
-def sdf_chain_emulated(p, x, spec: vo.SDFSpec) -> torch.Tensor:
+def sdf_chain_emulated(p, x, spec: vo.SDFSpec, return_z: bool = False):
     """SDF value through the chain kernel's arithmetic: fp16 operands (weights and activations rounded to nearest),
     exact products, fp32 accumulation, base-2 softplus units (t = z * beta/ln2; the beta scaling cancels between
-    layers), skip 1/sqrt2 applied to the skip layer's accumulator.  Returns sdf [N,1] in fp32."""
+    layers), skip 1/sqrt2 applied to the skip layer's accumulator.  Returns sdf [N,1] in fp32 (and, with `return_z`,
+    the pre-activations z_l = t_l * ln2/beta of layers 0..L-2 that the training-forward variant stores)."""
     f16 = lambda a: a.to(torch.float16).to(torch.float32)
     L = spec.n_lin
     skip = spec.skip_in[0] if len(spec.skip_in) else -1
     y = (x * spec.scale).to(torch.float32)
     e = vo.embed(y, spec.multires).to(torch.float32) * B2
     h = f16(e)
+    zs = []
     for l in range(L):
         W = f16(vo.effective_weight(p, f"lin{l}").to(torch.float32))
         b = p[f"lin{l}.bias"].to(torch.float32) * B2
@@ -333,6 +335,35 @@ def sdf_chain_emulated(p, x, spec: vo.SDFSpec) -> torch.Tensor:
         acc = h @ W.t()                                    # fp16-representable operands: fp32 products are exact
         t = acc * dsc + b
         if l == L - 1:
-            return (t[:, :1] / B2) / spec.scale
+            sdf = (t[:, :1] / B2) / spec.scale
+            return (sdf, zs) if return_z else sdf
+        zs.append(t / B2)
         h = f16(softplus_base2(t))
     raise AssertionError("unreachable")
+
+
+def sdf_normals_emulated(p, x, spec: vo.SDFSpec) -> torch.Tensor:
+    """Normals through the tensor-core mode's arithmetic: pre-activations from the fused chain (above), then the
+    layer-wise reverse pass of csrc/sdf_net.cu (vdn_sdf_normals) with both GEMM operands rounded to tf32 and fp32
+    accumulation - delta_l = sp'(z_l) * Gin_l is formed in fp32 in the operand prologue and rounded once."""
+    L = spec.n_lin
+    skip = spec.skip_in[0] if len(spec.skip_in) else -1
+    _, Z = sdf_chain_emulated(p, x, spec, return_z=True)
+    W = [vo.effective_weight(p, f"lin{l}").to(torch.float32) for l in range(L)]
+    y = (x * spec.scale).to(torch.float32)
+    d_e = x.shape[1] * (1 + 2 * spec.multires)
+    G = [None] * (L + 1)
+
+    def gin(l):
+        if l == L - 2:
+            return W[L - 1][0:1, :].expand(x.shape[0], -1)
+        g = G[l + 1]
+        return g[:, : W[l].shape[0]] * INV_SQRT2 if l + 1 == skip else g
+    for l in range(L - 2, -1, -1):
+        delta = to_tf32(sp1(Z[l]) * gin(l))
+        G[l] = delta @ to_tf32(W[l])
+    de = G[0]
+    if skip >= 0:
+        de = de + G[skip][:, W[skip].shape[1] - d_e:] * INV_SQRT2
+    J = embed_jac(y, spec.multires)
+    return torch.einsum("nc,ncj->nj", de, J)

@@ -159,3 +159,9 @@ def test_chain_kernel_arithmetic_within_tensor_core_tolerance():
     err = float((got - want).abs().max() / want.abs().max())
     print(f"chain arithmetic (CPU emulation) rel err {err:.2e}")
     assert err < 2e-3
+    # normals: chain pre-activations + tf32 layer-wise reverse pass (vdn_sdf_normals' arithmetic)
+    wantn = vo.sdf_gradient(nets64.sdf, x.double(), nets64.sdf_spec).detach().squeeze(1)
+    gotn = ar.sdf_normals_emulated(nets32.sdf, x, nets32.sdf_spec).double()
+    errn = float((gotn - wantn).abs().max() / wantn.abs().max())
+    print(f"tensor-core normals (CPU emulation) rel err {errn:.2e}")
+    assert errn < 2e-3
