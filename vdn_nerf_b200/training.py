@@ -66,9 +66,11 @@ def train_step(renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=N
 class GraphedTrainStep:
     """`train_step` captured once into a CUDA graph and replayed: the ~250 launches of a step (a good third of them
     few-microsecond PyTorch element-wise kernels of the sampler and the loss) are issued by one graph launch, which
-    removes the gaps between them.  Shapes are fixed at capture.  With `grad_sync` (data parallel) the two NCCL
-    all-reduces of the step are captured as well (NCCL >= 2.9 supports stream capture); every rank must construct and
-    replay its graph in lock step.
+    removes the gaps between them.  Shapes are fixed at capture.
+
+    Single process only in practice: `grad_sync` / `global_batch` are accepted so that the two NCCL all-reduces of a
+    data-parallel step could be captured as well, but that path is EXPERIMENTAL - the one 2-GPU trial of round 1 hung
+    during warm-up / capture - and `bench.py` launches multi-GPU steps eagerly.
 
     The inputs of every call are copied into static device buffers; parameter tensors must keep their storage
     (in-place optimiser updates); `param.grad` tensors are allocated once, inside the graph's memory pool, and
