@@ -71,3 +71,21 @@ def test_data_parallel_equals_single_process():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world_size, _free_port(), ret), nprocs=world_size, join=True)
     assert all(ret.get(r) for r in range(world_size)), dict(ret)
+
+
+def test_flat_grad_allreduce_single_process_paths():
+    """Without a process group the reducer is a scaled identity; parameters that received no gradient get zeros, the
+    flat buffer and its views are reused across calls."""
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(2, 2))]
+    ps[0].grad = torch.full((3, 4), 2.0)
+    ps[2].grad = torch.arange(4.0).reshape(2, 2)
+    sync = vdist.FlatGradAllReduce(ps)
+    sync(scale=0.5)
+    assert torch.equal(ps[0].grad, torch.full((3, 4), 1.0))
+    assert torch.equal(ps[1].grad, torch.zeros(5))
+    assert torch.equal(ps[2].grad, 0.5 * torch.arange(4.0).reshape(2, 2))
+    flat = sync.flat
+    ps[1].grad = torch.ones(5)
+    sync()
+    assert sync.flat is flat and torch.equal(ps[1].grad, torch.ones(5))
+    assert torch.equal(sync.flat, torch.cat([p.grad.reshape(-1) for p in ps]))
