@@ -1,9 +1,14 @@
-// SDF network (8x256 softplus(beta=100) MLP with skip connection, reference dpt_models/fields.py:9-108):
-// exact-fp32 layer-wise path.  Three passes, each a chain of gemm_nt launches with fused prologues/epilogues:
+// SDF network (8x256 softplus(beta=100) MLP with skip connection, reference dpt_models/fields.py:9-108).
+// Three passes, each a sequence of GEMM launches with fused prologues / epilogues (FFMA kernels in the exact-fp32
+// mode, tcgen05 kernels in the tensor-core mode):
 //
 //   vdn_sdf_forward   value (+ feature) forward                           fields.py:72-92
 //   vdn_sdf_normals   analytic reverse-mode input gradient d sdf / d x    fields.py:97-108 (replaces autograd.grad)
 //   vdn_sdf_backward  hand-derived backward of (sdf, feature, normals)    replaces autograd double backward
+//
+// In the tensor-core mode the forward runs through the fused chain kernel of sdf_chain_tc.cuh: all layers for a
+// value-only query (and the grid query), layers 0..L-2 with stored pre-activations for the training forward, whose
+// multi-head last layer stays a layer-wise launch.
 //
 // Math: SURVEY.md Appendix A.  Storage: one pre-activation tensor Z_l per layer (activations are recomputed
 // in the consumer's operand prologue), plus G_l = d sdf / d(input of layer l) from the normals pass.
