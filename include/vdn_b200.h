@@ -39,6 +39,11 @@ const char* vdn_error_string(int code);
  * out; vdn_tc_fault() reads it (synchronising). */
 int vdn_set_mode(int mode);
 int vdn_get_mode(void);
+/* Tensor-core mode only: 1 (default) runs the training passes of the three networks as fused layer chains
+ * (csrc/chain_engine.cuh: activations resident in tensor memory, 16-bit saved tensors, grouped TMA weight gradient),
+ * 0 runs them layer by layer (csrc/gemm_tc.cuh).  Must not change between a forward and its backward. */
+int vdn_set_chain(int on);
+int vdn_get_chain(void);
 int vdn_tc_fault(void);
 
 /* Debug aid: when device_buf (8192 int64 of device memory) is non-null, the tcgen05 kernels record time stamps there:
@@ -65,7 +70,8 @@ long long vdn_mlp_layout(int L, const int* in_dims /*host*/, const int* out_dims
  * (second entry null / 0 rows when unused).  g == null means a plain (not weight-normed) weight. */
 int vdn_mlp_pack(int L, const int* in_dims, const int* out_dims, const float* const* v, const float* const* g,
                  const float* const* b, const int* rows, const int* rot /*host, nullable: per-layer input-column
-                 rotation*/, float* packed, void* stream);
+                 rotation*/, const int* orot /*host, nullable: per-layer output rotation of the fp16 tile images
+                 (vdn_sdf_layer_orot / vdn_nerf_layer_orot)*/, float* packed, void* stream);
 /* Weight-norm backward + un-padding: packed gradient -> d weight_v, d weight_g, d bias (overwritten). */
 int vdn_mlp_unpack_grads(int L, const int* in_dims, const int* out_dims, const float* const* v,
                          const float* const* g, const int* rows, const int* rot, const float* dpacked,
@@ -73,6 +79,9 @@ int vdn_mlp_unpack_grads(int L, const int* in_dims, const int* out_dims, const f
 
 /* ---- SDFNetwork (fields.py:9-108).  cfg (host) = {d_in, multires, d_hidden, n_layers, d_out, skip_layer|-1} */
 int vdn_sdf_layer_dims(const int* cfg, int* in_dims, int* out_dims); /* returns number of linear layers */
+/* Output rotation per layer that vdn_mlp_pack must be given for this network (the stacked [sdf ; feature] head presents
+ * its features first in the fp16 tile images); returns the number of layers. */
+int vdn_sdf_layer_orot(const int* cfg, int* orot);
 long long vdn_sdf_blob_floats(const int* cfg, long long N, int save);
 long long vdn_sdf_blobg_floats(const int* cfg, long long N);
 long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N);

@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdn_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 
@@ -25,13 +25,16 @@ SIGNATURES = {
     "vdn_prof_read": (I, [I, P, P, P]),
     "vdn_prof_read_bytes": (I, [I, P]),
     "vdn_mlp_layout": (L, [I, P, P, P, P, P]),
-    "vdn_mlp_pack": (I, [I, P, P, P, P, P, P, P, P, P]),
+    "vdn_mlp_pack": (I, [I, P, P, P, P, P, P, P, P, P, P]),
     "vdn_mlp_unpack_grads": (I, [I, P, P, P, P, P, P, P, P, P, P, P]),
     "vdn_set_mode": (I, [I]),
     "vdn_get_mode": (I, []),
+    "vdn_set_chain": (I, [I]),
+    "vdn_get_chain": (I, []),
     "vdn_tc_fault": (I, []),
     "vdn_debug_timeline": (I, [P]),
     "vdn_sdf_layer_dims": (I, [P, P, P]),
+    "vdn_sdf_layer_orot": (I, [P, P]),
     "vdn_sdf_blob_floats": (L, [P, L, I]),
     "vdn_sdf_blobg_floats": (L, [P, L]),
     "vdn_sdf_bwd_ws_floats": (L, [P, L]),

@@ -8,6 +8,7 @@
 namespace vdn {
 std::atomic<long long> g_launches{0};
 int g_mode = 0;
+int g_chain = 1;
 int* g_tc_fault = nullptr;
 long long* g_tc_dbg = nullptr;
 
@@ -38,7 +39,7 @@ void prof_end(int family, cudaStream_t st) {
 }  // namespace vdn
 using namespace vdn;
 
-extern "C" int vdn_abi_version(void) { return 3; }
+extern "C" int vdn_abi_version(void) { return 4; }
 extern "C" long long vdn_launch_count(void) { return g_launches.load(); }
 extern "C" const char* vdn_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
@@ -54,6 +55,8 @@ extern "C" int vdn_set_mode(int mode) {
   return 0;
 }
 extern "C" int vdn_get_mode(void) { return g_mode; }
+extern "C" int vdn_set_chain(int on) { g_chain = on ? 1 : 0; return 0; }
+extern "C" int vdn_get_chain(void) { return g_chain; }
 extern "C" int vdn_tc_fault(void) {
   if (!g_tc_fault) return 0;
   int h = 0;

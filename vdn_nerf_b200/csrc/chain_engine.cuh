@@ -1,0 +1,627 @@
+// Chain engine (tensor-core mode): ONE persistent tcgen05 kernel that runs a whole layer chain of an MLP pass for
+// tiles of 128 points, the activations / cotangents never leaving the SM between layers.  The host describes a pass
+// as a table of PHASES; a phase is one GEMM  D[128 x n] = A[128 x K] * B[n x K]^T  plus an element-wise epilogue
+// that turns D into the next phase's A operand and / or into the few tensors that have to reach HBM.
+//
+//   passes built on it (sdf_net.cu, relu_nets.cu):
+//     SDF training forward        fields.py:72-92      (softplus chain, stores the fp16 layer inputs)
+//     SDF analytic normals        fields.py:97-108     (reverse-mode input gradient)
+//     SDF backward phase 1 / 2    replaces autograd's double backward (Appendix A (1), (2))
+//     RenderingNetwork / NeRF forward and input-gradient passes   fields.py:148-176, 324-355
+//
+// Execution model (the one of sdf_chain_tc.cuh, generalised): per CTA two tiles ("slots" X and Y) are in flight and
+// alternate phases.  The A operand of a slot lives in TENSOR MEMORY as packed 16-bit pairs (columns 256 + 128 s ..,
+// lane = point) and is the A operand of tcgen05.mma kind::f16 (fp16 or bf16 A, fp16 weights, fp32 accumulate); one
+// 256-column fp32 accumulator D is shared by both slots: sixteen epilogue warps drain it into registers as soon as
+// a phase completes, release it for the other slot's MMAs, and run the element-wise work from registers while the
+// tensor pipe is busy with the other slot.  Weight K blocks ([n x 64] fp16 SWIZZLE_128B images, mlp_layout.cuh)
+// stream through a 6-stage cp.async.bulk / mbarrier ring; the first blocks of a phase serve both slots.
+//
+// What reaches HBM is 16-bit: every phase may store the A operand it produces (row-major [Npad, ld] fp16 / bf16) -
+// that tensor is at the same time the saved activation of the backward passes and an operand of the grouped
+// weight-gradient kernel (wgrad16.cuh), which reads it through TMA tensor maps.  Saved activations are read back
+// by the later passes as per-thread 128-byte rows (thread = point, 64 consecutive features).
+//
+// Thread mapping of the epilogue warps: warp w -> TMEM lane quarter q = w & 3 (rows 32 q .. 32 q + 31) and column
+// block hq = w >> 2 (columns 64 hq .. 64 hq + 63), eight groups of eight columns.
+#pragma once
+#include "gemm_tc.cuh"
+#include <cuda_fp16.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace vdn {
+namespace ce {
+
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;   // + warp 16: TMEM alloc + MMA issue; warp 17: weight stream
+constexpr int WSTAGES = 6;
+constexpr int KEEP = 4;                          // weight blocks of a phase kept in the ring for the second slot
+constexpr uint32_t W_STAGE = 32768;
+constexpr int MAX_PHASES = 16;
+constexpr int MAX_STASH = 2;
+constexpr size_t SMEM = WSTAGES * W_STAGE + 1024 + MAX_PHASES * 256 * sizeof(float) + 2 * 256 * sizeof(float);
+
+constexpr float kB2 = 144.26950408889634f;       // beta / ln 2 (Softplus(beta=100), fields.py:50)
+constexpr float kInvB2 = 1.0f / 144.26950408889634f;
+
+enum Op : int {
+  OP_OUT32 = 0,   // fp32 output only: o32[m, c] = act(x) * o32_mul (act 0 none, 1 sigmoid, 2 relu)
+  OP_SOFTPLUS,    // A = fp16 log2(1 + 2^x)                                     (SDF forward, base-2 softplus units)
+  OP_NSTEP,       // A = fp16 S * x,  S = 1 - 2^-aux0                            (SDF normals pass: delta_{l-1})
+  OP_P1STEP,      // A = bf16 S * x * a_mul ; o16b = bf16 100 (1 - S) aux1 x     (backward of the normals pass)
+  OP_P2STEP,      // A = bf16 S * x + aux1                                       (ordinary backward with injection)
+  OP_RELU,        // A = fp16 max(x, 0)
+  OP_LINEAR,      // A = fp16 x
+  OP_STASH,       // scratch <- raw accumulator
+  OP_MASK,        // A = bf16 (aux0 > 0 ? x : 0)   (aux0 null: x)
+};
+// x = acc * dsc + bias (+ stash) (+ r1[m] * row[c])
+
+struct Phase {
+  // ---- tensor-core side ----
+  long long img_off;     // float offset (into `packed`) of K block 0 of the 16-bit image of B
+  long long img2_off;    // second image accumulated with the same A (the "lo" part of a bf16 hi/lo weight), -1: none
+  int img_rows;          // rows per K block of that image
+  int row0;              // first image row (multiple of 8)
+  int kb0;               // first K block
+  int n_mma;             // N of the MMA (multiple of 16, <= 256)
+  int nks;               // K steps of 16 (1..16)
+  int a_col;             // packed-column offset of the A operand inside the slot
+  int a_bf16;            // A operand format (0 fp16, 1 bf16)
+  int b_bf16;            // B (weight image) format
+  // ---- epilogue ----
+  int op;
+  int width;             // valid output columns of this phase (<= n_mma)
+  float dsc;             // accumulator scale
+  long long bias_off;    // float offset of the bias in `packed`, -1: none
+  float bias_mul;
+  int a_out;             // 1: the epilogue writes the slot (A of the next phase)
+  int a_wr;              // number of A columns written (multiple of 8, zero padded beyond width + tail)
+  float a_mul;           // OP_P1STEP: scale of the A written
+  const void* aux0; int ld0; int aux0_bf16;
+  const void* aux1; int ld1; int aux1_bf16;
+  void* o16a; int ldo16a; float o16a_mul; int o16a_bf16;   // 16-bit copy of the A values (times o16a_mul)
+  void* o16c; int ldo16c; int o16c_bf16;    // another copy of the A values (e.g. the other 16-bit format)
+  void* o16b; int ldo16b;                   // second 16-bit output (OP_P1STEP), bf16
+  float* o32; int ldo32; int o32_c0, o32_w; float o32_mul; int act;   // fp32 store of act(x) for columns [o32_c0, o32_c0 + o32_w)
+  float* o32b; int ldo32b; int o32b_c0, o32b_w;                       // second fp32 store of x (no activation), other columns
+  const void* tail; int ldt; int tail_w; float tail_mul; int tail_bf16;   // A columns [width, width + tail_w) from here
+  const float* r1; int r1_stride; float r1_mul; int r1_row;   // rank-1 term, r1_row in {0, 1}
+  int stash_w, stash_r;  // stash index written (OP_STASH) / read (-1: none)
+  const void* aload; int al_ld, al_w;       // after this phase: load [128 x al_w] 16-bit values into the slot (A of the next)
+};
+
+struct Args {
+  int P;
+  long long N;
+  const float* packed;
+  const void* a0; int a0_ld, a0_w;          // A operand of phase 0
+  long long row_off[2]; int row_len[2];     // rank-1 row vectors (float offsets into packed, -1: none)
+  float* stash;                             // [grid][2][MAX_STASH][8][512][8] floats
+  Phase ph[MAX_PHASES];
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_b2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void unpack_h8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void unpack_b8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, int bf16, float (&f)[8]) {
+  if (bf16) unpack_b8(u, f); else unpack_h8(u, f);
+}
+// a' = log2(1 + 2^t), same evaluation as sdf_chain_tc.cuh
+__device__ __forceinline__ float softplus2(float t) {
+  const float w = ex2f(-fabsf(t));
+  float q = fmaf(0.04008112847805023f, w, -0.1803952157497406f);
+  q = fmaf(q, w, 0.4036492109298706f);
+  q = fmaf(q, w, -0.7047332525253296f);
+  q = fmaf(q, w, 1.4414016008377075f);
+  return fmaf(w, q, fmaxf(t, 0.0f));
+}
+__device__ __forceinline__ uint4 ld16(const void* base, long long m, int ld, int c) {
+  return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + m * ld + c));
+}
+__device__ __forceinline__ void st16(void* base, long long m, int ld, int c, const uint32_t (&p)[4]) {
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + m * ld + c) = make_uint4(p[0], p[1], p[2], p[3]);
+}
+__device__ __forceinline__ float ld16_one(const void* base, long long idx, int bf16) {
+  const uint16_t h = __ldg(reinterpret_cast<const uint16_t*>(base) + idx);
+  return bf16 ? __uint_as_float((uint32_t)h << 16) : __half2float(__ushort_as_half(h));
+}
+
+// One phase's element-wise work for one thread: its row m, columns c0 .. c0 + 63 (accumulator values v).
+// `half` selects columns c0 + 32 half .. + 31 (four groups of eight): the accumulator is drained and processed in two
+// halves so that 32 + ~45 registers suffice (a thread of a 576-thread CTA has 96).
+template <int OP>
+__device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], int half, const float* sb, const float* srow,
+                                       long long m, long long N, int c0, uint32_t tA, float* stash_base) {
+  constexpr bool kBf16 = (OP == OP_P1STEP || OP == OP_P2STEP || OP == OP_MASK);
+  const int ncols = ph.a_out ? ph.a_wr : ph.width;      // columns this phase touches
+  const float r1v = ph.r1 ? ph.r1[m < N ? m * ph.r1_stride : 0] * ph.r1_mul : 0.0f;
+  const float* rr = srow + ph.r1_row * 256;
+  const bool rowok = m < N;
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {
+    const int g = half * 4 + gi;
+    const int cg = c0 + 8 * g;
+    if (cg >= ncols) break;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = fmaf(v[gi][j], ph.dsc, sb[cg + j]);
+    if (ph.r1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaf(r1v, rr[cg + j], x[j]);
+    }
+    if (OP != OP_STASH && ph.stash_r >= 0) {
+      const float4* sp = reinterpret_cast<const float4*>(stash_base + ((size_t)ph.stash_r * 8 + g) * (512 * 8));
+      const float4 s0 = sp[0], s1 = sp[1];
+      x[0] += s0.x; x[1] += s0.y; x[2] += s0.z; x[3] += s0.w; x[4] += s1.x; x[5] += s1.y; x[6] += s1.z; x[7] += s1.w;
+    }
+    if (OP == OP_STASH) {
+      float4* sp = reinterpret_cast<float4*>(stash_base + ((size_t)ph.stash_w * 8 + g) * (512 * 8));
+      sp[0] = make_float4(v[gi][0], v[gi][1], v[gi][2], v[gi][3]);
+      sp[1] = make_float4(v[gi][4], v[gi][5], v[gi][6], v[gi][7]);
+      continue;
+    }
+    // fp32 side output of x (final outputs, skip-connection tails)
+    if (ph.o32 && rowok && cg + 8 > ph.o32_c0 && cg < ph.o32_c0 + ph.o32_w) {
+      float* op = ph.o32 + m * ph.ldo32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cg + j - ph.o32_c0;
+        if (c >= 0 && c < ph.o32_w) {
+          float y = x[j];
+          if (ph.act == 1) y = 1.0f / (1.0f + expf(-y));
+          else if (ph.act == 2) y = fmaxf(y, 0.0f);
+          op[c] = y * ph.o32_mul;
+        }
+      }
+    }
+    if (ph.o32b && rowok && cg + 8 > ph.o32b_c0 && cg < ph.o32b_c0 + ph.o32b_w) {
+      float* op = ph.o32b + m * ph.ldo32b;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cg + j - ph.o32b_c0;
+        if (c >= 0 && c < ph.o32b_w) op[c] = x[j];
+      }
+    }
+    if (OP == OP_OUT32) continue;
+    // ---- the A value (and the optional second output) ----
+    float r[8], r2[8];
+    float s_[8];
+    if (OP == OP_NSTEP || OP == OP_P1STEP || OP == OP_P2STEP) {
+      if (cg < ph.width) {
+        float a8[8];
+        unpack8(ld16(ph.aux0, m, ph.ld0, cg), ph.aux0_bf16, a8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);     // softplus'(z) = 1 - 2^-a'
+      }
+    }
+    if (OP == OP_SOFTPLUS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = softplus2(x[j]);
+    } else if (OP == OP_NSTEP) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = cg < ph.width ? s_[j] * x[j] : 0.0f;
+    } else if (OP == OP_P1STEP) {
+      float d8[8];
+      if (cg < ph.width) unpack8(ld16(ph.aux1, m, ph.ld1, cg), ph.aux1_bf16, d8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        r[j] = cg < ph.width ? s_[j] * x[j] * ph.a_mul : 0.0f;
+        r2[j] = cg < ph.width ? 100.0f * (1.0f - s_[j]) * d8[j] * x[j] : 0.0f;
+      }
+    } else if (OP == OP_P2STEP) {
+      float z8[8];
+      const bool inj = ph.aux1 != nullptr && cg < ph.width;
+      if (inj) unpack8(ld16(ph.aux1, m, ph.ld1, cg), ph.aux1_bf16, z8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = cg < ph.width ? fmaf(s_[j], x[j], inj ? z8[j] : 0.0f) : 0.0f;
+    } else if (OP == OP_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaxf(x[j], 0.0f);
+    } else if (OP == OP_LINEAR) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = x[j];
+    } else if (OP == OP_MASK) {
+      if (ph.aux0 && cg < ph.width) {
+        float h8[8];
+        unpack8(ld16(ph.aux0, m, ph.ld0, cg), ph.aux0_bf16, h8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = x[j];
+      }
+    }
+    // ragged edge: columns >= width carry the skip tail or zero padding
+    if (cg + 8 > ph.width) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cg + j;
+        if (c >= ph.width) {
+          const int tcol = c - ph.width;
+          r[j] = (ph.tail && tcol < ph.tail_w) ? ld16_one(ph.tail, m * ph.ldt + tcol, ph.tail_bf16) * ph.tail_mul : 0.0f;
+          if (OP == OP_P1STEP) r2[j] = 0.0f;
+        }
+      }
+    }
+    uint32_t p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = kBf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
+    if (ph.a_out) tc::tmem_st4(tA + (uint32_t)(4 * g), p);
+    if (ph.o16a) {
+      if (ph.o16a_mul != 1.0f || (ph.o16a_bf16 != 0) != kBf16) {
+        uint32_t pm[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pm[i] = ph.o16a_bf16 ? pack_b2(r[2 * i] * ph.o16a_mul, r[2 * i + 1] * ph.o16a_mul)
+                               : pack_h2(r[2 * i] * ph.o16a_mul, r[2 * i + 1] * ph.o16a_mul);
+        st16(ph.o16a, m, ph.ldo16a, cg, pm);
+      } else {
+        st16(ph.o16a, m, ph.ldo16a, cg, p);
+      }
+    }
+    if (ph.o16c) {
+      uint32_t pc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pc[i] = ph.o16c_bf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
+      st16(ph.o16c, m, ph.ldo16c, cg, pc);
+    }
+    if (OP == OP_P1STEP && ph.o16b) {
+      uint32_t p2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p2[i] = pack_b2(r2[2 * i], r2[2 * i + 1]);
+      st16(ph.o16b, m, ph.ldo16b, cg, p2);
+    }
+  }
+}
+
+static __global__ void __launch_bounds__(THREADS, 1)
+chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t w_full[WSTAGES], w_empty[WSTAGES], a_ready[2], d_full, d_drained;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sW = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  float* sB = reinterpret_cast<float*>(smem_raw + (sW - smem_u32(smem_raw)) + WSTAGES * W_STAGE);
+  float* sRow = sB + MAX_PHASES * 256;
+  const long long ntiles = (a.N + 127) / 128;
+  const long long G = gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < WSTAGES; ++s) { mbar_init(smem_u32(&w_full[s]), 1); mbar_init(smem_u32(&w_empty[s]), 1); }
+    for (int j = 0; j < 2; ++j) mbar_init(smem_u32(&a_ready[j]), EPI_WARPS * 32);
+    mbar_init(smem_u32(&d_full), 1);
+    mbar_init(smem_u32(&d_drained), EPI_WARPS * 32);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < a.P * 256; i += THREADS) {      // biases (scaled), zero beyond the phase's width
+    const int p = i >> 8, n = i & 255;
+    const Phase& ph = a.ph[p];
+    sB[i] = (ph.bias_off >= 0 && n < ph.width) ? a.packed[ph.bias_off + n] * ph.bias_mul : 0.0f;
+  }
+  for (int i = tid; i < 512; i += THREADS) {             // rank-1 row vectors
+    const int r = i >> 8, n = i & 255;
+    sRow[i] = (a.row_off[r] >= 0 && n < a.row_len[r]) ? a.packed[a.row_off[r] + n] : 0.0f;
+  }
+  if (warp == EPI_WARPS) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // accumulator D: columns [0,256); 16-bit A tiles: slot X columns [256,384), slot Y columns [384,512)
+  const uint32_t tmem_base = tmem_base_s;
+  bool ok = true;
+
+  if (warp < EPI_WARPS) {
+    // ================= epilogue warps =================
+    const int q = warp & 3, hq = warp >> 2;
+    const int row = q * 32 + lane;
+    const int c0 = hq * 64;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t tD = lane_base + (uint32_t)c0;
+    uint32_t dcnt = 0;
+    // [128 x w] 16-bit values, row-major in HBM -> slot s (packed columns 0 ..), then signal the slot
+    auto aload = [&](int s, long long tile, const void* src, int ld, int w) {
+      const long long m = tile * 128 + row;               // < Npad: the buffers are padded to whole tiles
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (c0 + 8 * g < w) {
+          const uint4 u = ld16(src, m, ld, c0 + 8 * g);
+          const uint32_t r[4] = {u.x, u.y, u.z, u.w};
+          tmem_st4(lane_base + 256u + (uint32_t)(s * 128 + hq * 32 + 4 * g), r);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&a_ready[s]));
+    };
+    // this thread's lines of the tensors a phase reads -> L2, one phase ahead
+    auto prefetch = [&](const Phase& ph, long long m) {
+      if (ph.aux0 && c0 < ph.width)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(ph.aux0) + m * ph.ld0 + c0));
+      if (ph.aux1 && c0 < ph.width)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(ph.aux1) + m * ph.ld1 + c0));
+    };
+    if ((long long)blockIdx.x < ntiles) aload(0, blockIdx.x, a.a0, a.a0_ld, a.a0_w);
+    if (blockIdx.x + G < ntiles) aload(1, blockIdx.x + G, a.a0, a.a0_ld, a.a0_w);
+    for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
+      const bool hasY = tX + G < ntiles;
+      for (int p = 0; p < a.P && ok; ++p) {
+        const Phase& ph = a.ph[p];
+        const bool last = (p == a.P - 1);
+        const float* sb = sB + p * 256;
+        for (int s = 0; s < 2 && ok; ++s) {
+          if (s && !hasY) break;
+          const long long tile = tX + s * G;
+          const long long m = tile * 128 + row;
+          if (!last) {
+            prefetch(a.ph[p + 1], m);
+            if (ph.aload && c0 < ph.al_w)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(ph.aload) + m * ph.al_ld + c0));
+          } else {
+            const long long tn = tX + (2 + s) * G;
+            if (tn < ntiles) {
+              prefetch(a.ph[0], tn * 128 + row);
+              if (c0 < a.a0_w)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(a.a0) + (tn * 128 + row) * a.a0_ld + c0));
+            }
+          }
+          ok = mbar_wait(smem_u32(&d_full), dcnt & 1);
+          ++dcnt;
+          tc_fence_after();
+          const uint32_t tA = lane_base + 256u + (uint32_t)(s * 128 + hq * 32);
+          float* stb = a.stash ? a.stash + (((size_t)blockIdx.x * 2 + s) * MAX_STASH * 8) * (512 * 8) + (size_t)tid * 8 : nullptr;
+          // the accumulator is drained in two halves of 32 columns; D is released once the second half sits in registers
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            float v[4][8];
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              if (c0 + 32 * half + 8 * gi < ph.n_mma) {
+                tmem_ld8(tD + (uint32_t)(32 * half + 8 * gi), v[gi]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[gi][j] = 0.0f;
+              }
+            }
+            tmem_ld_wait();
+            if (half == 1) {
+              tc_fence_before();
+              mbar_arrive(smem_u32(&d_drained));
+              // the slot's next A operand is what it holds already: release the MMA issuer right away
+              if (!last && !ph.a_out && !ph.aload) mbar_arrive(smem_u32(&a_ready[s]));
+            }
+            switch (ph.op) {
+              case OP_OUT32: run_op<OP_OUT32>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+              case OP_SOFTPLUS: run_op<OP_SOFTPLUS>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+              case OP_NSTEP: run_op<OP_NSTEP>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+              case OP_P1STEP: run_op<OP_P1STEP>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+              case OP_P2STEP: run_op<OP_P2STEP>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+              case OP_RELU: run_op<OP_RELU>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+              case OP_LINEAR: run_op<OP_LINEAR>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+              case OP_STASH: run_op<OP_STASH>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+              default: run_op<OP_MASK>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
+            }
+          }
+          if (!last) {
+            if (ph.a_out) {
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(smem_u32(&a_ready[s]));
+            } else if (ph.aload) {
+              aload(s, tile, ph.aload, ph.al_ld, ph.al_w);
+            }
+          } else {
+            const long long tn = tX + (2 + s) * G;     // the slot's next tile
+            if (tn < ntiles) aload(s, tn, a.a0, a.a0_ld, a.a0_w);
+          }
+        }
+      }
+    }
+  } else if (tid == EPI_WARPS * 32) {
+    // ================= MMA issuer: A from tensor memory, weights from shared memory =================
+    uint32_t acnt[2] = {0, 0};
+    uint32_t wt = 0, drained = 0;
+    const uint32_t tAcol = tmem_base + 256u;
+    for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
+      const bool hasY = tX + G < ntiles;
+      for (int p = 0; p < a.P && ok; ++p) {
+        const Phase& ph = a.ph[p];
+        const uint32_t idesc = umma_idesc_f16(128, (uint32_t)ph.n_mma) | (ph.a_bf16 ? (1u << 7) : 0u) | (ph.b_bf16 ? (1u << 10) : 0u);
+        const int nkb1 = (ph.nks + 3) >> 2;                      // K blocks of one image
+        const int nkb = ph.img2_off >= 0 ? 2 * nkb1 : nkb1;      // blocks streamed per phase (hi image, then lo image)
+        const int keep = nkb < KEEP ? nkb : KEEP;
+        for (int s = 0; s < 2 && ok; ++s) {
+          if (s && !hasY) break;
+          // the accumulator of the previous phase must have been drained (first phase ever: passes immediately)
+          ok = mbar_wait(smem_u32(&d_drained), (drained & 1) ^ 1);
+          ++drained;
+          ok = ok && mbar_wait(smem_u32(&a_ready[s]), acnt[s] & 1);
+          ++acnt[s];
+          tc_fence_after();
+          // Slot X streams all blocks of the phase in order and leaves the LAST `keep` in the ring; slot Y uses those
+          // first (no wait), releases them, then takes the others, which were fetched again behind them.  (Holding the
+          // last blocks rather than the first keeps the ring deadlock-free when a phase has more blocks than stages.)
+          for (int j = 0; j < nkb && ok; ++j) {
+            const bool held = (s == 1 && j < keep);
+            const int kb = s == 0 ? j : (held ? nkb - keep + j : j - keep);
+            const uint32_t w = wt + (uint32_t)(s == 0 || held ? kb : nkb + kb);
+            const uint32_t ws = w % WSTAGES, wph = (w / WSTAGES) & 1;
+            if (!held) {
+              ok = mbar_wait(smem_u32(&w_full[ws]), wph);
+              tc_fence_after();
+            }
+            const uint32_t b0 = sW + ws * W_STAGE;
+            const int ka = kb >= nkb1 ? kb - nkb1 : kb;          // K block of A (the lo image reuses the same A columns)
+            const int nk = ph.nks - 4 * ka < 4 ? ph.nks - 4 * ka : 4;
+            for (int ks = 0; ks < nk; ++ks)
+              umma_f16_ts(tmem_base, tAcol + (uint32_t)(s * 128 + ph.a_col + ka * 32 + ks * 8), umma_desc_sw128(b0 + ks * 32),
+                          idesc, (j | ks) ? 1u : 0u);
+            if (s == 1 || !hasY || kb < nkb - keep) umma_commit(smem_u32(&w_empty[ws]));
+          }
+          umma_commit(smem_u32(&d_full));
+        }
+        wt += (uint32_t)(hasY ? 2 * nkb - keep : nkb);
+      }
+    }
+  } else if (tid == (EPI_WARPS + 1) * 32) {
+    // ================= weight stream (TMA engine), in the order the MMA issuer consumes the blocks =================
+    uint32_t wt = 0;
+    for (long long tX = blockIdx.x; tX < ntiles && ok; tX += 2 * G) {
+      const bool hasY = tX + G < ntiles;
+      for (int p = 0; p < a.P && ok; ++p) {
+        const Phase& ph = a.ph[p];
+        const uint32_t bytes = (uint32_t)ph.n_mma * 128u;
+        const int nkb1 = (ph.nks + 3) >> 2;
+        const int nkb = ph.img2_off >= 0 ? 2 * nkb1 : nkb1;
+        const int keep = nkb < KEEP ? nkb : KEEP;
+        const int nfetch = hasY ? 2 * nkb - keep : nkb;
+        for (int f = 0; f < nfetch && ok; ++f, ++wt) {
+          const int kb = f < nkb ? f : f - nkb;                  // slot X: all blocks; slot Y: the first nkb - keep again
+          const int ka = kb >= nkb1 ? kb - nkb1 : kb;
+          const long long img = kb >= nkb1 ? ph.img2_off : ph.img_off;
+          const uint32_t ws = wt % WSTAGES, wph = (wt / WSTAGES) & 1;
+          ok = mbar_wait_backoff(smem_u32(&w_empty[ws]), wph ^ 1, 256);
+          mbar_arrive_expect_tx(smem_u32(&w_full[ws]), bytes);
+          bulk_g2s(sW + ws * W_STAGE, a.packed + img + ((size_t)(ph.kb0 + ka) * ph.img_rows + ph.row0) * 32, bytes,
+                   smem_u32(&w_full[ws]));
+        }
+      }
+    }
+  }
+  if (!ok && fault) *fault = 1;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+inline Phase make_phase() {
+  Phase p;
+  memset(&p, 0, sizeof(p));
+  p.dsc = 1.0f; p.bias_off = -1; p.bias_mul = 1.0f; p.a_mul = 1.0f; p.o16a_mul = 1.0f; p.o32_mul = 1.0f; p.tail_mul = 1.0f;
+  p.r1_mul = 1.0f; p.stash_w = -1; p.stash_r = -1; p.img2_off = -1;
+  return p;
+}
+inline void init_args(Args* a) {
+  memset(a, 0, sizeof(*a));
+  a->row_off[0] = a->row_off[1] = -1;
+}
+// B = rows [row0, row0 + n) of the fp16 image at img_off ([kblocks][img_rows][64]), K blocks kb0 ..
+inline void set_mma(Phase* p, long long img_off, int img_rows, int row0, int kb0, int n, int k, int a_col = 0) {
+  p->img_off = img_off; p->img2_off = -1; p->img_rows = img_rows; p->row0 = row0; p->kb0 = kb0;
+  p->n_mma = (n + 15) & ~15; p->nks = (k + 15) / 16; p->a_bf16 = 0; p->b_bf16 = 0; p->a_col = a_col;
+}
+// bf16 A operand times a bf16 hi/lo weight pair (two accumulating passes over the same A columns)
+inline void set_mma_bf16(Phase* p, long long hi_off, long long lo_off, int img_rows, int row0, int kb0, int n, int k,
+                         int a_col = 0) {
+  set_mma(p, hi_off, img_rows, row0, kb0, n, k, a_col);
+  p->img2_off = lo_off; p->a_bf16 = 1; p->b_bf16 = 1;
+}
+inline size_t stash_floats(int grid) { return (size_t)grid * 2 * MAX_STASH * 8 * 512 * 8; }
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+inline int grid_for(long long N) {
+  const long long ntiles = (N + 127) / 128;
+  const int sms = num_sms();
+  return (int)(ntiles < sms ? ntiles : sms);
+}
+
+// Debug aid (environment variable VDN_SYNC=1): synchronise after every launch of the new kernels and name the one that
+// failed on stderr.  Off by default: the library never synchronises.
+static inline int debug_sync(cudaStream_t st, const char* what, int tag) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VDN_SYNC"); on = (e && e[0] == '1') ? 1 : 0; }
+  cudaError_t e = cudaGetLastError();
+  if (on && e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (on && e != cudaSuccess) fprintf(stderr, "[vdn] %s (tag %d) failed: %s\n", what, tag, cudaGetErrorString(e));
+  return (int)e;
+}
+
+// Debug aid (VDN_NOMIX=1): declare every operand fp16 to the tensor core (numerically wrong for bf16 data; isolates
+// instruction-descriptor problems).
+static inline bool debug_nomix() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VDN_NOMIX"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+
+// Validates the table (the kernel trusts it) and launches.  Returns a cudaError_t value.
+static inline int launch(const Args& a_in, cudaStream_t st, int family) {
+  Args a = a_in;
+  if (debug_nomix())
+    for (int p = 0; p < a.P; ++p) a.ph[p].a_bf16 = a.ph[p].b_bf16 = 0;
+  if (a.N <= 0) return 0;
+  if (a.P < 1 || a.P > MAX_PHASES || !a.a0 || (a.a0_w & 7) || a.a0_w > 256) return (int)cudaErrorInvalidValue;
+  double flops = 0.0, bytes = 0.0;
+  for (int p = 0; p < a.P; ++p) {
+    const Phase& ph = a.ph[p];
+    if (ph.n_mma < 16 || ph.n_mma > 256 || (ph.n_mma & 15) || ph.nks < 1 || ph.nks > 16 || (ph.row0 & 7) ||
+        ph.width > ph.n_mma || (ph.a_out && (p == a.P - 1 || (ph.a_wr & 7) || ph.a_wr > 256)) ||
+        (ph.aload && (ph.a_out || p == a.P - 1 || (ph.al_w & 7))) || (ph.img_off & 255) ||
+        (ph.img2_off >= 0 && (ph.img2_off & 255)) || (ph.a_bf16 != ph.b_bf16))
+      return (int)cudaErrorInvalidValue;
+    if ((ph.op == OP_STASH || ph.stash_r >= 0) && !a.stash) return (int)cudaErrorInvalidValue;
+    flops += 2.0 * (double)a.N * ph.n_mma * ph.nks * 16 * (ph.img2_off >= 0 ? 2 : 1);
+    const double row16 = 2.0 * (double)a.N;
+    if (ph.aux0) bytes += row16 * ph.width;
+    if (ph.aux1) bytes += row16 * ph.width;
+    if (ph.o16a) bytes += row16 * (ph.a_out ? ph.a_wr : ph.width);
+    if (ph.o16b) bytes += row16 * ph.width;
+    if (ph.o16c) bytes += row16 * (ph.a_out ? ph.a_wr : ph.width);
+    if (ph.o32) bytes += 4.0 * (double)a.N * ph.o32_w;
+    if (ph.o32b) bytes += 4.0 * (double)a.N * ph.o32b_w;
+    if (ph.aload) bytes += row16 * ph.al_w;
+  }
+  bytes += 2.0 * (double)a.N * a.a0_w;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  prof_begin(family, st, flops, bytes);
+  VDN_LAUNCH(chain_kernel, grid_for(a.N), THREADS, SMEM, st, a, g_tc_fault);
+  prof_end(family, st);
+  return debug_sync(st, "chain_kernel", a.ph[0].op);
+}
+
+}  // namespace ce
+}  // namespace vdn

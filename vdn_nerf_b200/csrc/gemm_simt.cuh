@@ -402,7 +402,7 @@ inline bool operand_ok(const Operand& o) {
 // Optional per-family timing (vdn_prof_enable): CUDA events around the GEMM launches on the launching stream.
 void prof_begin(int family, cudaStream_t st, double flops, double bytes = 0.0);
 void prof_end(int family, cudaStream_t st);
-enum { PROF_GEMM_NT = 0, PROF_WGRAD = 1, PROF_TC = 2, PROF_CHAIN = 3, PROF_FAMILIES = 4 };
+enum { PROF_GEMM_NT = 0, PROF_WGRAD = 1, PROF_TC = 2, PROF_CHAIN = 3, PROF_CHAIN_TRAIN = 4, PROF_WGRAD16 = 5, PROF_FAMILIES = 6 };
 
 // Algorithmic HBM bytes of one GEMM launch: every operand / output element moved once (weights are L2 resident).
 inline double operand_bytes(const Operand& A, double M) {

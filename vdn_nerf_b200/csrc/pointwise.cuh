@@ -122,19 +122,22 @@ static __global__ void embed_jvp_kernel(const float* __restrict__ x, int ldx, lo
 //   sum_k f_k^2 ( -sin(f_k y_j) de_sin[k,j] - cos(f_k y_j) de_cos[k,j] )       
 static __global__ void embed_second_kernel(const float* __restrict__ x, int ldx, long long N, int d, int L, float scale,
                                     const float* __restrict__ nbar, int ldn, const float* __restrict__ de, int ldde,
-                                    float oscale, float* __restrict__ out, int ldo) {
+                                    const float* __restrict__ de2, int ldde2, float oscale, float* __restrict__ out,
+                                    int ldo) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * d) return;
   long long m = idx / d;
   int j = (int)(idx - m * d);
   float y = x[m * ldx + j] * scale;
   const float* r = de + m * ldde;
+  const float* r2 = de2 ? de2 + m * ldde2 : nullptr;       // optional second part of d sdf / d e (skip connection)
   float acc = 0.0f, f = 1.0f;
   for (int k = 0; k < L; ++k) {
     float s, c;
     sincosf(y * f, &s, &c);
     int cs = d + (2 * k) * d + j, cc = cs + d;
-    acc += f * f * (-s * r[cs] - c * r[cc]);
+    const float vs = r[cs] + (r2 ? r2[cs] : 0.0f), vc = r[cc] + (r2 ? r2[cc] : 0.0f);
+    acc += f * f * (-s * vs - c * vc);
     f *= 2.0f;
   }
   out[m * ldo + j] += oscale * nbar[m * ldn + j] * acc;

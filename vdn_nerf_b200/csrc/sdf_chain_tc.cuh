@@ -47,6 +47,7 @@ constexpr size_t CH_SMEM = CH_WSTAGES * CH_W_STAGE + 1024 + VDN_MAX_LAYERS * 256
 struct ChainLayer {
   long long img_off, bias_off;   // float offsets into the packed buffer
   int out_ld, out_dim, n_mma, nkb;
+  int row0;                      // first image row of the B tile (the sdf row of a rotated last layer)
 };
 struct ChainArgs {
   int L, skip, d_e, multires;
@@ -375,7 +376,7 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
           const uint32_t ws = wt % CH_WSTAGES, wph = (wt / CH_WSTAGES) & 1;
           ok = mbar_wait_backoff(smem_u32(&w_empty[ws]), wph ^ 1, 256);
           mbar_arrive_expect_tx(smem_u32(&w_full[ws]), bytes);
-          bulk_g2s(sW + ws * CH_W_STAGE, a.packed + Ly.img_off + (size_t)kb * Ly.out_ld * 32, bytes, smem_u32(&w_full[ws]));
+          bulk_g2s(sW + ws * CH_W_STAGE, a.packed + Ly.img_off + ((size_t)kb * Ly.out_ld + Ly.row0) * 32, bytes, smem_u32(&w_full[ws]));
         }
       }
     }
@@ -391,7 +392,8 @@ sdf_chain_tc_kernel(const __grid_constant__ ChainArgs a, int* __restrict__ fault
 static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, int d_hidden, int skip, float scale,
                                    const float* packed, const float* x, const float* xs, const float* ys,
                                    const float* zs, int ny, int nz, int i0, long long N, float* out, int lds, float out_mul,
-                                   cudaStream_t st, float* const* save_z = nullptr, float* save_u = nullptr, int ldz = 0) {
+                                   cudaStream_t st, int orot_last = 0, float* const* save_z = nullptr, float* save_u = nullptr,
+                                   int ldz = 0) {
   const int d_e = d_in * (1 + 2 * multires);
   if (d_in != 3 || d_hidden != 256 || d_e > 64 || ly.L < 2 || ly.L > VDN_MAX_LAYERS) return -1;
   for (int l = 1; l < ly.L; ++l)
@@ -405,7 +407,9 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
     c.img_off = ly.off_ih[l]; c.bias_off = ly.off_b[l]; c.out_ld = ly.out_ld[l]; c.out_dim = ly.out_dim[l];
     c.n_mma = (l == ly.L - 1) ? 16 : ((ly.out_dim[l] + 15) & ~15);
     c.nkb = (ly.in_dim[l] + 63) / 64;
-    if (c.n_mma > 256 || c.nkb > 4) return -1;
+    // last layer: only the sdf output is needed; with a rotated image (orot = 1) it sits at position out_dim - 1
+    c.row0 = (l == ly.L - 1 && orot_last) ? ly.out_dim[l] - orot_last : 0;
+    if (c.n_mma > 256 || c.nkb > 4 || (c.row0 & 7)) return -1;
   }
   // value-only: all L layers, sdf out.  Training forward (save_z given): layers 0..L-2 with stored pre-activations.
   const bool save = save_z != nullptr;

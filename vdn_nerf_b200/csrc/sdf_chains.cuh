@@ -1,0 +1,394 @@
+// SDF network on the chain engine (tensor-core mode): training forward, analytic normals and the two-phase backward
+// of SURVEY.md Appendix A as four chain launches + one grouped weight-gradient launch, all saved tensors 16-bit.
+//
+//   reference: SDFNetwork.forward / .gradient (dpt_models/fields.py:72-108) and autograd's double backward through them.
+//
+// Saved tensors (row-major, Npad = N rounded up to 128 rows; "A16" etc. are the names used in DESIGN.md).  The forward
+// and the normals pass compute with fp16 operands (10-bit mantissa; the stated <= 2e-3 tolerance on normals needs it), the
+// backward passes with bf16 cotangents (fp32 exponent range) against bf16 hi/lo weight pairs - tcgen05 kind::f16 cannot
+// mix the two formats in one instruction, so the layer inputs are kept in both:
+//   forward blob   E16 / EB16 [Npad, 64] fp16 / bf16   kB2 * embedding (layer-0 input; kB2 = beta / ln2: base-2 softplus units)
+//                  A16_l / AB16_l [Npad,256]           l = 0..L-2: a'_l = kB2 * softplus(z_l); the layer before the skip
+//                                                      connection holds [a' | kB2 * e] = sqrt2 * kB2 * (skip-layer input)
+//   normals blob   D16L [Npad,256] fp16   delta of the last hidden layer (first operand of the normals chain)
+//                  DB16_l [Npad,256] bf16 delta_l = softplus'(z_l) * d sdf / d h_l  (softplus' = 1 - 2^-a')
+//                  DE0, DES [Npad,48] fp32  d sdf / d e through layer 0 and through the skip connection
+//   backward ws    Q16_0 [Npad,64], Q16_l [Npad,256] bf16  q-bar_l (phase 1);  ZG16_l bf16 injected cotangents;
+//                  ZB16_l bf16  z-bar_l * (dsc_l / kB2)  (phase 2; pre-scaled so that ZB^T AB16 = z-bar^T u);
+//                  FB16 [Npad,256] bf16 feature cotangent; SB / ONESB [Npad,64] bf16 (column 0: d_sdf / kB2, ones)
+// Nothing else of a layer reaches HBM: softplus'(z) and softplus''(z) * a are recomputed from A16 / AB16 and DB16.
+#pragma once
+#include "chain_engine.cuh"
+#include "wgrad16.cuh"
+#include "pointwise.cuh"
+#include <cuda_bf16.h>
+
+namespace vdn {
+
+extern int g_chain;    // api.cu: fused training chains enabled (tensor-core mode only)
+
+
+inline long long pad128(long long n) { return (n + 127) / 128 * 128; }
+
+// ---- pointwise producers of the 16-bit chain inputs -----------------------------------------------------
+// E16[m, c] = fp16(kB2 * e_c(x * scale)), zero beyond d_e and beyond row N  (embedder.py:15-36, d = 3)
+static __global__ void sdf_embed16_kernel(const float* __restrict__ x, long long N, long long Npad, int L, float scale,
+                                          __half* __restrict__ e16, __nv_bfloat16* __restrict__ eb16) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Npad * 64) return;
+  const long long m = idx >> 6;
+  const int c = (int)(idx & 63);
+  float v = 0.0f;
+  if (m < N && c < 3 + 6 * L) {
+    if (c < 3) {
+      v = x[m * 3 + c] * scale;
+    } else {
+      const int k = (c - 3) / 6, rem = (c - 3) - 6 * k, j = rem % 3;
+      const float y = x[m * 3 + j] * scale * (float)(1 << k);
+      v = rem < 3 ? sinf(y) : cosf(y);
+    }
+  }
+  e16[idx] = __float2half_rn(v * ce::kB2);
+  eb16[idx] = __float2bfloat16_rn(v * ce::kB2);
+}
+
+// delta of the last hidden layer: D16[m, c] = fp16((1 - 2^-A16[m, c]) * w[c]),  w = first row of the last weight
+static __global__ void sdf_delta_last_kernel(const __half* __restrict__ a16, const float* __restrict__ wrow,
+                                             long long Npad, int width, __half* __restrict__ d16,
+                                             __nv_bfloat16* __restrict__ db16) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 columns
+  if (idx >= Npad * 32) return;
+  const int c = (int)(idx & 31) * 8;
+  const uint4 u = *reinterpret_cast<const uint4*>(a16 + idx * 8);
+  float a8[8];
+  ce::unpack_h8(u, a8);
+  uint32_t p[4], pb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float d0 = c + 2 * i < width ? (1.0f - exp2f(-a8[2 * i])) * wrow[c + 2 * i] : 0.0f;
+    const float d1 = c + 2 * i + 1 < width ? (1.0f - exp2f(-a8[2 * i + 1])) * wrow[c + 2 * i + 1] : 0.0f;
+    p[i] = ce::pack_h2(d0, d1);
+    pb[i] = ce::pack_b2(d0, d1);
+  }
+  *reinterpret_cast<uint4*>(d16 + idx * 8) = make_uint4(p[0], p[1], p[2], p[3]);
+  *reinterpret_cast<uint4*>(db16 + idx * 8) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+}
+
+// Q16_0[m, c] = bf16((J_e n-bar)[c]): forward-mode product with the embedding Jacobian (pointwise.cuh embed_jvp_kernel)
+static __global__ void sdf_qbar0_kernel(const float* __restrict__ x, long long N, long long Npad, int L, float scale,
+                                        const float* __restrict__ nbar, __nv_bfloat16* __restrict__ q16) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Npad * 64) return;
+  const long long m = idx >> 6;
+  const int c = (int)(idx & 63);
+  float v = 0.0f;
+  if (m < N && c < 3 + 6 * L) {
+    if (c < 3) {
+      v = nbar[m * 3 + c];
+    } else {
+      const int k = (c - 3) / 6, rem = (c - 3) - 6 * k, j = rem % 3;
+      const float f = (float)(1 << k);
+      const float y = x[m * 3 + j] * scale * f;
+      v = (rem < 3 ? f * cosf(y) : -f * sinf(y)) * nbar[m * 3 + j];
+    }
+  }
+  q16[idx] = __float2bfloat16_rn(v);
+}
+
+// dst[m, c] = bf16(src[m * lds + c] * mul) for c < w (zero beyond, zero rows beyond N; src null: zeros), c < ldd
+static __global__ void rows_to_bf16_kernel(const float* __restrict__ src, int lds, int w, float mul, long long N,
+                                           long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Npad * ldd) return;
+  const long long m = idx / ldd;
+  const int c = (int)(idx - m * ldd);
+  dst[idx] = __float2bfloat16_rn((src && m < N && c < w) ? src[m * lds + c] * mul : 0.0f);
+}
+static __global__ void rows_to_fp16_kernel(const float* __restrict__ src, int lds, int w, float mul, long long N,
+                                           long long Npad, __half* __restrict__ dst, int ldd) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Npad * ldd) return;
+  const long long m = idx / ldd;
+  const int c = (int)(idx - m * ldd);
+  dst[idx] = __float2half_rn((src && m < N && c < w) ? src[m * lds + c] * mul : 0.0f);
+}
+// dst[m, 0] = bf16(1) for m < N, everything else zero: the "ones" operand that turns a column sum into a GEMM row
+static __global__ void ones_col_bf16_kernel(long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Npad * ldd) return;
+  const long long m = idx / ldd;
+  dst[idx] = __float2bfloat16_rn((m < N && idx - m * ldd == 0) ? 1.0f : 0.0f);
+}
+template <class K, class... A>
+static inline int launch1d(K kern, long long total, cudaStream_t st, A... args) {
+  if (total <= 0) return 0;
+  VDN_LAUNCH(kern, (unsigned)((total + 255) / 256), 256, 0, st, args...);
+  return (int)cudaGetLastError();
+}
+
+// ---- layouts ----------------------------------------------------------------------------------------------
+struct SdfChainBufs {
+  long long Npad;
+  __half* E16; __nv_bfloat16* EB16;
+  __half* A16[VDN_MAX_LAYERS];
+  __nv_bfloat16* AB16[VDN_MAX_LAYERS];
+  __half* D16L;
+  __nv_bfloat16* DB16[VDN_MAX_LAYERS];
+  float* DE0; float* DES;
+  __nv_bfloat16* Q16[VDN_MAX_LAYERS + 1];
+  __nv_bfloat16* ZG16[VDN_MAX_LAYERS];
+  __nv_bfloat16* ZB16[VDN_MAX_LAYERS];
+  __nv_bfloat16* FB16; __nv_bfloat16* SB; __nv_bfloat16* ONESB;
+  float* EB; float* ES;
+};
+static inline long long sdf_chain_blob_floats(int L, long long N) { return pad128(N) * (64 + (long long)(L - 1) * 256); }
+static inline long long sdf_chain_blobg_floats(int L, long long N) { return pad128(N) * (128 + (long long)(L - 1) * 128 + 96); }
+static inline long long sdf_chain_ws_floats(int L, long long N) {
+  return pad128(N) * (32 + 3LL * (L - 1) * 128 + 128 + 32 + 32 + 96);
+}
+static inline void sdf_chain_carve(int L, long long N, float* blob, float* blobg, float* ws, SdfChainBufs* b) {
+  const long long Np = pad128(N);
+  b->Npad = Np;
+  if (blob) {
+    b->E16 = reinterpret_cast<__half*>(blob);
+    b->EB16 = reinterpret_cast<__nv_bfloat16*>(blob + Np * 32);
+    for (int l = 0; l < L - 1; ++l) {
+      b->A16[l] = reinterpret_cast<__half*>(blob + Np * 64 + (long long)l * Np * 256);
+      b->AB16[l] = reinterpret_cast<__nv_bfloat16*>(blob + Np * 64 + (long long)l * Np * 256 + Np * 128);
+    }
+  }
+  if (blobg) {
+    b->D16L = reinterpret_cast<__half*>(blobg);
+    for (int l = 0; l < L - 1; ++l) b->DB16[l] = reinterpret_cast<__nv_bfloat16*>(blobg + Np * 128 + (long long)l * Np * 128);
+    b->DE0 = blobg + Np * 128 + (long long)(L - 1) * Np * 128;
+    b->DES = b->DE0 + Np * 48;
+  }
+  if (ws) {
+    float* p = ws;
+    b->Q16[0] = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 32;
+    for (int l = 1; l <= L - 1; ++l) { b->Q16[l] = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128; }
+    for (int l = 0; l < L - 1; ++l) { b->ZG16[l] = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128; }
+    for (int l = 0; l < L - 1; ++l) { b->ZB16[l] = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128; }
+    b->FB16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128;
+    b->SB = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 32;
+    b->ONESB = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 32;
+    b->EB = p; p += Np * 48;
+    b->ES = p;
+  }
+}
+
+// Shape of the SDF net as the chains need it (taken from SdfCfg by the caller).
+struct SdfShape {
+  int L, skip, d_e, multires;
+  float scale;
+  const MlpLayout* ly;
+};
+static inline float sdf_dsc(const SdfShape& s, int l) { return l == s.skip ? kInvSqrt2 : 1.0f; }
+
+// ---- training forward: E16 -> [A16_l] -> sdf, feature -------------------------------------------------------
+static inline int sdf_chain_forward(const SdfShape& s, const float* packed, const float* x, long long N, float* sdf, int lds,
+                                    float* feat, int ldf, float out_mul, int save, const SdfChainBufs& b, cudaStream_t st) {
+  const MlpLayout& ly = *s.ly;
+  const int L = s.L;
+  int e = launch1d(sdf_embed16_kernel, b.Npad * 64, st, x, N, b.Npad, s.multires, s.scale, b.E16, b.EB16);
+  if (e) return e;
+  ce::Args a;
+  ce::init_args(&a);
+  a.N = N; a.packed = packed;
+  a.a0 = b.E16; a.a0_ld = 64; a.a0_w = 64;
+  int P = 0;
+  for (int l = 0; l < L - 1; ++l) {
+    ce::Phase& p = a.ph[P++];
+    p = ce::make_phase();
+    ce::set_mma(&p, ly.off_ih[l], ly.out_ld[l], 0, 0, ly.out_dim[l], ly.in_dim[l]);
+    p.op = ce::OP_SOFTPLUS; p.width = ly.out_dim[l]; p.dsc = sdf_dsc(s, l);
+    p.bias_off = ly.off_b[l]; p.bias_mul = ce::kB2;
+    p.a_out = 1; p.a_wr = 256;
+    if (save) {
+      p.o16a = b.A16[l]; p.ldo16a = 256; p.o16a_bf16 = 0;
+      p.o16c = b.AB16[l]; p.ldo16c = 256; p.o16c_bf16 = 1;
+    }
+    if (l + 1 == s.skip) { p.tail = b.E16; p.ldt = 64; p.tail_w = s.d_e; p.tail_mul = 1.0f; p.tail_bf16 = 0; }
+  }
+  const int lo = L - 1;
+  if (sdf) {   // image position out_dim-1 holds output 0 (orot = 1): one N = 16 MMA
+    ce::Phase& p = a.ph[P++];
+    p = ce::make_phase();
+    ce::set_mma(&p, ly.off_ih[lo], ly.out_ld[lo], ly.out_dim[lo] - 1, 0, 16, ly.in_dim[lo]);
+    p.op = ce::OP_OUT32; p.width = 1; p.dsc = sdf_dsc(s, lo) * ce::kInvB2; p.bias_off = ly.off_b[lo];
+    p.o32 = sdf; p.ldo32 = lds; p.o32_c0 = 0; p.o32_w = 1; p.o32_mul = out_mul / s.scale;
+  }
+  if (feat) {
+    ce::Phase& p = a.ph[P++];
+    p = ce::make_phase();
+    ce::set_mma(&p, ly.off_ih[lo], ly.out_ld[lo], 0, 0, ly.out_dim[lo] - 1, ly.in_dim[lo]);
+    p.op = ce::OP_OUT32; p.width = ly.out_dim[lo] - 1; p.dsc = sdf_dsc(s, lo) * ce::kInvB2; p.bias_off = ly.off_b[lo] + 1;
+    p.o32 = feat; p.ldo32 = ldf; p.o32_c0 = 0; p.o32_w = ly.out_dim[lo] - 1;
+  }
+  a.P = P;
+  return ce::launch(a, st, PROF_CHAIN_TRAIN);
+}
+
+// ---- analytic normals: D16_{L-2} -> ... -> DE0 (+ DES), then J_e^T ----------------------------------------------
+static inline int sdf_chain_normals(const SdfShape& s, const float* packed, const float* x, long long N,
+                                    const SdfChainBufs& b, float* normals, cudaStream_t st) {
+  const MlpLayout& ly = *s.ly;
+  const int L = s.L;
+  int e = launch1d(sdf_delta_last_kernel, b.Npad * 32, st, (const __half*)b.A16[L - 2], packed + ly.off_w[L - 1], b.Npad,
+                   ly.out_dim[L - 2], b.D16L, b.DB16[L - 2]);
+  if (e) return e;
+  ce::Args a;
+  ce::init_args(&a);
+  a.N = N; a.packed = packed;
+  a.a0 = b.D16L; a.a0_ld = 256; a.a0_w = 256;
+  int P = 0;
+  for (int l = L - 2; l >= 0; --l) {     // a_l = delta_l W_l ; epilogue -> delta_{l-1}
+    ce::Phase& p = a.ph[P++];
+    p = ce::make_phase();
+    ce::set_mma(&p, ly.off_iht[l], ly.in_ld[l], 0, 0, ly.in_dim[l], ly.out_dim[l]);
+    p.dsc = sdf_dsc(s, l);
+    if (l > 0) {
+      p.op = ce::OP_NSTEP; p.width = ly.out_dim[l - 1];
+      p.aux0 = b.A16[l - 1]; p.ld0 = 256;
+      p.a_out = 1; p.a_wr = 256;
+      p.o16a = b.DB16[l - 1]; p.ldo16a = 256; p.o16a_bf16 = 1;
+      if (l == s.skip) { p.o32 = b.DES; p.ldo32 = 48; p.o32_c0 = ly.out_dim[l - 1]; p.o32_w = s.d_e; }
+    } else {
+      p.op = ce::OP_OUT32; p.width = s.d_e;
+      p.o32 = b.DE0; p.ldo32 = 48; p.o32_c0 = 0; p.o32_w = s.d_e;
+    }
+  }
+  a.P = P;
+  e = ce::launch(a, st, PROF_CHAIN_TRAIN);
+  if (e) return e;
+  const long long tot = N * 3;
+  VDN_LAUNCH(embed_vjp_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, x, 3, N, 3, s.multires, s.scale, b.DE0, 48,
+             s.skip >= 0 ? b.DES : nullptr, 48, 1.0f, 1.0f, normals, 3, 0);
+  return (int)cudaGetLastError();
+}
+
+// ---- backward ------------------------------------------------------------------------------------------------
+static inline int sdf_chain_backward(const SdfShape& s, const float* packed, const float* x, long long N,
+                                     const SdfChainBufs& b, const float* d_sdf, int lds, const float* d_feat, int ldf,
+                                     const float* d_normals, float* dpacked, float* d_x, cudaStream_t st) {
+  const MlpLayout& ly = *s.ly;
+  const int L = s.L;
+  const bool have_n = d_normals != nullptr;
+  int e;
+  // ---- phase 1: backward of the normals pass, l = 0 .. L-2 ----
+  if (have_n) {
+    e = launch1d(sdf_qbar0_kernel, b.Npad * 64, st, x, N, b.Npad, s.multires, s.scale, d_normals, b.Q16[0]);
+    if (e) return e;
+    ce::Args a;
+    ce::init_args(&a);
+    a.N = N; a.packed = packed;
+    a.a0 = b.Q16[0]; a.a0_ld = 64; a.a0_w = 64;
+    int P = 0;
+    for (int l = 0; l <= L - 2; ++l) {    // delta-bar_l = q-bar_l W_l^T ; epilogue -> q-bar_{l+1}, z-bar^g_l
+      ce::Phase& p = a.ph[P++];
+      p = ce::make_phase();
+      ce::set_mma_bf16(&p, ly.off_ib[l], ly.off_ib2[l], ly.out_ld[l], 0, 0, ly.out_dim[l], ly.in_dim[l]);
+      p.op = ce::OP_P1STEP; p.width = ly.out_dim[l];
+      p.aux0 = b.AB16[l]; p.ld0 = 256; p.aux0_bf16 = 1; p.aux1 = b.DB16[l]; p.ld1 = 256; p.aux1_bf16 = 1;
+      p.a_mul = sdf_dsc(s, l + 1);
+      p.a_out = l < L - 2 ? 1 : 0; p.a_wr = 256;
+      p.o16a = b.Q16[l + 1]; p.ldo16a = 256; p.o16a_bf16 = 1;
+      p.o16b = b.ZG16[l]; p.ldo16b = 256;
+      if (l + 1 == s.skip) { p.tail = b.Q16[0]; p.ldt = 64; p.tail_w = s.d_e; p.tail_mul = kInvSqrt2; p.tail_bf16 = 1; }
+    }
+    a.P = P;
+    e = ce::launch(a, st, PROF_CHAIN_TRAIN);
+    if (e) return e;
+  }
+  // ---- phase 2: ordinary backward with the injected cotangents, l = L-1 .. 1 (.. 0 for the point gradient) ----
+  const int lo = L - 1;
+  const int nf = ly.out_dim[lo] - 1;
+  e = launch1d(rows_to_bf16_kernel, b.Npad * 256, st, d_feat, ldf, nf, 1.0f, N, b.Npad, b.FB16, 256);
+  if (e) return e;
+  e = launch1d(rows_to_bf16_kernel, b.Npad * 64, st, d_sdf, lds, 1, ce::kInvB2 / s.scale, N, b.Npad, b.SB, 64);
+  if (e) return e;
+  if (have_n) {
+    e = launch1d(ones_col_bf16_kernel, b.Npad * 64, st, N, b.Npad, b.ONESB, 64);
+    if (e) return e;
+  }
+  {
+    ce::Args a;
+    ce::init_args(&a);
+    a.N = N; a.packed = packed;
+    a.a0 = b.FB16; a.a0_ld = 256; a.a0_w = 256;
+    a.row_off[0] = ly.off_w[lo]; a.row_len[0] = ly.in_dim[lo];
+    int P = 0;
+    for (int l = lo; l >= 1; --l) {      // u-bar = z-bar_l W_l ; epilogue -> z-bar_{l-1}
+      ce::Phase& p = a.ph[P++];
+      p = ce::make_phase();
+      const int k = l == lo ? nf : ly.out_dim[l];
+      ce::set_mma_bf16(&p, ly.off_ibt[l], ly.off_ibt2[l], ly.in_ld[l], 0, 0, ly.in_dim[l], k);
+      p.op = ce::OP_P2STEP; p.width = ly.out_dim[l - 1]; p.dsc = sdf_dsc(s, l);
+      if (l == lo && d_sdf) { p.r1 = d_sdf; p.r1_stride = lds; p.r1_mul = sdf_dsc(s, l) / s.scale; p.r1_row = 0; }
+      p.aux0 = b.AB16[l - 1]; p.ld0 = 256; p.aux0_bf16 = 1;
+      if (have_n) { p.aux1 = b.ZG16[l - 1]; p.ld1 = 256; p.aux1_bf16 = 1; }
+      p.a_out = (l > 1 || d_x) ? 1 : 0; p.a_wr = 256;
+      p.o16a = b.ZB16[l - 1]; p.ldo16a = 256; p.o16a_bf16 = 1; p.o16a_mul = sdf_dsc(s, l - 1) * ce::kInvB2;
+      if (l == s.skip && d_x) { p.o32 = b.ES; p.ldo32 = 48; p.o32_c0 = ly.out_dim[l - 1]; p.o32_w = s.d_e; }
+    }
+    if (d_x) {
+      ce::Phase& p = a.ph[P++];
+      p = ce::make_phase();
+      ce::set_mma_bf16(&p, ly.off_ibt[0], ly.off_ibt2[0], ly.in_ld[0], 0, 0, ly.in_dim[0], ly.out_dim[0]);
+      p.op = ce::OP_OUT32; p.width = s.d_e; p.dsc = sdf_dsc(s, 0);
+      p.o32 = b.EB; p.ldo32 = 48; p.o32_c0 = 0; p.o32_w = s.d_e;
+    }
+    a.P = P;
+    e = ce::launch(a, st, PROF_CHAIN_TRAIN);
+    if (e) return e;
+  }
+  // ---- weight and bias gradients: one grouped launch ----
+  {
+    wg::Builder w(N, dpacked);
+    int mE = w.add_map(b.EB16, 64, 64), mA[VDN_MAX_LAYERS], mD[VDN_MAX_LAYERS], mQ[VDN_MAX_LAYERS + 1], mZ[VDN_MAX_LAYERS];
+    for (int l = 0; l < L - 1; ++l) {
+      mA[l] = w.add_map(b.AB16[l], 256, 256);
+      mZ[l] = w.add_map(b.ZB16[l], 256, 256);
+      if (have_n) mD[l] = w.add_map(b.DB16[l], 256, 256);
+    }
+    if (have_n) {
+      mQ[0] = w.add_map(b.Q16[0], 64, 64);
+      for (int l = 1; l <= L - 1; ++l) mQ[l] = w.add_map(b.Q16[l], 256, 256);
+    }
+    const int mF = w.add_map(b.FB16, 256, 256), mS = w.add_map(b.SB, 64, 64);
+    const int mO = have_n ? w.add_map(b.ONESB, 64, 64) : 0;
+    for (int l = 0; l < L - 1; ++l) {     // W-bar_l = [z-bar_l ; delta_l]^T [u_l ; q-bar_l]
+      wg::Job* j = w.add_job(ly.out_dim[l], ly.in_dim[l], ly.off_w[l], ly.in_ld[l], 1.0f, ly.off_b[l],
+                             ce::kB2 / sdf_dsc(s, l));
+      wg::Builder::add_seg(j, mZ[l], 0, 1, l == 0 ? mE : mA[l - 1], 0, 1);
+      if (have_n) wg::Builder::add_seg(j, mD[l], 0, 1, mQ[l], 0, 1);
+    }
+    {   // last layer, feature rows 1 .. nf
+      wg::Job* j = w.add_job(nf, ly.in_dim[lo], ly.off_w[lo] + ly.in_ld[lo], ly.in_ld[lo], sdf_dsc(s, lo) * ce::kInvB2,
+                             ly.off_b[lo] + 1, 1.0f);
+      wg::Builder::add_seg(j, mF, 0, 1, mA[lo - 1], 0, 1);
+    }
+    if (d_sdf || have_n) {   // last layer, row 0: sdf cotangent, and the column sum of q-bar_{L-1} (a_{L-1} IS that row)
+      wg::Job* j = w.add_job(1, ly.in_dim[lo], ly.off_w[lo], ly.in_ld[lo], 1.0f, ly.off_b[lo], ce::kB2);
+      wg::Builder::add_seg(j, mS, 0, 1, mA[lo - 1], 0, 1);
+      if (have_n) wg::Builder::add_seg(j, mO, 0, 1, mQ[lo], 0, 1);
+    }
+    e = w.launch(st, PROF_WGRAD16);
+    if (e) return e;
+  }
+  // ---- gradient w.r.t. the points (learnable poses) ----
+  if (d_x) {
+    const long long tot = N * 3;
+    VDN_LAUNCH(embed_vjp_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, x, 3, N, 3, s.multires, s.scale, b.EB, 48,
+               s.skip >= 0 ? b.ES : nullptr, 48, 1.0f, s.scale, d_x, 3, 0);
+    if (have_n) {
+      VDN_LAUNCH(embed_second_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, x, 3, N, 3, s.multires, s.scale, d_normals, 3,
+                 b.DE0, 48, s.skip >= 0 ? b.DES : nullptr, 48, s.scale, d_x, 3);
+    }
+    e = (int)cudaGetLastError();
+    if (e) return e;
+  }
+  return 0;
+}
+
+}  // namespace vdn

@@ -14,6 +14,7 @@
 // in the consumer's operand prologue), plus G_l = d sdf / d(input of layer l) from the normals pass.
 #include "gemm_tn_tc.cuh"
 #include "sdf_chain_tc.cuh"
+#include "sdf_chains.cuh"
 #include "pointwise.cuh"
 #include "../../include/vdn_b200.h"
 
@@ -47,6 +48,20 @@ static int parse_sdf_cfg(const int* cfg, float scale, SdfCfg* c) {
   c->ldH = round_up(c->d_hidden, 16);
   return make_layout(c->L, in_dims, out_dims, &c->ly);
 }
+
+// Output rotation of the fp16 weight images (mlp_layout.cuh): the stacked [sdf ; feature] last layer presents its
+// features first when the feature count is a multiple of 8 (so that the scalar row starts an 8-row swizzle atom).
+static int sdf_orot_last(const SdfCfg& c) { return (c.d_out > 1 && ((c.d_out - 1) & 7) == 0) ? 1 : 0; }
+
+// The fused training chains (sdf_chains.cuh) cover the shipped shape: 3-D points, 256-wide hidden layers, an embedding
+// of at most 64 columns, 256 feature outputs, one optional skip connection; anything else runs layer-wise.
+static bool sdf_chain_ok(const SdfCfg& c) {
+  if (g_mode != 1 || !g_chain) return false;
+  if (c.d_in != 3 || c.d_hidden != 256 || c.d_e > 48 || c.d_out != 257 || c.L < 3 || c.L > 12) return false;
+  if (c.skip >= 0 && c.ly.out_dim[c.skip - 1] + c.d_e != 256) return false;
+  return wg::encode_fn() != nullptr;
+}
+static SdfShape sdf_shape(const SdfCfg& c) { return SdfShape{c.L, c.skip, c.d_e, c.multires, c.scale, &c.ly}; }
 
 struct SdfBlob {
   float* E;
@@ -132,13 +147,23 @@ extern "C" int vdn_sdf_layer_dims(const int* cfg, int* in_dims, int* out_dims) {
 extern "C" long long vdn_sdf_blob_floats(const int* cfg, long long N, int save) {
   SdfCfg c;
   if (parse_sdf_cfg(cfg, 1.0f, &c)) return -1;
-  return sdf_blob_floats(c, N, save);
+  const long long a = sdf_blob_floats(c, N, save), b = sdf_chain_blob_floats(c.L, N);   // either path fits
+  return a > b ? a : b;
+}
+
+extern "C" int vdn_sdf_layer_orot(const int* cfg, int* orot) {
+  SdfCfg c;
+  if (parse_sdf_cfg(cfg, 1.0f, &c)) return -1;
+  for (int l = 0; l < c.L; ++l) orot[l] = 0;
+  orot[c.L - 1] = sdf_orot_last(c);
+  return c.L;
 }
 
 extern "C" long long vdn_sdf_blobg_floats(const int* cfg, long long N) {
   SdfCfg c;
   if (parse_sdf_cfg(cfg, 1.0f, &c)) return -1;
-  return sdf_blobg_floats(c, N);
+  const long long a = sdf_blobg_floats(c, N), b = sdf_chain_blobg_floats(c.L, N);
+  return a > b ? a : b;
 }
 
 static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x, long long N, float* sdf, int lds,
@@ -147,8 +172,13 @@ static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x
   if (N > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   if (g_mode == 1 && !feat && !save) {   // tensor-core mode, value only: fused chain kernel
     int r = launch_sdf_chain(c.ly, c.d_in, c.multires, c.d_hidden, c.skip, c.scale, packed, x, nullptr, nullptr, nullptr,
-                             0, 0, 0, N, sdf, lds, out_mul, st);
+                             0, 0, 0, N, sdf, lds, out_mul, st, sdf_orot_last(c));
     if (r >= 0) return r;
+  }
+  if (sdf_chain_ok(c)) {                 // training / feature forward on the chain engine, 16-bit saved activations
+    SdfChainBufs b;
+    sdf_chain_carve(c.L, N, blob, nullptr, nullptr, &b);
+    return sdf_chain_forward(sdf_shape(c), packed, x, N, sdf, lds, feat, ldf, out_mul, save, b, st);
   }
   SdfBlob b;
   carve_blob(c, N, save, blob, &b);
@@ -161,7 +191,7 @@ static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x
     float* zs[VDN_MAX_LAYERS];
     for (int l = 0; l < c.L - 1; ++l) zs[l] = (save || l == c.L - 2) ? b.Z[l] : nullptr;
     int r = launch_sdf_chain(c.ly, c.d_in, c.multires, c.d_hidden, c.skip, c.scale, packed, x, nullptr, nullptr, nullptr,
-                             0, 0, 0, N, nullptr, 0, 1.0f, st, zs, save ? b.U : nullptr, c.ldH);
+                             0, 0, 0, N, nullptr, 0, 1.0f, st, sdf_orot_last(c), zs, save ? b.U : nullptr, c.ldH);
     if (r > 0) return r;
     if (r == 0) l0 = c.L - 1;
   }
@@ -223,7 +253,7 @@ extern "C" int vdn_grid_sdf(const int* cfg, float scale, const float* packed, co
   long long count = (long long)(i1 - i0) * ny * nz;
   if (g_mode == 1) {   // tensor-core mode: lattice points are generated inside the fused chain kernel
     int r = launch_sdf_chain(c.ly, c.d_in, c.multires, c.d_hidden, c.skip, c.scale, packed, nullptr, xs, ys, zs, ny, nz,
-                             i0, count, u_slab, 1, out_mul, st);
+                             i0, count, u_slab, 1, out_mul, st, sdf_orot_last(c));
     if (r >= 0) return r;
   }
   VDN_LAUNCH(grid_points_kernel, (unsigned)((count + 255) / 256), 256, 0, st, xs, ys, zs, i0, ny, nz, count, pts);
@@ -238,6 +268,11 @@ extern "C" int vdn_sdf_normals(const int* cfg, float scale, const float* packed,
   if (parse_sdf_cfg(cfg, scale, &c)) return (int)cudaErrorInvalidValue;
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (sdf_chain_ok(c)) {
+    SdfChainBufs cb;
+    sdf_chain_carve(c.L, N, const_cast<float*>(blob), blobg, nullptr, &cb);
+    return sdf_chain_normals(sdf_shape(c), packed, x, N, cb, normals, st);
+  }
   SdfBlob b;
   carve_blob(c, N, 1, const_cast<float*>(blob), &b);
   SdfBlobG g;
@@ -274,8 +309,10 @@ extern "C" long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N) {
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
-  return 3 * N * c.ldH + (long long)(c.L - 1) * N * c.ldH + N * c.ly.out_ld[c.L - 1] + 3 * N * c.ldE +
-         S * maxw + 256 * maxo + 64;
+  const long long a = 3 * N * c.ldH + (long long)(c.L - 1) * N * c.ldH + N * c.ly.out_ld[c.L - 1] + 3 * N * c.ldE +
+                      S * maxw + 256 * maxo + 64;
+  const long long b = sdf_chain_ws_floats(c.L, N);
+  return a > b ? a : b;
 }
 
 extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed, const float* x, long long N,
@@ -295,6 +332,11 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
   if (blobg) carve_blobg(c, N, const_cast<float*>(blobg), &g);
   const bool have_n = (d_normals != nullptr);
   if (have_n && !blobg) return (int)cudaErrorInvalidValue;
+  if (sdf_chain_ok(c)) {
+    SdfChainBufs cb;
+    sdf_chain_carve(c.L, N, const_cast<float*>(blob), const_cast<float*>(blobg), ws, &cb);
+    return sdf_chain_backward(sdf_shape(c), packed, x, N, cb, d_sdf, lds, d_feat, ldf, d_normals, dpacked, d_x, st);
+  }
 
   // workspace carve
   float* Q[2] = {ws, ws + N * c.ldH};
@@ -387,8 +429,8 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
                                                                    kInvSqrt2, c.scale, d_x, c.d_in, 0);
     if (have_n) {
       VDN_LAUNCH(embed_second_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, x, c.d_in, N, c.d_in, c.multires, c.scale,
-                                                                        d_normals, c.d_in, g.DE, c.ldE, c.scale,
-                                                                        d_x, c.d_in);
+                                                                        d_normals, c.d_in, g.DE, c.ldE, nullptr, 0,
+                                                                        c.scale, d_x, c.d_in);
     }
     e = (int)cudaGetLastError();
     if (e) return e;

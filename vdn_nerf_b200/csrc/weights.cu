@@ -6,6 +6,7 @@
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "../../include/vdn_b200.h"
 
 namespace vdn {
@@ -15,8 +16,8 @@ struct PackLayer {
   const float* g[2];
   const float* b[2];
   int rows[2];
-  int in_dim, in_ld, out_dim, out_ld, rot;
-  long long off_w, off_wt, off_b, off_iw, off_iwt, off_ih;
+  int in_dim, in_ld, out_dim, out_ld, rot, orot;
+  long long off_w, off_wt, off_b, off_iw, off_iwt, off_ih, off_iht, off_ib, off_ib2, off_ibt, off_ibt2;
 };
 struct PackArgs {
   int L;
@@ -61,6 +62,13 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
   float* IW = packed + P.off_iw;
   float* IWT = packed + P.off_iwt;
   __half* IH = reinterpret_cast<__half*>(packed + P.off_ih);
+  __half* IHT = reinterpret_cast<__half*>(packed + P.off_iht);
+  __nv_bfloat16* IB = reinterpret_cast<__nv_bfloat16*>(packed + P.off_ib);
+  __nv_bfloat16* IB2 = reinterpret_cast<__nv_bfloat16*>(packed + P.off_ib2);
+  __nv_bfloat16* IBT = reinterpret_cast<__nv_bfloat16*>(packed + P.off_ibt);
+  __nv_bfloat16* IBT2 = reinterpret_cast<__nv_bfloat16*>(packed + P.off_ibt2);
+  int rj = r - P.orot;                      // position of output r in the (rotated) fp16 images
+  if (rj < 0) rj += P.out_dim;
   for (int k = lane; k < P.in_ld; k += 32) {
     float w = 0.0f;
     if (k < P.in_dim) {
@@ -74,7 +82,15 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
       const float t = round_tf32(w);
       IW[(long long)(k >> 5) * P.out_ld * 32 + (tc::sw128_offset((uint32_t)r, (uint32_t)(k & 31)) >> 2)] = t;
       IWT[(long long)(r >> 5) * P.in_ld * 32 + (tc::sw128_offset((uint32_t)k, (uint32_t)(r & 31)) >> 2)] = t;
-      IH[(long long)(k >> 6) * P.out_ld * 64 + (tc::sw128_offset_h((uint32_t)r, (uint32_t)(k & 63)) >> 1)] = __float2half_rn(w);
+      const __half hw = __float2half_rn(w);
+      const long long i_w = (long long)(k >> 6) * P.out_ld * 64 + (tc::sw128_offset_h((uint32_t)rj, (uint32_t)(k & 63)) >> 1);
+      const long long i_t = (long long)(rj >> 6) * P.in_ld * 64 + (tc::sw128_offset_h((uint32_t)k, (uint32_t)(rj & 63)) >> 1);
+      IH[i_w] = hw;
+      IHT[i_t] = hw;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+      IB[i_w] = hi; IB2[i_w] = lo;
+      IBT[i_t] = hi; IBT2[i_t] = lo;
     }
   }
   if (lane == 0) B[r] = P.b[src] ? P.b[src][rr] : 0.0f;
@@ -146,7 +162,7 @@ extern "C" long long vdn_mlp_layout(int L, const int* in_dims, const int* out_di
 
 extern "C" int vdn_mlp_pack(int L, const int* in_dims, const int* out_dims, const float* const* v,
                             const float* const* g, const float* const* b, const int* rows, const int* rot,
-                            float* packed, void* stream) {
+                            const int* orot, float* packed, void* stream) {
   MlpLayout ly;
   if (make_layout(L, in_dims, out_dims, &ly)) return (int)cudaErrorInvalidValue;
   PackArgs a;
@@ -164,8 +180,11 @@ extern "C" int vdn_mlp_pack(int L, const int* in_dims, const int* out_dims, cons
     P.in_dim = ly.in_dim[l]; P.in_ld = ly.in_ld[l]; P.out_dim = ly.out_dim[l]; P.out_ld = ly.out_ld[l];
     P.rot = rot ? rot[l] : 0;
     if (P.rot < 0 || P.rot >= P.in_dim) return (int)cudaErrorInvalidValue;
+    P.orot = orot ? orot[l] : 0;
+    if (P.orot < 0 || P.orot >= P.out_dim) return (int)cudaErrorInvalidValue;
     P.off_w = ly.off_w[l]; P.off_wt = ly.off_wt[l]; P.off_b = ly.off_b[l];
-    P.off_iw = ly.off_iw[l]; P.off_iwt = ly.off_iwt[l]; P.off_ih = ly.off_ih[l];
+    P.off_iw = ly.off_iw[l]; P.off_iwt = ly.off_iwt[l]; P.off_ih = ly.off_ih[l]; P.off_iht = ly.off_iht[l];
+    P.off_ib = ly.off_ib[l]; P.off_ib2 = ly.off_ib2[l]; P.off_ibt = ly.off_ibt[l]; P.off_ibt2 = ly.off_ibt2[l];
   }
   a.row_start[L] = start;
   cudaStream_t st = (cudaStream_t)stream;

@@ -1,0 +1,322 @@
+// Grouped weight-gradient kernel of the fused chains (tensor-core mode): ONE launch accumulates the weight (and bias)
+// gradients of every layer of a network,
+//
+//     dW_l[out, in] += scale * sum_p  X_l[p, out] * Y_l[p, in]         (W-bar += z-bar^T u, delta^T q-bar)
+//
+// from the 16-bit operand tensors the chain kernels (chain_engine.cuh) left in HBM: X = a cotangent (bf16) or the
+// normals-pass delta (fp16), Y = the layer input (fp16) or a phase-1 cotangent (bf16), both row-major [points, ld].
+// A "job" is one (layer, output-row block) with up to two (X, Y) segments that share an accumulator
+// (W-bar_l = [z-bar ; delta]^T [u ; q-bar]); the batch is split over the CTAs so that (jobs x splits) fills one wave of
+// the 148 SMs, every CTA streaming its points exactly once:
+//   * operands arrive by TMA TENSOR MAPS (cp.async.bulk.tensor.2d, UTMALDG; 64 x 64 boxes, SWIZZLE_128B, rows beyond N
+//     zero-filled by the TMA unit) - a 64-point stage is 8 boxes = 64 KB, three stages in flight;
+//   * the reduction runs over the points, so both operands are MN-major for tcgen05.mma kind::f16 (fp16 / bf16 mixed
+//     per instruction descriptor), the box image is exactly the canonical MN-major SWIZZLE_128B layout;
+//   * a 256 x 256 fp32 accumulator (two 128-lane halves x 256 TMEM columns) lives in tensor memory for the whole split
+//     and is added to the packed gradient with red.global.add.v4.f32 (no partial slabs, no reduce launch);
+//   * four warps sum the columns of X from the staged tiles for the bias gradient while the tensor pipe works.
+// The kernel is bandwidth bound by construction (128 FLOP per operand byte): the figure of merit is HBM GB/s.
+#pragma once
+#include "chain_engine.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace vdn {
+namespace wg {
+
+constexpr int MAX_MAPS = 56;
+constexpr int MAX_JOBS = 40;
+constexpr int MAX_UNITS = 160;
+constexpr int STAGES = 3;
+constexpr uint32_t STAGE_BYTES = 65536;
+constexpr int THREADS = 192;      // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2-5: bias sums + flush
+constexpr size_t SMEM = STAGES * STAGE_BYTES + 1024;
+
+struct Job {
+  int nseg;                     // 1 or 2 segments accumulated into the same tile
+  int xmap[2], ymap[2];         // tensor-map indices
+  int xcol[2], ycol[2];         // first column (element) inside the tensor
+  int xbf16[2], ybf16[2];
+  int m_tiles;                  // 128-row halves of the output block (1 or 2)
+  int n_mma;                    // MMA N (multiple of 16, <= 256)
+  int rows, cols;               // valid extent of the output block
+  long long dw_off;             // float offset of dW[row 0 of the block][col 0] in the packed gradient
+  int dw_ld;
+  float scale;
+  long long db_off;             // float offset of the bias gradient of row 0 of the block, -1: none
+  float db_scale;
+};
+struct Unit { int job, c0, c1; };   // 64-point chunks [c0, c1)
+
+struct alignas(64) Args {
+  CUtensorMap maps[MAX_MAPS];
+  Job jobs[MAX_JOBS];
+  Unit units[MAX_UNITS];
+  float* dpacked;
+};
+
+__device__ __forceinline__ uint32_t idesc_mn(uint32_t M, uint32_t N, int a_bf16, int b_bf16) {
+  return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
+}
+// MN-major SWIZZLE_128B operand: 64-element (128-byte) chunks of M/N lbo bytes apart, 8-row K groups 1024 bytes apart
+__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tm), "r"(x), "r"(y), "r"(bar)
+               : "memory");
+}
+
+static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full[STAGES], empty[STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const Unit un = a.units[blockIdx.x];
+  const Job& jb = a.jobs[un.job];
+  const int nchunks = un.c1 - un.c0;
+  const int x_boxes = jb.m_tiles * 2, y_boxes = (jb.n_mma + 63) >> 6;
+  const int nit = nchunks * jb.nseg;           // stages to process: chunk-major, segment-minor
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1 + 4); }
+    mbar_init(smem_u32(&acc_full), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  bool ok = true;
+
+  if (tid == 0) {
+    // ================= TMA producer =================
+    const uint32_t bytes = (uint32_t)(x_boxes + y_boxes) * 8192u;
+    for (int it = 0; it < nit && ok; ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      const int seg = it % jb.nseg, chunk = un.c0 + it / jb.nseg;
+      ok = mbar_wait_backoff(smem_u32(&empty[s]), ph ^ 1, 64);
+      const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES, bar = smem_u32(&full[s]);
+      mbar_arrive_expect_tx(bar, bytes);
+      const CUtensorMap* xm = &a.maps[jb.xmap[seg]];
+      const CUtensorMap* ym = &a.maps[jb.ymap[seg]];
+      for (int b = 0; b < x_boxes; ++b) tma_load_2d(base + (uint32_t)b * 8192u, xm, jb.xcol[seg] + 64 * b, chunk * 64, bar);
+      for (int b = 0; b < y_boxes; ++b) tma_load_2d(base + 32768u + (uint32_t)b * 8192u, ym, jb.ycol[seg] + 64 * b, chunk * 64, bar);
+    }
+  } else if (tid == 32) {
+    // ================= MMA issuer =================
+    for (int it = 0; it < nit && ok; ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      const int seg = it % jb.nseg;
+      ok = mbar_wait(smem_u32(&full[s]), ph);
+      tc_fence_after();
+      const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES;
+      const uint32_t idesc = idesc_mn(128, (uint32_t)jb.n_mma, jb.xbf16[seg], jb.ybf16[seg]);
+      for (int mh = 0; mh < jb.m_tiles; ++mh)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16_ss(tmem_base + (uint32_t)(mh * 256), desc_mn(base + (uint32_t)(mh * 16384 + ks * 2048), 8192u),
+                      desc_mn(base + 32768u + (uint32_t)(ks * 2048), 8192u), idesc, (it | ks) ? 1u : 0u);
+      umma_commit(smem_u32(&empty[s]));
+    }
+    umma_commit(smem_u32(&acc_full));
+  } else if (warp >= 2) {
+    // ================= bias sums (during the main loop), then the flush =================
+    const int t = tid - 64;                        // 0..127: features 2t, 2t+1 of the X tile
+    float bs0 = 0.f, bs1 = 0.f;
+    const bool want_b = jb.db_off >= 0;
+    for (int it = 0; it < nit && ok; ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      const int seg = it % jb.nseg;
+      // always wait for the stage before releasing it: the `empty` barrier counts one arrival per warp and stage use,
+      // a warp running ahead of the fill would arrive into the wrong barrier phase
+      ok = mbar_wait(smem_u32(&full[s]), ph);
+      if (ok && want_b && seg == 0 && 2 * t < jb.m_tiles * 128) {
+        const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES + (uint32_t)(t >> 5) * 8192u;
+        const uint32_t u = (uint32_t)(t & 31) >> 2, sub = (uint32_t)(t & 3) * 4u;
+        const bool bf = jb.xbf16[0] != 0;
+#pragma unroll 8
+        for (uint32_t k = 0; k < 64; ++k) {
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + k * 128u + ((u ^ (k & 7u)) << 4) + sub));
+          if (bf) {
+            bs0 += __uint_as_float(w << 16);
+            bs1 += __uint_as_float(w & 0xffff0000u);
+          } else {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+            bs0 += f.x; bs1 += f.y;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
+    }
+    if (ok) ok = mbar_wait(smem_u32(&acc_full), 0);
+    tc_fence_after();
+    if (ok && nit > 0) {
+      if (want_b) {
+        float* db = a.dpacked + jb.db_off;
+        if (2 * t < jb.rows) atomicAdd(db + 2 * t, bs0 * jb.db_scale);
+        if (2 * t + 1 < jb.rows) atomicAdd(db + 2 * t + 1, bs1 * jb.db_scale);
+      }
+      const int q = warp & 3;                      // TMEM lane quarter this warp may read
+      for (int mh = 0; mh < jb.m_tiles; ++mh) {
+        const int r = mh * 128 + q * 32 + lane;
+        float* drow = a.dpacked + jb.dw_off + (long long)r * jb.dw_ld;
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * 256);
+        for (int cc = 0; cc < jb.n_mma; cc += 32) {
+          if (cc >= jb.cols) break;
+          float v[32];
+          tmem_ld32(tb + (uint32_t)cc, v);          // columns beyond n_mma inside the 32 are stale: masked by `cols` below
+          tmem_ld_wait();
+          if (r < jb.rows) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int c = cc + j;
+              if (c + 3 < jb.cols) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c), "f"(v[j] * jb.scale),
+                             "f"(v[j + 1] * jb.scale), "f"(v[j + 2] * jb.scale), "f"(v[j + 3] * jb.scale)
+                             : "memory");
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (c + e < jb.cols) atomicAdd(drow + c + e, v[j + e] * jb.scale);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!ok && fault) *fault = 1;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Collects the operand tensors and jobs of one network, then launches.
+struct Builder {
+  Args a;
+  int nmaps = 0, njobs = 0;
+  long long N = 0;
+  double cost[MAX_JOBS];
+  bool bad = false;
+
+  explicit Builder(long long n, float* dpacked) : N(n) {
+    memset(&a, 0, sizeof(a));
+    a.dpacked = dpacked;
+  }
+  // row-major 16-bit tensor [N rows, `cols` valid columns, leading dimension ld elements]
+  int add_map(const void* ptr, int cols, int ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || nmaps >= MAX_MAPS || ((uintptr_t)ptr & 15) || (ld & 7)) { bad = true; return 0; }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64, 64};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&a.maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { bad = true; return 0; }
+    return nmaps++;
+  }
+  Job* add_job(int rows, int cols, long long dw_off, int dw_ld, float scale, long long db_off, float db_scale) {
+    if (njobs >= MAX_JOBS || rows < 1 || rows > 256 || cols < 1 || cols > 256) { bad = true; return &a.jobs[0]; }
+    Job* j = &a.jobs[njobs++];
+    memset(j, 0, sizeof(*j));
+    j->rows = rows; j->cols = cols; j->m_tiles = (rows + 127) / 128; j->n_mma = (cols + 15) & ~15;
+    j->dw_off = dw_off; j->dw_ld = dw_ld; j->scale = scale; j->db_off = db_off; j->db_scale = db_scale;
+    return j;
+  }
+  static void add_seg(Job* j, int xmap, int xcol, int xbf16, int ymap, int ycol, int ybf16) {
+    const int s = j->nseg++;
+    if (s >= 2) return;
+    j->xmap[s] = xmap; j->xcol[s] = xcol; j->xbf16[s] = xbf16; j->ymap[s] = ymap; j->ycol[s] = ycol; j->ybf16[s] = ybf16;
+  }
+  int launch(cudaStream_t st, int family) {
+    if (bad) return (int)cudaErrorInvalidValue;
+    if (njobs == 0 || N <= 0) return 0;
+    const int chunks = (int)((N + 63) / 64);
+    const int sms = ce::num_sms();
+    double total = 0.0;
+    for (int j = 0; j < njobs; ++j) {
+      const Job& jb = a.jobs[j];
+      if (jb.nseg < 1 || jb.nseg > 2) return (int)cudaErrorInvalidValue;
+      cost[j] = (double)jb.nseg * (jb.m_tiles * 2 + (jb.n_mma + 63) / 64);
+      total += cost[j];
+    }
+    // splits per job proportional to its bytes, at least one, at most one per 64-point chunk, sum <= number of SMs
+    int splits[MAX_JOBS], sum = 0;
+    for (int j = 0; j < njobs; ++j) {
+      int s = (int)(cost[j] / total * (sms - njobs)) + 1;
+      if (s > chunks) s = chunks;
+      splits[j] = s;
+      sum += s;
+    }
+    if (sum > MAX_UNITS || sum > sms) return (int)cudaErrorInvalidValue;
+    int nu = 0;
+    double flops = 0.0, bytes = 0.0;
+    for (int j = 0; j < njobs; ++j) {
+      for (int s = 0; s < splits[j]; ++s) {
+        Unit& u = a.units[nu++];
+        u.job = j;
+        u.c0 = (int)((long long)chunks * s / splits[j]);
+        u.c1 = (int)((long long)chunks * (s + 1) / splits[j]);
+      }
+      const Job& jb = a.jobs[j];
+      flops += 2.0 * (double)N * jb.nseg * jb.m_tiles * 128 * jb.n_mma;
+      bytes += 2.0 * (double)N * jb.nseg * (jb.rows + jb.cols);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    if (ce::debug_nomix())
+      for (int j = 0; j < njobs; ++j)
+        for (int sgm = 0; sgm < 2; ++sgm) a.jobs[j].xbf16[sgm] = a.jobs[j].ybf16[sgm] = 0;
+    prof_begin(family, st, flops, bytes);
+    VDN_LAUNCH(wgrad16_kernel, nu, THREADS, SMEM, st, a, g_tc_fault);
+    prof_end(family, st);
+    return ce::debug_sync(st, "wgrad16_kernel", nu);
+  }
+};
+
+}  // namespace wg
+}  // namespace vdn

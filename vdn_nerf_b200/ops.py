@@ -53,6 +53,15 @@ def get_precision() -> str:
     return [k for k, v in _PRECISIONS.items() if v == m][0]
 
 
+def set_chain(on: bool) -> None:
+    """Tensor-core mode: run the training passes as fused layer chains (default) or layer by layer (diagnostics)."""
+    check(_lib.load().vdn_set_chain(1 if on else 0), "vdn_set_chain")
+
+
+def get_chain() -> bool:
+    return bool(_lib.load().vdn_get_chain())
+
+
 def tc_fault() -> int:
     """Non-zero if a tensor-core kernel hit a barrier time-out since the library was loaded (synchronises)."""
     return int(_lib.load().vdn_tc_fault())
@@ -80,7 +89,8 @@ class PackedMLP:
     parameter's storage or version counter changes, i.e. once per optimiser step.
     """
 
-    def __init__(self, in_dims: Sequence[int], out_dims: Sequence[int], sources, rot: Optional[Sequence[int]] = None):
+    def __init__(self, in_dims: Sequence[int], out_dims: Sequence[int], sources, rot: Optional[Sequence[int]] = None,
+                 orot: Optional[Sequence[int]] = None):
         self.in_dims = [int(v) for v in in_dims]
         self.out_dims = [int(v) for v in out_dims]
         self.L = len(self.in_dims)
@@ -105,6 +115,8 @@ class PackedMLP:
             rows += [srcs[0][0].shape[0], srcs[1][0].shape[0] if len(srcs) > 1 else 0]
         self._rows = int_array(rows)
         self._rot = int_array(list(rot) if rot is not None else [0] * self.L)
+        # output rotation of the fp16 tile images (stacked [scalar ; features] heads present their features first)
+        self._orot = int_array(list(orot) if orot is not None else [0] * self.L)
         lib = _lib.load()
         L = self.L
         self.off_w = (ctypes.c_longlong * L)()
@@ -136,7 +148,7 @@ class PackedMLP:
             lib = _lib.load()
             check(lib.vdn_mlp_pack(self.L, self._in, self._out, self._src_ptrs(lambda s: s[0]),
                                    self._src_ptrs(lambda s: s[1]), self._src_ptrs(lambda s: s[2]), self._rows,
-                                   self._rot, _p(buf), _stream()), "vdn_mlp_pack")
+                                   self._rot, self._orot, _p(buf), _stream()), "vdn_mlp_pack")
             self._packed = buf
             self._key = key
         return self._packed
@@ -230,7 +242,9 @@ class SdfHandle:
         if L <= 0:
             raise _lib.VdnLibraryError(f"unsupported SDFNetwork configuration {self.cfg_list}")
         self.L = L
-        self.mlp = PackedMLP(list(ind[:L]), list(outd[:L]), sources_fn())
+        orot = (ctypes.c_int * 16)()
+        lib.vdn_sdf_layer_orot(self.cfg, orot)
+        self.mlp = PackedMLP(list(ind[:L]), list(outd[:L]), sources_fn(), orot=list(orot[:L]))
 
 
 def sdf_value(h: SdfHandle, x: torch.Tensor) -> torch.Tensor:
