@@ -132,10 +132,10 @@ def max_over_ranks(x, world, dev):
 
 def ncu_traffic(name):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches) from the
-    committed `ncu --set full` summary profiles/r01_ncu_full_<name>.txt; None when the file is missing."""
+    committed `ncu --set full` summary profiles/r02_ncu_full_<name>.txt; None when the file is missing."""
     units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_%s.txt" % name)
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_full_%s.txt" % name)
         tot, n = 0.0, 0
         for ln in open(path):
             f = ln.split()
@@ -215,35 +215,86 @@ def cpu_reference_grid(n_points, reps):
 
 # ------------------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores: the UNMODIFIED reference staged under
+    oracle/_ref (oracle/stage_ref.py) when it travelled with the snapshot, else the oracle port.  Same rays, weights and
+    config as the CUDA arm (512 rays per step); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import stage_ref
     depth = args.workload == "train_wdepth"
+    have_ref = stage_ref.available()
+    threads = os.cpu_count() or 1
     if args.workload == "grid":
-        sample = 1 << 17
-        vals = []
-        v, threads, times = cpu_reference_grid(sample, args.warmup + args.steps)
+        sample = 4 * 64 ** 3
+        if have_ref:
+            from oracle import ref_runner
+            from vdn_nerf_b200 import configs
+            torch.set_num_threads(threads)
+            mods, _, _ = ref_runner.build(configs.CONFIGS["womsk_white"], "cpu")
+            pts = torch.rand(sample, 3) * 2.02 - 1.01
+            times = []
+            with torch.no_grad():
+                for i in range(args.warmup + args.steps):
+                    t0 = time.perf_counter()
+                    for blk in pts.split(64 ** 3):           # extract_fields queries 64^3 blocks (renderer.py:10-30)
+                        mods[1].sdf(blk)
+                    if i >= args.warmup:
+                        times.append(time.perf_counter() - t0)
+            v = sample * len(times) / sum(times)
+            kind = "reference"
+        else:
+            v, threads, times = cpu_reference_grid(sample, args.warmup + args.steps)
+            kind = "port"
         value, unit, metric, ms = v, "pts/s", "sdf_grid_pts_per_s", 1e3 * sum(times) / len(times)
         cfg = {"workload": "extract_fields SDF grid query, womsk_white SDF net, x-slabs per rank", "resolution": 512,
-               "mode": "reference algorithm, PyTorch CPU fp32"}
-        sample_s = f"{sample} lattice-like points per step, PyTorch CPU fp32"
+               "mode": "reference, PyTorch CPU fp32"}
+        sample_s = f"{sample} lattice points per step (4 blocks of 64^3 of the 512^3 grid), SDFNetwork.sdf, PyTorch CPU fp32"
     else:
-        sample = 64
-        v, threads, times = cpu_reference_step(sample, depth, args.steps, warm=args.warmup)
+        sample = args.rays
+        if have_ref:
+            from oracle import ref_runner
+            r = ref_runner.run("cpu", sample, args.steps, args.warmup, depth, threads)
+            v, times = r["rays_per_s"], [t * 1e-3 for t in r["times_ms"]]
+            kind = "reference"
+        else:
+            v, threads, times = cpu_reference_step(sample, depth, args.steps, warm=args.warmup)
+            kind = "port"
         value, unit, metric, ms = v, "rays/s", "train_rays_per_s", 1e3 * sum(times) / len(times)
         cfg = {"workload": "womsk_white%s training step (BASELINE configs[%d]): render fwd + driver loss + bwd"
                            % ("_wdepth" if depth else "", 2 if depth else 1), "rays_per_step_per_gpu": args.rays,
                "global_batch": args.rays, "n_samples": 64, "n_importance": 64, "n_outside": 32,
-               "mode": "reference algorithm, PyTorch CPU fp32 autograd"}
-        sample_s = f"{sample} rays per step (bounded sample of the {args.rays}-ray batch), PyTorch CPU fp32, autograd"
+               "mode": "reference, PyTorch CPU fp32 autograd"}
+        sample_s = f"{sample} rays per step (the full batch), PyTorch CPU fp32 autograd, {threads} threads"
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample_s},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": kind, "sample": sample_s},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference cannot travel to the GPU box; this is oracle/vdn_oracle.py, the restatement that "
-                    "oracle/make_golden.py pinned bit-exact against the live reference"}
+            "note": ("the unmodified reference classes (dpt_models/{embedder,fields,renderer}.py staged byte for byte under "
+                     "oracle/_ref by oracle/stage_ref.py) on the host cores" if kind == "reference" else
+                     "oracle/_ref was not staged on this box: this is oracle/vdn_oracle.py, the restatement pinned "
+                     "bit-exact against the live reference")}
     print(json.dumps(line))
+
+
+def reference_cuda_eager(rays, depth, steps=10, warmup=3, timeout=600):
+    """The reference's own eager CUDA path on this GPU: the staged reference classes under
+    torch.set_default_tensor_type('torch.cuda.FloatTensor') (dpt_runner.py:744), in a subprocess because the switch is
+    process-wide.  Returns the parsed JSON of oracle/ref_runner.py or {"unavailable": why}."""
+    from oracle import stage_ref
+    if not stage_ref.available():
+        return {"unavailable": "oracle/_ref not staged on this box"}
+    cmd = [sys.executable, "-m", "oracle.ref_runner", "--device", "cuda", "--rays", str(rays), "--steps", str(steps),
+           "--warmup", str(warmup)] + (["--depth"] if depth else [])
+    try:
+        out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": "no result: " + out.stderr.strip()[-300:]}
+    except Exception as ex:    # noqa: BLE001 - a failed side measurement must not fail the bench line
+        return {"unavailable": repr(ex)[:300]}
 
 
 def run_ours(args):
@@ -376,7 +427,7 @@ def run_ours(args):
         lib.vdn_prof_enable(1)
         fn(0)
         fam = {}
-        for f, nm in ((0, "gemm_nt"), (1, "wgrad"), (2, "tc"), (3, "chain")):
+        for f, nm in ((0, "gemm_nt"), (1, "wgrad"), (2, "tc"), (3, "chain"), (4, "chain_train"), (5, "wgrad16")):
             msn, sp, fl, by = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double(), ctypes.c_double()
             lib.vdn_prof_read(f, ctypes.byref(msn), ctypes.byref(sp), ctypes.byref(fl))
             lib.vdn_prof_read_bytes(f, ctypes.byref(by))
@@ -387,28 +438,40 @@ def run_ours(args):
         ach = alg / (gemm_ms * 1e-3) / 1e12
         tensor_view = {"achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                        "algorithmic_flops_per_step": alg, "executed_flops_per_step": sum(v[2] for v in fam.values()),
-                       "peak_source": pk["source"] + " bf16 sustained (dense tf32 peak is half of it)"}
+                       "note": "algorithmic FLOPs of the whole step (SURVEY 8(d)) / summed MLP-kernel time",
+                       "peak_source": pk["source"] + " bf16 sustained (kind::f16 rate)"}
         common = {"launches_by_family": {k: v[1] for k, v in fam.items()}, "ms_by_family": {k: v[0] for k, v in fam.items()},
-                  "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps)}
+                  "kernel_ms_per_step": gemm_ms, "share_of_step": gemm_ms / (ms / args.steps),
+                  "all_families": {k: {"ms": v[0], "launches": v[1], "GB/s": (v[3] / (v[0] * 1e-3) / 1e9) if v[0] else 0.0,
+                                       "TFLOP/s": (v[2] / (v[0] * 1e-3) / 1e12) if v[0] else 0.0}
+                                   for k, v in fam.items()}}
+        names = {"gemm_nt": "gemm_nt_kernel (FFMA)", "wgrad": "gemm_tn(_tc)_kernel (layer-wise weight gradient)",
+                 "tc": "gemm_nt_tc_kernel (layer-wise tcgen05 kind::tf32 GEMM)",
+                 "chain": "sdf_chain_tc_kernel (fused SDF value chain of the hierarchical sampler, kind::f16)",
+                 "chain_train": "chain_kernel (fused training chains: SDF forward / normals / backward phases 1+2, colour and "
+                                "NeRF forward / backward; tcgen05 kind::f16, A operand in TMEM, 16-bit saved tensors)",
+                 "wgrad16": "wgrad16_kernel (grouped weight gradient, TMA tensor maps, MN-major bf16 operands)"}
         if args.precision == "tf32":
-            # the layer-wise tcgen05 GEMMs stream every activation through HBM once per layer: they are bandwidth bound
-            dom = "tc" if fam["tc"][0] >= fam["wgrad"][0] else "wgrad"
-            gbs = fam[dom][3] / (fam[dom][0] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "%s (layer-wise tcgen05 kind::tf32 GEMM with fused prologue/epilogue), %d launches "
-                    "per step; algorithmic bytes = every operand / output / auxiliary element once"
-                    % ("gemm_nt_tc_kernel" if dom == "tc" else "gemm_tn_tc_kernel", fam[dom][1]),
-                    "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                    "traffic": ncu_traffic("nt" if dom == "tc" else "tn"),
-                    "traffic_note": "DRAM bytes per launch, mean of the two launches captured with ncu --set full "
-                                    "(profiles/r01_ncu_full_%s.txt); compare algorithmic_bytes_per_launch"
-                                    % ("nt" if dom == "tc" else "tn"),
-                    "algorithmic_bytes_per_launch": fam[dom][3] / max(1, fam[dom][1]),
-                    "algorithmic_bytes_per_step": fam[dom][3], "kernel_ms": fam[dom][0],
-                    "peak_source": pk["source"] + " hbm (copy)",
-                    "all_gemm_families": {k: {"ms": v[0], "launches": v[1], "GB/s": (v[3] / (v[0] * 1e-3) / 1e9) if v[0] else 0.0,
-                                              "TFLOP/s": (v[2] / (v[0] * 1e-3) / 1e12) if v[0] else 0.0}
-                                          for k, v in fam.items()},
-                    "tensor_view": tensor_view}
+            dom = max(fam, key=lambda k: fam[k][0])
+            d_ms, d_n, d_fl, d_by = fam[dom]
+            gbs = d_by / (d_ms * 1e-3) / 1e9
+            tfs = d_fl / (d_ms * 1e-3) / 1e12
+            f_h, f_t = gbs / pk["hbm"], tfs / pk["bf16_sustained"]
+            # the roof that binds the dominant kernel is the one it sits closer to
+            if f_h >= f_t:
+                roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": f_h,
+                        "peak_source": pk["source"] + " hbm (copy)"}
+            else:
+                roof = {"bound": "tensor", "achieved": tfs, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": f_t,
+                        "peak_source": pk["source"] + " bf16 sustained"}
+            roof.update({"kernel": "%s, %d launches per step" % (names[dom], d_n),
+                         "hbm_frac": f_h, "tensor_frac": f_t,
+                         "traffic": ncu_traffic(dom),
+                         "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r02_ncu_full_%s.txt) when "
+                                         "committed; compare algorithmic_bytes_per_launch" % dom,
+                         "algorithmic_bytes_per_launch": d_by / max(1, d_n), "algorithmic_bytes_per_step": d_by,
+                         "executed_flops_per_launch": d_fl / max(1, d_n), "kernel_ms": d_ms,
+                         "launch_ms": d_ms / max(1, d_n), "tensor_view": tensor_view})
         else:
             roof = dict(tensor_view)
             roof.update({"bound": "tensor", "traffic": None,
@@ -430,22 +493,35 @@ def run_ours(args):
     clocks = cs.summary()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import stage_ref
+            have_ref = stage_ref.available()
+            threads = os.cpu_count() or 1
             if cpu_kind == "grid":
                 v, threads, times = cpu_reference_grid(1 << 17, 3)
                 cb = {"value": v, "unit": "pts/s", "cores": threads, "kind": "port",
                       "sample": "131072 points x 3 reps of SDFNetwork.sdf, PyTorch CPU fp32 (oracle port)"}
+            elif have_ref:
+                from oracle import ref_runner
+                r = ref_runner.run("cpu", B, 2, 1, depth, threads)
+                cb = {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["threads"], "kind": "reference",
+                      "sample": "%d rays x 2 timed steps (1 warm-up) of render + loss + backward through the unmodified "
+                                "reference classes (oracle/_ref), PyTorch CPU fp32 autograd" % B}
             else:
                 v, threads, times = cpu_reference_step(128, depth, 2)
                 cb = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
                       "sample": "128 rays x 2 timed steps (1 warm-up) of render+loss+backward, PyTorch CPU fp32 "
-                                "autograd (oracle port of the reference)"}
+                                "autograd (oracle port of the reference; oracle/_ref not staged on this box)"}
             line["cpu_baseline"] = cb
+            if cpu_kind == "train" and not args.no_ref_cuda:
+                # the reference's own eager CUDA path on this same GPU; reported, not a target
+                line["reference_cuda_eager"] = reference_cuda_eager(B, depth)
         line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
                      "scaling": "weak", "vs_baseline": None,
                      "dtype": line.get("dtype", "tf32" if args.precision == "tf32" else "f32"),
                      "data": "synthetic", "gpu_launches": int(launches), "clocks": clocks})
         order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"]
+                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline",
+                 "reference_cuda_eager", "clocks"]
         print(json.dumps({k: line[k] for k in order if k in line}))
     if world > 1:
         import torch.distributed as dist
@@ -462,6 +538,7 @@ def main():
     ap.add_argument("--rays", type=int, default=512, help="rays per step per GPU")
     ap.add_argument("--resolution", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's eager-CUDA leg (subprocess)")
     ap.add_argument("--no-cuda-graph", action="store_true",
                     help="training workloads: launch every kernel eagerly instead of replaying the captured step")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],

@@ -33,18 +33,22 @@ long long vdn_launch_count(void);
 /* cudaGetErrorString for the codes this library returns. */
 const char* vdn_error_string(int code);
 
-/* Arithmetic mode of the MLP contractions: 0 = exact fp32 (FFMA kernels; parity <= 1e-5), 1 = tf32 tensor cores
- * (tcgen05.mma kind::tf32 with fp32 accumulation in TMEM; parity <= 2e-3 on colour and normals).  Process-wide.
- * Mode 1 allocates one 4-byte device flag that a tcgen05 kernel raises if one of its bounded barrier waits times
- * out; vdn_tc_fault() reads it (synchronising). */
+/* Arithmetic mode of the MLP contractions: 0 = exact fp32 (FFMA kernels; parity <= 1e-5), 1 = tensor cores (tcgen05.mma
+ * with fp32 accumulation in TMEM: fp16 operands in the forward / normals chains, bf16 in the backward chains, tf32 in the
+ * layer-wise kernels; parity <= 2e-3 on colour and normals).  Process-wide.
+ * A tcgen05 kernel raises a 4-byte device flag if one of its bounded barrier waits times out.  The flag is memory of the
+ * CALLER (vdn_set_fault_flag; the library allocates nothing); vdn_tc_fault() reads it synchronously,
+ * vdn_tc_fault_async() enqueues a copy to (pinned) host memory on a stream. */
 int vdn_set_mode(int mode);
 int vdn_get_mode(void);
+int vdn_set_fault_flag(int* device_flag);
+int vdn_tc_fault(void);
+int vdn_tc_fault_async(int* host_dst /*host, pinned*/, void* stream);
 /* Tensor-core mode only: 1 (default) runs the training passes of the three networks as fused layer chains
  * (csrc/chain_engine.cuh: activations resident in tensor memory, 16-bit saved tensors, grouped TMA weight gradient),
  * 0 runs them layer by layer (csrc/gemm_tc.cuh).  Must not change between a forward and its backward. */
 int vdn_set_chain(int on);
 int vdn_get_chain(void);
-int vdn_tc_fault(void);
 
 /* Debug aid: when device_buf (8192 int64 of device memory) is non-null, the tcgen05 kernels record time stamps there:
  * CTA 0 of a layer-wise GEMM launch its pipeline events as clock64() in entries [0, 512) and every CTA (first 1500)
@@ -110,12 +114,16 @@ int vdn_grid_sdf(const int* cfg, float scale, const float* packed, const float* 
  * cfg (host) = {d_feature, mode(0 idr,1 no_view_dir,2 no_normal), d_out, d_hidden, n_layers, multires_view,
  *               squeeze_out} */
 int vdn_rendernet_layer_dims(const int* cfg, int* in_dims, int* out_dims);
+/* Input-column rotation per layer for vdn_mlp_pack / vdn_mlp_unpack_grads: layer 0 is packed as [feature | extras], and
+ * that is also the column order of the saved input row and of d_cin below. */
+int vdn_rendernet_layer_rot(const int* cfg, int* rot);
 long long vdn_rendernet_blob_floats(const int* cfg, long long N);
 long long vdn_rendernet_bwd_ws_floats(const int* cfg, long long N);
 int vdn_rendernet_forward(const int* cfg, const float* packed, const float* points, const float* normals,
                           const float* view_dirs, const float* feats, int ldf, long long N, float* out, float* blob,
                           void* stream);
-/* d_cin (nullable): [N, round_up(in0,16)] cotangent of the concatenated input row of fields.py:154. */
+/* d_cin (nullable): [N, round_up(in0,16)] cotangent of the input row of fields.py:154 in the ROTATED column order
+ * [feature | points | view embedding | normals] (vdn_rendernet_layer_rot). */
 int vdn_rendernet_backward(const int* cfg, const float* packed, long long N, const float* blob, const float* out,
                            const float* d_out, float* dpacked, float* d_cin, float* ws, void* stream);
 
@@ -123,6 +131,8 @@ int vdn_rendernet_backward(const int* cfg, const float* packed, long long N, con
  * cfg (host) = {D, W, d_in, d_in_view, multires, multires_view, skip|-1, rgb_dims, dpt_dim(0 = no depth head)}
  * Packed layers: pts_linears[0..D-1], [alpha_linear;feature_linear], views_linears[0], [rgb_linear;dpt_linear]. */
 int vdn_nerf_layer_dims(const int* cfg, int* in_dims, int* out_dims);
+/* Output rotation per layer for vdn_mlp_pack (stacked [alpha ; feature] head: features first in the 16-bit images). */
+int vdn_nerf_layer_orot(const int* cfg, int* orot);
 long long vdn_nerf_blob_floats(const int* cfg, long long N);
 long long vdn_nerf_bwd_ws_floats(const int* cfg, long long N);
 int vdn_nerf_forward(const int* cfg, const float* packed, const float* pts, const float* views, long long N,

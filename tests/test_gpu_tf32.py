@@ -21,22 +21,27 @@ from vdn_nerf_b200.training import driver_loss
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-3
-GTOL = 1e-2
+GTOL = 1e-2              # layer-wise tensor-core path (tf32 operands)
+GTOL_CHAIN = 2e-2        # fused chains: bf16 cotangents (8-bit mantissa, fp32 range) against bf16 hi/lo weights
 GTOL_RELU_L2 = 1e-1
 
 
 def grad_ok(name, got, want):
     if name.startswith(("sdf.",)) or name == "x":
-        return util.relerr(got, want) < GTOL
+        return util.relerr(got, want) < (GTOL_CHAIN if ops.get_chain() else GTOL)
     return util.relerr_l2(got, want) < GTOL_RELU_L2
 
 
-@pytest.fixture(scope="module", autouse=True)
-def tf32_mode():
+@pytest.fixture(scope="module", autouse=True, params=["chains", "layerwise"])
+def tf32_mode(request):
+    """Every test of this module runs twice: with the fused training chains (the default tensor-core path) and with
+    the layer-wise tcgen05 GEMMs (the path of shapes the chains do not cover)."""
     ops.set_precision("tf32")
+    ops.set_chain(request.param == "chains")
     yield
     torch.cuda.synchronize()
     fault = ops.tc_fault()
+    ops.set_chain(True)
     ops.set_precision("fp32")
     assert fault == 0, "a tcgen05 kernel timed out on a barrier"
 

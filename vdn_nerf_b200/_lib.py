@@ -32,6 +32,8 @@ SIGNATURES = {
     "vdn_set_chain": (I, [I]),
     "vdn_get_chain": (I, []),
     "vdn_tc_fault": (I, []),
+    "vdn_set_fault_flag": (I, [P]),
+    "vdn_tc_fault_async": (I, [P, P]),
     "vdn_debug_timeline": (I, [P]),
     "vdn_sdf_layer_dims": (I, [P, P, P]),
     "vdn_sdf_layer_orot": (I, [P, P]),
@@ -43,11 +45,13 @@ SIGNATURES = {
     "vdn_sdf_backward": (I, [P, F, P, P, L, P, P, P, I, P, I, P, P, P, P, P]),
     "vdn_grid_sdf": (I, [P, F, P, P, P, P, I, I, I, I, F, P, P, P, P]),
     "vdn_rendernet_layer_dims": (I, [P, P, P]),
+    "vdn_rendernet_layer_rot": (I, [P, P]),
     "vdn_rendernet_blob_floats": (L, [P, L]),
     "vdn_rendernet_bwd_ws_floats": (L, [P, L]),
     "vdn_rendernet_forward": (I, [P, P, P, P, P, P, I, L, P, P, P]),
     "vdn_rendernet_backward": (I, [P, P, L, P, P, P, P, P, P, P]),
     "vdn_nerf_layer_dims": (I, [P, P, P]),
+    "vdn_nerf_layer_orot": (I, [P, P]),
     "vdn_nerf_blob_floats": (L, [P, L]),
     "vdn_nerf_bwd_ws_floats": (L, [P, L]),
     "vdn_nerf_forward": (I, [P, P, P, P, L, P, P, P, P, P]),

@@ -45,14 +45,19 @@ extern "C" const char* vdn_error_string(int code) { return cudaGetErrorString((c
 
 extern "C" int vdn_set_mode(int mode) {
   if (mode != 0 && mode != 1) return (int)cudaErrorInvalidValue;
-  if (mode == 1 && !g_tc_fault) {  // 4-byte device flag raised by a timed-out barrier wait in a tcgen05 kernel
-    cudaError_t e = cudaMalloc(&g_tc_fault, sizeof(int));
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemset(g_tc_fault, 0, sizeof(int));
-    if (e != cudaSuccess) return (int)e;
-  }
   g_mode = mode;
   return 0;
+}
+// The 4-byte device flag a tcgen05 kernel raises when one of its bounded barrier waits times out.  The caller owns the
+// memory (a torch tensor on the device the kernels run on); null switches the reporting off.
+extern "C" int vdn_set_fault_flag(int* device_flag) {
+  g_tc_fault = device_flag;
+  return 0;
+}
+// Enqueue a device -> host copy of the flag on `stream` (host_dst should be pinned); no synchronisation.
+extern "C" int vdn_tc_fault_async(int* host_dst, void* stream) {
+  if (!g_tc_fault || !host_dst) return 0;
+  return (int)cudaMemcpyAsync(host_dst, g_tc_fault, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 }
 extern "C" int vdn_get_mode(void) { return g_mode; }
 extern "C" int vdn_set_chain(int on) { g_chain = on ? 1 : 0; return 0; }

@@ -39,7 +39,7 @@ constexpr int WSTAGES = 6;
 constexpr int KEEP = 4;                          // weight blocks of a phase kept in the ring for the second slot
 constexpr uint32_t W_STAGE = 32768;
 constexpr int MAX_PHASES = 16;
-constexpr int MAX_STASH = 2;
+constexpr int MAX_STASH = 2;                     // stash slots per tile (fp16, 64 values per thread each)
 constexpr size_t SMEM = WSTAGES * W_STAGE + 1024 + MAX_PHASES * 256 * sizeof(float) + 2 * 256 * sizeof(float);
 
 constexpr float kB2 = 144.26950408889634f;       // beta / ln 2 (Softplus(beta=100), fields.py:50)
@@ -98,7 +98,7 @@ struct Args {
   const float* packed;
   const void* a0; int a0_ld, a0_w;          // A operand of phase 0
   long long row_off[2]; int row_len[2];     // rank-1 row vectors (float offsets into packed, -1: none)
-  float* stash;                             // [grid][2][MAX_STASH][8][512][8] floats
+  uint16_t* stash;                          // fp16 scratch [grid][2][MAX_STASH][8][512][8] (stays in L2)
   Phase ph[MAX_PHASES];
 };
 
@@ -161,7 +161,7 @@ __device__ __forceinline__ float ld16_one(const void* base, long long idx, int b
 // halves so that 32 + ~45 registers suffice (a thread of a 576-thread CTA has 96).
 template <int OP>
 __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], int half, const float* sb, const float* srow,
-                                       long long m, long long N, int c0, uint32_t tA, float* stash_base) {
+                                       long long m, long long N, int c0, uint32_t tA, uint16_t* stash_base) {
   constexpr bool kBf16 = (OP == OP_P1STEP || OP == OP_P2STEP || OP == OP_MASK);
   const int ncols = ph.a_out ? ph.a_wr : ph.width;      // columns this phase touches
   const float r1v = ph.r1 ? ph.r1[m < N ? m * ph.r1_stride : 0] * ph.r1_mul : 0.0f;
@@ -179,15 +179,17 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = fmaf(r1v, rr[cg + j], x[j]);
     }
-    if (OP != OP_STASH && ph.stash_r >= 0) {
-      const float4* sp = reinterpret_cast<const float4*>(stash_base + ((size_t)ph.stash_r * 8 + g) * (512 * 8));
-      const float4 s0 = sp[0], s1 = sp[1];
-      x[0] += s0.x; x[1] += s0.y; x[2] += s0.z; x[3] += s0.w; x[4] += s1.x; x[5] += s1.y; x[6] += s1.z; x[7] += s1.w;
+    if (OP != OP_STASH && ph.stash_r >= 0) {      // written earlier by this very thread: plain (coherent) load
+      const uint4 u = *reinterpret_cast<const uint4*>(stash_base + ((size_t)ph.stash_r * 8 + g) * (512 * 8));
+      float s8[8];
+      unpack_h8(u, s8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += s8[j];
     }
     if (OP == OP_STASH) {
-      float4* sp = reinterpret_cast<float4*>(stash_base + ((size_t)ph.stash_w * 8 + g) * (512 * 8));
-      sp[0] = make_float4(v[gi][0], v[gi][1], v[gi][2], v[gi][3]);
-      sp[1] = make_float4(v[gi][4], v[gi][5], v[gi][6], v[gi][7]);
+      *reinterpret_cast<uint4*>(stash_base + ((size_t)ph.stash_w * 8 + g) * (512 * 8)) =
+          make_uint4(pack_h2(v[gi][0], v[gi][1]), pack_h2(v[gi][2], v[gi][3]), pack_h2(v[gi][4], v[gi][5]),
+                     pack_h2(v[gi][6], v[gi][7]));
       continue;
     }
     // fp32 side output of x (final outputs, skip-connection tails)
@@ -399,7 +401,7 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
           ++dcnt;
           tc_fence_after();
           const uint32_t tA = lane_base + 256u + (uint32_t)(s * 128 + hq * 32);
-          float* stb = a.stash ? a.stash + (((size_t)blockIdx.x * 2 + s) * MAX_STASH * 8) * (512 * 8) + (size_t)tid * 8 : nullptr;
+          uint16_t* stb = a.stash ? a.stash + (((size_t)blockIdx.x * 2 + s) * MAX_STASH * 8) * (512 * 8) + (size_t)tid * 8 : nullptr;
           // the accumulator is drained in two halves of 32 columns; D is released once the second half sits in registers
 #pragma unroll 1
           for (int half = 0; half < 2; ++half) {
@@ -547,7 +549,6 @@ inline void set_mma_bf16(Phase* p, long long hi_off, long long lo_off, int img_r
   set_mma(p, hi_off, img_rows, row0, kb0, n, k, a_col);
   p->img2_off = lo_off; p->a_bf16 = 1; p->b_bf16 = 1;
 }
-inline size_t stash_floats(int grid) { return (size_t)grid * 2 * MAX_STASH * 8 * 512 * 8; }
 
 inline int num_sms() {
   static int n = 0;
@@ -563,6 +564,8 @@ inline int grid_for(long long N) {
   const int sms = num_sms();
   return (int)(ntiles < sms ? ntiles : sms);
 }
+
+inline size_t stash_floats(long long N) { return (size_t)grid_for(N) * 2 * MAX_STASH * 8 * 512 * 8 / 2; }
 
 // Debug aid (environment variable VDN_SYNC=1): synchronise after every launch of the new kernels and name the one that
 // failed on stderr.  Off by default: the library never synchronises.

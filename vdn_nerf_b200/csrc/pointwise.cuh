@@ -196,9 +196,10 @@ static __global__ void head_edges_kernel(const float* __restrict__ a, long long 
   else dst[m * ldd + wreal + j - 1] = 0.0f;
 }
 
-// Rendering-network input row (reference fields.py:148-158):
-//   idr:          [points(3) | PE_L(view)(3+6L) | normals(3) | feats(F)]
-//   no_view_dir:  [points | normals | feats]         no_normal: [points | PE(view) | feats]
+// Rendering-network input row (reference fields.py:148-158), stored ROTATED as [feats(F) | extras] like the packed
+// first layer (rot = in0 - F), so that the fused chains can treat the 256-wide feature as the main operand:
+//   idr extras:   [points(3) | PE_L(view)(3+6L) | normals(3)]
+//   no_view_dir:  [points | normals]         no_normal: [points | PE(view)]
 // One warp per row: lanes 0..2 write the point / view-embedding / normal columns of their coordinate,
 // all lanes copy the feature columns with coalesced accesses.
 static __global__ void rendernet_input_kernel(const float* __restrict__ pts, const float* __restrict__ nrm,
@@ -211,25 +212,26 @@ static __global__ void rendernet_input_kernel(const float* __restrict__ pts, con
   const int d = 3;
   const int nview = (mode != 1) ? d * (1 + 2 * L) : 0;
   const int nnrm = (mode != 2) ? 3 : 0;
+  float* x = r + F;                     // extras follow the feature columns
   if (lane < 3) {
     const int j = lane;
-    r[j] = pts[m * 3 + j];
+    x[j] = pts[m * 3 + j];
     if (mode != 1) {
       float v = view[m * 3 + j];
-      r[3 + j] = v;
+      x[3 + j] = v;
       float f = 1.0f;
       for (int k = 0; k < L; ++k) {
         float s, co;
         sincosf(v * f, &s, &co);
-        r[3 + d + 2 * k * d + j] = s;
-        r[3 + d + 2 * k * d + d + j] = co;
+        x[3 + d + 2 * k * d + j] = s;
+        x[3 + d + 2 * k * d + d + j] = co;
         f *= 2.0f;
       }
     }
-    if (mode != 2) r[3 + nview + j] = nrm[m * 3 + j];
+    if (mode != 2) x[3 + nview + j] = nrm[m * 3 + j];
   }
   const int c0 = 3 + nview + nnrm;
-  for (int j = lane; j < F; j += 32) r[c0 + j] = feat[m * ldf + j];
+  for (int j = lane; j < F; j += 32) r[j] = feat[m * ldf + j];
   for (int c = c0 + F + lane; c < ldc; c += 32) r[c] = 0.0f;
 }
 

@@ -4,6 +4,7 @@
 // Post-activation tensors H_l are stored (ReLU backward only needs the sign), heads that share an input are
 // packed as one stacked weight so they run as one GEMM with a splitting epilogue.
 #include "gemm_tn_tc.cuh"
+#include "relu_chains.cuh"
 #include "pointwise.cuh"
 #include "../../include/vdn_b200.h"
 
@@ -36,6 +37,17 @@ static int parse_rn_cfg(const int* cfg, RnCfg* c) {
   return make_layout(c->L, in_dims, out_dims, &c->ly);
 }
 
+// Fused chains (relu_chains.cuh) for the shipped shape: 256 feature inputs, 256-wide hidden layers, at most 48 extra
+// input columns, at most 128 outputs.
+static bool rn_chain_ok(const RnCfg& c) {
+  if (g_mode != 1 || !g_chain) return false;
+  const int nextra = c.in0 - c.d_feature;
+  if (c.d_feature != 256 || c.d_hidden != 256 || nextra < 1 || nextra > 48 || c.d_out > 128 || c.L < 2 || c.L > 10) return false;
+  return wg::encode_fn() != nullptr;
+}
+static RnShape rn_shape(const RnCfg& c) {
+  return RnShape{c.L, c.d_feature, c.in0 - c.d_feature, c.d_out, c.mode, c.multires_view, c.squeeze_out, c.ldIn, &c.ly};
+}
 }  // namespace vdn
 using namespace vdn;
 
@@ -50,7 +62,17 @@ extern "C" int vdn_rendernet_layer_dims(const int* cfg, int* in_dims, int* out_d
 extern "C" long long vdn_rendernet_blob_floats(const int* cfg, long long N) {
   RnCfg c;
   if (parse_rn_cfg(cfg, &c)) return -1;
-  return N * c.ldIn + (long long)(c.L - 1) * N * c.ldH;
+  const long long a = N * c.ldIn + (long long)(c.L - 1) * N * c.ldH, b = rn_chain_blob_floats(c.L, N);
+  return a > b ? a : b;
+}
+
+// Input-column rotation of the packed layers (layer 0 is stored as [feature | extras]); returns the number of layers.
+extern "C" int vdn_rendernet_layer_rot(const int* cfg, int* rot) {
+  RnCfg c;
+  if (parse_rn_cfg(cfg, &c)) return -1;
+  for (int l = 0; l < c.L; ++l) rot[l] = 0;
+  rot[0] = c.in0 - c.d_feature;
+  return c.L;
 }
 
 extern "C" int vdn_rendernet_forward(const int* cfg, const float* packed, const float* points, const float* normals,
@@ -60,6 +82,11 @@ extern "C" int vdn_rendernet_forward(const int* cfg, const float* packed, const 
   if (parse_rn_cfg(cfg, &c)) return (int)cudaErrorInvalidValue;
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (rn_chain_ok(c)) {
+    RnChainBufs cb;
+    rn_chain_carve(c.L, N, blob, nullptr, &cb);
+    return rn_chain_forward(rn_shape(c), packed, points, normals, view_dirs, feats, ldf, N, out, cb, st);
+  }
   float* CIN = blob;
   float* H = blob + N * c.ldIn;
   long long threads = N * 32;
@@ -93,7 +120,8 @@ extern "C" long long vdn_rendernet_bwd_ws_floats(const int* cfg, long long N) {
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
-  return 2 * N * c.ldH + N * c.ly.out_ld[c.L - 1] + S * maxw + 256 * maxo + 64;
+  const long long a = 2 * N * c.ldH + N * c.ly.out_ld[c.L - 1] + S * maxw + 256 * maxo + 64, b = rn_chain_ws_floats(c.L, N);
+  return a > b ? a : b;
 }
 
 // d_out: [N, d_out] contiguous cotangent of the network output; `out` is the forward output.
@@ -105,6 +133,11 @@ extern "C" int vdn_rendernet_backward(const int* cfg, const float* packed, long 
   if (parse_rn_cfg(cfg, &c)) return (int)cudaErrorInvalidValue;
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (rn_chain_ok(c)) {
+    RnChainBufs cb;
+    rn_chain_carve(c.L, N, const_cast<float*>(blob), ws, &cb);
+    return rn_chain_backward(rn_shape(c), packed, N, cb, out, d_out, dpacked, d_cin, st);
+  }
   const MlpLayout& ly = c.ly;
   const int L = c.L, M = (int)N;
   const float* CIN = blob;
@@ -197,6 +230,16 @@ static void carve_nerf(const NerfCfg& c, long long N, float* p, NerfBlob* b) {
   for (int i = 0; i < c.D; ++i) { b->H[i] = p; p += N * c.ldH; }
   b->HV = p;
 }
+static int nerf_orot_head(const NerfCfg& c) { return (c.W & 7) == 0 ? 1 : 0; }
+static bool nerf_chain_ok(const NerfCfg& c) {
+  if (g_mode != 1 || !g_chain) return false;
+  if (c.W != 256 || c.d_e > 96 || c.d_ev > 32 || c.D < 2 || c.D > 8 || c.rgb_dims + c.dpt_dim > 128 || c.rgb_dims < 1) return false;
+  if (c.skip >= 0 && c.skip > c.D - 2) return false;
+  return wg::encode_fn() != nullptr;
+}
+static NerfShape nerf_shape(const NerfCfg& c) {
+  return NerfShape{c.D, c.W, c.d_in, c.multires, c.multires_view, c.skip, c.rgb_dims, c.dpt_dim, c.d_e, c.d_ev, &c.ly};
+}
 // The input operand of pts layer i and where its post-ReLU output lives (buffer, ld, column offset).
 static Operand nerf_input(const NerfCfg& c, const NerfBlob& b, int i) {
   if (i == 0) return make_operand(b.E, c.ldE, c.ldE, c.d_e);
@@ -217,7 +260,17 @@ extern "C" int vdn_nerf_layer_dims(const int* cfg, int* in_dims, int* out_dims) 
 extern "C" long long vdn_nerf_blob_floats(const int* cfg, long long N) {
   NerfCfg c;
   if (parse_nerf_cfg(cfg, &c)) return -1;
-  return nerf_blob_floats(c, N);
+  const long long a = nerf_blob_floats(c, N), b = nerf_chain_blob_floats(c.D, N);
+  return a > b ? a : b;
+}
+
+// Output rotation per packed layer for vdn_mlp_pack (the stacked [alpha ; feature] head presents its features first).
+extern "C" int vdn_nerf_layer_orot(const int* cfg, int* orot) {
+  NerfCfg c;
+  if (parse_nerf_cfg(cfg, &c)) return -1;
+  for (int l = 0; l < c.L; ++l) orot[l] = 0;
+  orot[c.D] = nerf_orot_head(c);
+  return c.L;
 }
 
 extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float* pts, const float* views,
@@ -226,6 +279,11 @@ extern "C" int vdn_nerf_forward(const int* cfg, const float* packed, const float
   if (parse_nerf_cfg(cfg, &c)) return (int)cudaErrorInvalidValue;
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (nerf_chain_ok(c)) {
+    NerfChainBufs cb;
+    nerf_chain_carve(c.D, N, blob, nullptr, &cb);
+    return nerf_chain_forward(nerf_shape(c), packed, pts, views, N, sigma, rgb, dpt, cb, st);
+  }
   const MlpLayout& ly = c.ly;
   NerfBlob b;
   carve_nerf(c, N, blob, &b);
@@ -282,8 +340,10 @@ extern "C" long long vdn_nerf_bwd_ws_floats(const int* cfg, long long N) {
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
-  return 2 * N * c.ldH + N * c.ly.out_ld[c.D] + N * c.ldHV + N * c.ly.out_ld[c.D + 2] + N * c.ldV +
-         2 * N * c.ldE + S * maxw + 256 * maxo + 64;
+  const long long a = 2 * N * c.ldH + N * c.ly.out_ld[c.D] + N * c.ldHV + N * c.ly.out_ld[c.D + 2] + N * c.ldV +
+                      2 * N * c.ldE + S * maxw + 256 * maxo + 64;
+  const long long b = nerf_chain_ws_floats(c.D, N);
+  return a > b ? a : b;
 }
 
 // d_pts (nullable): [N, d_in]; d_views (nullable): [N, 3].
@@ -295,6 +355,11 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
   if (parse_nerf_cfg(cfg, &c)) return (int)cudaErrorInvalidValue;
   if (N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (nerf_chain_ok(c)) {
+    NerfChainBufs cb;
+    nerf_chain_carve(c.D, N, const_cast<float*>(blob), ws, &cb);
+    return nerf_chain_backward(nerf_shape(c), packed, pts, views, N, cb, d_sigma, d_rgb, d_dpt, dpacked, d_pts, d_views, st);
+  }
   const MlpLayout& ly = c.ly;
   NerfBlob b;
   carve_nerf(c, N, const_cast<float*>(blob), &b);

@@ -112,6 +112,20 @@ static __global__ void rows_to_fp16_kernel(const float* __restrict__ src, int ld
   const int c = (int)(idx - m * ldd);
   dst[idx] = __float2half_rn((src && m < N && c < w) ? src[m * lds + c] * mul : 0.0f);
 }
+// dst[m, :] = bf16([a[m, 0..wa) | b[m, 0..wb) | 0 ...]) up to ldd columns (null source: zeros), zero rows beyond N
+static __global__ void gather2_bf16_kernel(const float* __restrict__ a, int lda, int wa, const float* __restrict__ b, int ldb,
+                                           int wb, long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Npad * ldd) return;
+  const long long m = idx / ldd;
+  const int c = (int)(idx - m * ldd);
+  float v = 0.0f;
+  if (m < N) {
+    if (c < wa) { if (a) v = a[m * lda + c]; }
+    else if (c < wa + wb) { if (b) v = b[m * ldb + (c - wa)]; }
+  }
+  dst[idx] = __float2bfloat16_rn(v);
+}
 // dst[m, 0] = bf16(1) for m < N, everything else zero: the "ones" operand that turns a column sum into a GEMM row
 static __global__ void ones_col_bf16_kernel(long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,7 +303,7 @@ static inline int sdf_chain_backward(const SdfShape& s, const float* packed, con
       p = ce::make_phase();
       ce::set_mma_bf16(&p, ly.off_ib[l], ly.off_ib2[l], ly.out_ld[l], 0, 0, ly.out_dim[l], ly.in_dim[l]);
       p.op = ce::OP_P1STEP; p.width = ly.out_dim[l];
-      p.aux0 = b.AB16[l]; p.ld0 = 256; p.aux0_bf16 = 1; p.aux1 = b.DB16[l]; p.ld1 = 256; p.aux1_bf16 = 1;
+      p.aux0 = b.A16[l]; p.ld0 = 256; p.aux0_bf16 = 0; p.aux1 = b.DB16[l]; p.ld1 = 256; p.aux1_bf16 = 1;
       p.a_mul = sdf_dsc(s, l + 1);
       p.a_out = l < L - 2 ? 1 : 0; p.a_wr = 256;
       p.o16a = b.Q16[l + 1]; p.ldo16a = 256; p.o16a_bf16 = 1;
@@ -325,7 +339,7 @@ static inline int sdf_chain_backward(const SdfShape& s, const float* packed, con
       ce::set_mma_bf16(&p, ly.off_ibt[l], ly.off_ibt2[l], ly.in_ld[l], 0, 0, ly.in_dim[l], k);
       p.op = ce::OP_P2STEP; p.width = ly.out_dim[l - 1]; p.dsc = sdf_dsc(s, l);
       if (l == lo && d_sdf) { p.r1 = d_sdf; p.r1_stride = lds; p.r1_mul = sdf_dsc(s, l) / s.scale; p.r1_row = 0; }
-      p.aux0 = b.AB16[l - 1]; p.ld0 = 256; p.aux0_bf16 = 1;
+      p.aux0 = b.A16[l - 1]; p.ld0 = 256; p.aux0_bf16 = 0;
       if (have_n) { p.aux1 = b.ZG16[l - 1]; p.ld1 = 256; p.aux1_bf16 = 1; }
       p.a_out = (l > 1 || d_x) ? 1 : 0; p.a_wr = 256;
       p.o16a = b.ZB16[l - 1]; p.ldo16a = 256; p.o16a_bf16 = 1; p.o16a_mul = sdf_dsc(s, l - 1) * ce::kInvB2;

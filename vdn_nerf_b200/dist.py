@@ -45,6 +45,14 @@ def global_eikonal(eik_num: torch.Tensor, eik_den: torch.Tensor, group=None) -> 
     return eik_num.sum() / (den[0] + 1e-5)
 
 
+def global_sum(x: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of a (detached) scalar over all ranks; identity without an initialised process group."""
+    t = x.detach().reshape(1).clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t[0]
+
+
 class FlatGradAllReduce:
     """All-reduce(sum) of every parameter gradient through one flat fp32 buffer (1.41 M floats = 5.6 MB for
     the womsk_white networks): a single latency-bound collective per step, no bucketing."""

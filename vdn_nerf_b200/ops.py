@@ -15,7 +15,25 @@ from . import _lib
 from ._lib import check, int_array, ptr_array
 
 
+_FLAG = {}          # device index -> (int32 device tensor the tcgen05 kernels raise on a barrier time-out)
+_FLAG_DEV = None    # device whose flag is currently installed in the library
+_POLL = {}          # device index -> (pinned host int32 tensor, CUDA event of the last asynchronous flag copy)
+
+
+def _install_flag(dev: int) -> None:
+    """The fault flag is a torch tensor on the device the kernels run on (the library owns no device memory)."""
+    global _FLAG_DEV
+    if dev not in _FLAG:
+        _FLAG[dev] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", dev))
+    check(_lib.load().vdn_set_fault_flag(ctypes.c_void_p(_FLAG[dev].data_ptr())), "vdn_set_fault_flag")
+    _FLAG_DEV = dev
+
+
 def _stream():
+    """Current stream of the current device; keeps the library's fault flag on that device."""
+    dev = torch.cuda.current_device()
+    if _FLAG_DEV != dev:
+        _install_flag(dev)
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -24,11 +42,16 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def _prep(t: Optional[torch.Tensor], device=None) -> Optional[torch.Tensor]:
-    """Contiguous fp32 CUDA view of `t` (no copy when it already is one)."""
+    """Contiguous fp32 CUDA view of `t` (no copy when it already is one).  Kernels are launched on the CURRENT device's
+    current stream, so a tensor living on another device is an error (torch.cuda.set_device / torch.cuda.device first)."""
     if t is None:
         return None
     if not t.is_cuda:
         raise _lib.VdnLibraryError("vdn_nerf_b200 kernels need CUDA tensors (there is no CPU path); got " + str(t.device))
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.VdnLibraryError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                                   "the kernels launch on the current device's stream; wrap the call in "
+                                   "`with torch.cuda.device(tensor.device):`")
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
@@ -63,8 +86,44 @@ def get_chain() -> bool:
 
 
 def tc_fault() -> int:
-    """Non-zero if a tensor-core kernel hit a barrier time-out since the library was loaded (synchronises)."""
-    return int(_lib.load().vdn_tc_fault())
+    """Non-zero if a tensor-core kernel hit a barrier time-out on the current device since the flag was last reset
+    (synchronises)."""
+    dev = torch.cuda.current_device()
+    if dev not in _FLAG:
+        return 0
+    return int(_FLAG[dev].item())
+
+
+def reset_fault() -> None:
+    dev = torch.cuda.current_device()
+    if dev in _FLAG:
+        _FLAG[dev].zero_()
+
+
+def poll_fault() -> None:
+    """Asynchronous fault check for the training loop: raises if the flag copy enqueued by an EARLIER call shows a
+    barrier time-out, then enqueues a fresh device -> pinned-host copy of the flag on the current stream.  Never
+    synchronises; a fault is therefore reported one call late (call it once per step).  No-op during graph capture."""
+    if not torch.cuda.is_available() or torch.cuda.is_current_stream_capturing():
+        return
+    dev = torch.cuda.current_device()
+    if dev not in _FLAG:
+        return
+    host, ev = _POLL.get(dev, (None, None))
+    if host is not None and ev.query():
+        if int(host[0]) != 0:
+            host[0] = 0
+            _FLAG[dev].zero_()
+            raise _lib.VdnLibraryError("a tcgen05 kernel timed out on a barrier (device fault flag raised): the results of "
+                                       "the previous step(s) are not valid")
+    elif host is not None:
+        return                      # the previous copy is still in flight: do not pile up
+    if host is None:
+        host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        ev = torch.cuda.Event()
+    host.copy_(_FLAG[dev], non_blocking=True)
+    ev.record()
+    _POLL[dev] = (host, ev)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -150,8 +209,14 @@ class PackedMLP:
                                    self._src_ptrs(lambda s: s[1]), self._src_ptrs(lambda s: s[2]), self._rows,
                                    self._rot, self._orot, _p(buf), _stream()), "vdn_mlp_pack")
             self._packed = buf
-            self._key = key
+            # a pack recorded during graph capture has not run: never let an eager call trust that buffer
+            self._key = None if (_FORCE_REPACK or torch.cuda.is_current_stream_capturing()) else key
         return self._packed
+
+    def invalidate(self) -> None:
+        """Forget the cached packed weights (parameters changed in a way the version counters do not see, e.g. through
+        `.data` or by a captured optimiser step)."""
+        self._key = None
 
     def unpack_grads(self, dpacked: torch.Tensor, needs: Sequence[bool]) -> List[Optional[torch.Tensor]]:
         """Packed gradient -> gradients of self.params (same order); weight-norm backward included."""
@@ -355,12 +420,16 @@ class RenderNetHandle:
         self.L = L
         self.in0 = int(ind[0])
         self.ld_in = (self.in0 + 15) // 16 * 16
-        self.mlp = PackedMLP(list(ind[:L]), list(outd[:L]), sources_fn())
+        rot = (ctypes.c_int * 16)()
+        lib.vdn_rendernet_layer_rot(self.cfg, rot)
+        self.mlp = PackedMLP(list(ind[:L]), list(outd[:L]), sources_fn(), rot=list(rot[:L]))
+        # column ranges inside the (rotated) input row [feature | points | view embedding | normals]
         nview = 3 * (1 + 2 * multires_view) if self.mode != 1 else 0
-        self.col_view = (3, 3 + nview) if self.mode != 1 else None
-        self.col_nrm = (3 + nview, 3 + nview + 3) if self.mode != 2 else None
-        nn_ = 3 if self.mode != 2 else 0
-        self.col_feat = (3 + nview + nn_, 3 + nview + nn_ + d_feature)
+        F = d_feature
+        self.col_feat = (0, F)
+        self.col_pts = (F, F + 3)
+        self.col_view = (F + 3, F + 3 + nview) if self.mode != 1 else None
+        self.col_nrm = (F + 3 + nview, F + 3 + nview + 3) if self.mode != 2 else None
 
 
 class _RenderNetFn(torch.autograd.Function):
@@ -404,7 +473,7 @@ class _RenderNetFn(torch.autograd.Function):
         d_points = d_normals = d_view = d_feat = None
         if need_in:
             if ctx.needs_input_grad[1]:
-                d_points = d_cin[:, 0:3]
+                d_points = d_cin[:, h.col_pts[0]: h.col_pts[1]]
             if ctx.needs_input_grad[2] and h.col_nrm is not None:
                 d_normals = d_cin[:, h.col_nrm[0]: h.col_nrm[1]]
             if ctx.needs_input_grad[3] and h.col_view is not None:
@@ -439,7 +508,9 @@ class NerfHandle:
         rot = [0] * L
         if skip >= 0:
             rot[skip + 1] = int(ind[0])      # skip layer input is stored as [hidden | embedding]
-        self.mlp = PackedMLP(list(ind[:L]), list(outd[:L]), sources_fn(), rot=rot)
+        orot = (ctypes.c_int * 16)()
+        lib.vdn_nerf_layer_orot(self.cfg, orot)
+        self.mlp = PackedMLP(list(ind[:L]), list(outd[:L]), sources_fn(), rot=rot, orot=list(orot[:L]))
 
 
 class _NerfFn(torch.autograd.Function):
@@ -567,6 +638,11 @@ class _CompositeFn(torch.autograd.Function):
     def forward(ctx, o, d, mid_z, dists, sdf, nrm, col, feat, sigma_bg, rgb_bg, feat_bg, dists_bg, variance, bg_rgb,
                 cos_anneal):
         lib = _lib.load()
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            # only reachable with n_importance == 0 and differentiable near / far (the up-sampled z are detached,
+            # renderer.py:190, 368): the closed-form backward does not return these two cotangents
+            raise NotImplementedError("gradients with respect to the sample depths (mid_z / dists) are not implemented; "
+                                      "detach near / far or use n_importance > 0")
         o, d, mid_z, dists = _prep(o), _prep(d), _prep(mid_z), _prep(dists)
         B, S = mid_z.shape
         dev = mid_z.device

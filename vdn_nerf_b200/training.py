@@ -23,10 +23,13 @@ def driver_loss(render_out, true_rgb, mask=None, igr_weight=0.1, mask_weight=0.0
     the single-GPU value on the concatenated batch.
     """
     color = render_out["color_fine"]
+    mask_given = mask is not None
     if mask is None:
         mask = torch.ones_like(render_out["weight_sum"])
-    if data_parallel and global_batch is not None:
+    if data_parallel and global_batch is not None and not mask_given:
         mask_sum = float(global_batch) + 1e-5      # use_mask=False: mask == 1 (dpt_runner.py:209); host scalar
+    elif data_parallel:
+        mask_sum = vdist.global_sum(mask.sum()) + 1e-5     # use_mask=True: the normaliser is the global mask count
     else:
         mask_sum = mask.sum() + 1e-5
     color_error = (color - true_rgb) * mask
@@ -50,7 +53,10 @@ def driver_loss(render_out, true_rgb, mask=None, igr_weight=0.1, mask_weight=0.0
 
 def train_step(renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None,
                cos_anneal_ratio=1.0, perturb_overwrite=-1, igr_weight=0.1, grad_sync=None, global_batch=None):
-    """render + loss + backward (+ gradient all-reduce): the unit `train rays/s` counts.  Returns the loss."""
+    """render + loss + backward (+ gradient all-reduce): the unit `train rays/s` counts.  Returns the loss.
+    A barrier time-out of a tensor-core kernel in an earlier step raises here (asynchronous flag poll, no sync)."""
+    from . import ops
+    ops.poll_fault()
     for p in params:
         p.grad = None
     out = renderer.render(rays_o, rays_d, near, far, perturb_overwrite=perturb_overwrite,
@@ -74,7 +80,8 @@ class GraphedTrainStep:
 
     The inputs of every call are copied into static device buffers; parameter tensors must keep their storage
     (in-place optimiser updates); `param.grad` tensors are allocated once, inside the graph's memory pool, and
-    overwritten by each replay.  The weight packing launches are part of the graph (`ops.force_repack`)."""
+    overwritten by each replay (re-attached if `optimizer.zero_grad(set_to_none=True)` dropped them).  The weight
+    packing launches are part of the graph (`ops.force_repack`)."""
 
     def __init__(self, renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None,
                  cos_anneal_ratio=1.0, perturb_overwrite=-1, igr_weight=0.1, warmup=3, grad_sync=None, global_batch=None):
@@ -104,10 +111,18 @@ class GraphedTrainStep:
         finally:
             ops.force_repack(False)
         self.launches_per_replay = ops.launch_count() - c0     # kernels of this library inside the graph
+        self._grads = [p.grad for p in self.params]            # graph-pool tensors every replay writes into
 
     def __call__(self, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None):
         for dst, src in zip(self._static, (rays_o, rays_d, near, far, true_rgb, gt_feats, background_rgb)):
             if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        # an optimiser's zero_grad(set_to_none=True) (the default, as in dpt_runner.py:251) detaches the graph's gradient
+        # tensors from the parameters: put them back, the replay writes into exactly these
+        for p, g in zip(self.params, self._grads):
+            if p.grad is not g:
+                p.grad = g
         self.graph.replay()
+        from . import ops
+        ops.poll_fault()
         return self.loss, self.out
