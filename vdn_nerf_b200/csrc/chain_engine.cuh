@@ -85,6 +85,8 @@ struct Phase {
   void* o16c; int ldo16c; int o16c_bf16;    // another copy of the A values (e.g. the other 16-bit format)
   void* o16b; int ldo16b;                   // second 16-bit output (OP_P1STEP), bf16
   float* o32; int ldo32; int o32_c0, o32_w; float o32_mul; int act;   // fp32 store of act(x) for columns [o32_c0, o32_c0 + o32_w)
+  int o32_vec;           // set by launch(): full groups of that store may use 16-byte accesses
+  int fast;              // set by launch(): regular phase, run_op_fast applies
   float* o32b; int ldo32b; int o32b_c0, o32b_w;                       // second fp32 store of x (no activation), other columns
   const void* tail; int ldt; int tail_w; float tail_mul; int tail_bf16;   // A columns [width, width + tail_w) from here
   const float* r1; int r1_stride; float r1_mul; int r1_row;   // rank-1 term, r1_row in {0, 1}
@@ -145,39 +147,156 @@ __device__ __forceinline__ float softplus2(float t) {
   q = fmaf(q, w, 1.4414016008377075f);
   return fmaf(w, q, fmaxf(t, 0.0f));
 }
-__device__ __forceinline__ uint4 ld16(const void* base, long long m, int ld, int c) {
-  return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + m * ld + c));
+// ---- 16-bit tensors of the chains: TILE-BLOCKED layout ---------------------------------------------------------
+// A [Npad, W] tensor (W a multiple of 8) is stored as [tile = m / 128][column group = c / 8][row = m % 128][8 elements]:
+// the 32 lanes of an epilogue warp (32 consecutive rows, the same eight columns) read or write 512 contiguous bytes with
+// one 16-byte access each - a row-major layout would make every such access touch 32 different lines.  The grouped
+// weight-gradient kernel reads the same tensors through 4-D TMA tensor maps (wgrad16.cuh).
+__host__ __device__ __forceinline__ long long blk_index(long long m, int W, int c) {
+  return (m >> 7) * ((long long)W * 128) + (long long)(c >> 3) * 1024 + (m & 127) * 8 + (c & 7);
 }
-__device__ __forceinline__ void st16(void* base, long long m, int ld, int c, const uint32_t (&p)[4]) {
-  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + m * ld + c) = make_uint4(p[0], p[1], p[2], p[3]);
+// inverse: linear position in the blocked tensor -> (row m, column c); lets pointwise kernels write it coalesced
+__host__ __device__ __forceinline__ void blk_decode(long long idx, int W, long long* m, int* c) {
+  const long long per_tile = (long long)W * 128;
+  const long long tile = idx / per_tile;
+  const int rem = (int)(idx - tile * per_tile);
+  *m = tile * 128 + ((rem & 1023) >> 3);
+  *c = (rem >> 10) * 8 + (rem & 7);
 }
-__device__ __forceinline__ float ld16_one(const void* base, long long idx, int bf16) {
-  const uint16_t h = __ldg(reinterpret_cast<const uint16_t*>(base) + idx);
+__device__ __forceinline__ uint4 ld16(const void* base, long long m, int W, int c) {      // c multiple of 8
+  return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + blk_index(m, W, c)));
+}
+__device__ __forceinline__ void st16(void* base, long long m, int W, int c, const uint32_t (&p)[4]) {
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + blk_index(m, W, c)) = make_uint4(p[0], p[1], p[2], p[3]);
+}
+__device__ __forceinline__ float ld16_one(const void* base, long long m, int W, int c, int bf16) {
+  const uint16_t h = __ldg(reinterpret_cast<const uint16_t*>(base) + blk_index(m, W, c));
   return bf16 ? __uint_as_float((uint32_t)h << 16) : __half2float(__ushort_as_half(h));
 }
+// the 128-byte lines of columns [c0, c0 + 64) of rows m .. m + 31 (a warp's rows) -> L2; issued by lanes 0, 8, 16, 24
+__device__ __forceinline__ void prefetch16(const void* base, long long m, int W, int c0, int wmax, int lane) {
+  if (lane & 7) return;
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    if (c0 + 8 * g < wmax)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(base) + blk_index(m, W, c0 + 8 * g)));
+}
 
-// One phase's element-wise work for one thread: its row m, columns c0 .. c0 + 63 (accumulator values v).
-// `half` selects columns c0 + 32 half .. + 31 (four groups of eight): the accumulator is drained and processed in two
-// halves so that 32 + ~45 registers suffice (a thread of a 576-thread CTA has 96).
+// ---- cold paths, kept out of line so that the per-phase hot loop stays small (the kernel interprets nine epilogue
+// kinds; with everything inlined its hot paths did not fit the instruction cache) ---------------------------------
+__device__ __forceinline__ float apply_act(float t, int act) {
+  if (act == 1) return __frcp_rn(1.0f + ex2f(-1.4426950408889634f * t));      // sigmoid
+  if (act == 2) return fmaxf(t, 0.0f);
+  return t;
+}
+// fp32 side output of eight values, element-wise (ragged ranges, unaligned or strided destinations)
+static __device__ __noinline__ void o32_scalar(float* dst, int ld, int c_first, int w, int act, float mul, long long m, int cg,
+                                               float x0, float x1, float x2, float x3, float x4, float x5, float x6, float x7) {
+  const float x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+  float* op = dst + m * ld;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg + j - c_first;
+    if (c >= 0 && c < w) op[c] = apply_act(x[j], act) * mul;
+  }
+}
+// columns >= width of an A tile: skip-connection tail (from a 16-bit tensor) or zero padding; r is patched in place
+static __device__ __noinline__ void ragged_tail(const Phase& ph, long long m, int cg, float* r, float* r2) {
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg + j;
+    if (c >= ph.width) {
+      const int tcol = c - ph.width;
+      r[j] = (ph.tail && tcol < ph.tail_w) ? ld16_one(ph.tail, m, ph.ldt, tcol, ph.tail_bf16) * ph.tail_mul : 0.0f;
+      if (r2) r2[j] = 0.0f;
+    }
+  }
+}
+
+// Operand / storage formats are fixed per epilogue kind (launch() checks the table against them), so the hot loop has
+// no run-time format branches:            A written   aux0      aux1      o16a      o16c
+//   OP_SOFTPLUS  (SDF forward)            fp16        -         -         fp16      bf16
+//   OP_NSTEP     (SDF normals)            fp16        fp16      -         bf16      -
+//   OP_P1STEP    (SDF backward, phase 1)  bf16        fp16      bf16      bf16      -      (+ o16b bf16, tail bf16)
+//   OP_P2STEP    (SDF backward, phase 2)  bf16        fp16      bf16      bf16      -
+//   OP_RELU / OP_LINEAR (ReLU nets fwd)   fp16        -         -         bf16      -
+//   OP_MASK      (ReLU nets backward)     bf16        bf16      -         bf16      -
+template <int OP> struct OpTraits {
+  static constexpr bool bf16 = (OP == OP_P1STEP || OP == OP_P2STEP || OP == OP_MASK);       // format of the A written
+  static constexpr bool aux0 = (OP == OP_NSTEP || OP == OP_P1STEP || OP == OP_P2STEP || OP == OP_MASK);
+  static constexpr bool aux1 = (OP == OP_P1STEP || OP == OP_P2STEP);
+  static constexpr bool aux0_bf16 = (OP == OP_MASK);
+  static constexpr bool aux1_bf16 = true;
+  static constexpr bool o16a_bf16 = (OP != OP_SOFTPLUS);
+  static constexpr bool o16c_bf16 = true;
+};
+
+// element offset of (row m, column c0 + 32 half) in a tile-blocked tensor of width W; group gi adds gi * 1024
+__device__ __forceinline__ long long blk_base(long long m, int W, int c0, int half) {
+  return (m >> 7) * ((long long)W * 128) + (long long)((c0 >> 3) + 4 * half) * 1024 + (m & 127) * 8;
+}
+
+// raw 16-byte loads of the auxiliary tensors for the four groups of a half (issued well before their use)
 template <int OP>
-__device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], int half, const float* sb, const float* srow,
-                                       long long m, long long N, int c0, uint32_t tA, uint16_t* stash_base) {
-  constexpr bool kBf16 = (OP == OP_P1STEP || OP == OP_P2STEP || OP == OP_MASK);
+__device__ __forceinline__ void load_aux(const Phase& ph, long long m, int c0, int half, uint4 (&q0)[4], uint4 (&q1)[4]) {
+  if (OpTraits<OP>::aux0 && ph.aux0) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux0) + blk_base(m, ph.ld0, c0, half));
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi)
+      if (c0 + 32 * half + 8 * gi < ph.width) q0[gi] = __ldg(p + gi * 128);
+  }
+  if (OpTraits<OP>::aux1 && ph.aux1) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux1) + blk_base(m, ph.ld1, c0, half));
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi)
+      if (c0 + 32 * half + 8 * gi < ph.width) q1[gi] = __ldg(p + gi * 128);
+  }
+}
+__device__ __forceinline__ void unpack8t(const uint4& u, bool bf16, float (&f)[8]) {   // bf16 is a compile-time constant
+  if (bf16) unpack_b8(u, f); else unpack_h8(u, f);
+}
+
+// One phase's element-wise work for one thread: its row m, columns c0 + 32 half .. + 31 (four groups of eight; the
+// accumulator is drained and processed in two halves so that 32 + ~50 registers suffice: a thread of a 576-thread CTA
+// has 96).  q0 / q1 hold the auxiliary operands of this half.
+template <int OP>
+__device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], int half, const uint4 (&q0)[4],
+                                       const uint4 (&q1)[4], const float* sb, const float* srow, long long m, long long N,
+                                       int c0, uint32_t tA, uint16_t* stash_base) {
+  using T = OpTraits<OP>;
   const int ncols = ph.a_out ? ph.a_wr : ph.width;      // columns this phase touches
-  const float r1v = ph.r1 ? ph.r1[m < N ? m * ph.r1_stride : 0] * ph.r1_mul : 0.0f;
-  const float* rr = srow + ph.r1_row * 256;
+  const int width = ph.width;
+  const float dsc = ph.dsc;
   const bool rowok = m < N;
+  const bool has_r1 = ph.r1 != nullptr;
+  const float r1v = (has_r1 && rowok) ? ph.r1[m * ph.r1_stride] * ph.r1_mul : 0.0f;   // padded rows stay exactly zero
+  const float* rr = srow + ph.r1_row * 256;
+  const int cb = c0 + 32 * half;
+  // destinations of this half (tile-blocked 16-bit copies; fp32 row-major side output)
+  uint4* pa = ph.o16a ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16a) + blk_base(m, ph.ldo16a, c0, half)) : nullptr;
+  uint4* pc = ph.o16c ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16c) + blk_base(m, ph.ldo16c, c0, half)) : nullptr;
+  uint4* pb = (OP == OP_P1STEP && ph.o16b)
+                  ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16b) + blk_base(m, ph.ldo16b, c0, half)) : nullptr;
+  const bool o32_on = ph.o32 && rowok;
+  const bool o32b_on = ph.o32b && rowok;
+  float4* pv = (o32_on && ph.o32_vec) ? reinterpret_cast<float4*>(ph.o32 + m * ph.ldo32 + (cb - ph.o32_c0)) : nullptr;
+  const float om = ph.o16a_mul;
 #pragma unroll
   for (int gi = 0; gi < 4; ++gi) {
     const int g = half * 4 + gi;
-    const int cg = c0 + 8 * g;
+    const int cg = cb + 8 * gi;
     if (cg >= ncols) break;
     float x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = fmaf(v[gi][j], ph.dsc, sb[cg + j]);
-    if (ph.r1) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = fmaf(r1v, rr[cg + j], x[j]);
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + cg), b1 = *reinterpret_cast<const float4*>(sb + cg + 4);
+      x[0] = fmaf(v[gi][0], dsc, b0.x); x[1] = fmaf(v[gi][1], dsc, b0.y); x[2] = fmaf(v[gi][2], dsc, b0.z);
+      x[3] = fmaf(v[gi][3], dsc, b0.w); x[4] = fmaf(v[gi][4], dsc, b1.x); x[5] = fmaf(v[gi][5], dsc, b1.y);
+      x[6] = fmaf(v[gi][6], dsc, b1.z); x[7] = fmaf(v[gi][7], dsc, b1.w);
+    }
+    if (has_r1) {
+      const float4 w0 = *reinterpret_cast<const float4*>(rr + cg), w1 = *reinterpret_cast<const float4*>(rr + cg + 4);
+      x[0] = fmaf(r1v, w0.x, x[0]); x[1] = fmaf(r1v, w0.y, x[1]); x[2] = fmaf(r1v, w0.z, x[2]); x[3] = fmaf(r1v, w0.w, x[3]);
+      x[4] = fmaf(r1v, w1.x, x[4]); x[5] = fmaf(r1v, w1.y, x[5]); x[6] = fmaf(r1v, w1.z, x[6]); x[7] = fmaf(r1v, w1.w, x[7]);
     }
     if (OP != OP_STASH && ph.stash_r >= 0) {      // written earlier by this very thread: plain (coherent) load
       const uint4 u = *reinterpret_cast<const uint4*>(stash_base + ((size_t)ph.stash_r * 8 + g) * (512 * 8));
@@ -192,60 +311,26 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
                      pack_h2(v[gi][6], v[gi][7]));
       continue;
     }
-    // fp32 side output of x (final outputs, skip-connection tails)
-    if (ph.o32 && rowok && cg + 8 > ph.o32_c0 && cg < ph.o32_c0 + ph.o32_w) {
-      float* op = ph.o32 + m * ph.ldo32;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg + j - ph.o32_c0;
-        if (c >= 0 && c < ph.o32_w) {
-          float y = x[j];
-          if (ph.act == 1) y = 1.0f / (1.0f + expf(-y));
-          else if (ph.act == 2) y = fmaxf(y, 0.0f);
-          op[c] = y * ph.o32_mul;
-        }
+    // fp32 side outputs of x (final outputs, skip-connection tails)
+    if (o32_on && cg + 8 > ph.o32_c0 && cg < ph.o32_c0 + ph.o32_w) {
+      if (pv && cg >= ph.o32_c0 && cg + 8 <= ph.o32_c0 + ph.o32_w) {      // o32_vec: no activation, unit scale handled below
+        const float mul = ph.o32_mul;
+        pv[2 * gi] = make_float4(x[0] * mul, x[1] * mul, x[2] * mul, x[3] * mul);
+        pv[2 * gi + 1] = make_float4(x[4] * mul, x[5] * mul, x[6] * mul, x[7] * mul);
+      } else {
+        o32_scalar(ph.o32, ph.ldo32, ph.o32_c0, ph.o32_w, ph.act, ph.o32_mul, m, cg, x[0], x[1], x[2], x[3], x[4], x[5], x[6],
+                   x[7]);
       }
     }
-    if (ph.o32b && rowok && cg + 8 > ph.o32b_c0 && cg < ph.o32b_c0 + ph.o32b_w) {
-      float* op = ph.o32b + m * ph.ldo32b;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg + j - ph.o32b_c0;
-        if (c >= 0 && c < ph.o32b_w) op[c] = x[j];
-      }
-    }
+    if (o32b_on && cg + 8 > ph.o32b_c0 && cg < ph.o32b_c0 + ph.o32b_w)
+      o32_scalar(ph.o32b, ph.ldo32b, ph.o32b_c0, ph.o32b_w, 0, 1.0f, m, cg, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
     if (OP == OP_OUT32) continue;
     // ---- the A value (and the optional second output) ----
     float r[8], r2[8];
-    float s_[8];
-    if (OP == OP_NSTEP || OP == OP_P1STEP || OP == OP_P2STEP) {
-      if (cg < ph.width) {
-        float a8[8];
-        unpack8(ld16(ph.aux0, m, ph.ld0, cg), ph.aux0_bf16, a8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);     // softplus'(z) = 1 - 2^-a'
-      }
-    }
+    const bool in = cg < width;
     if (OP == OP_SOFTPLUS) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = softplus2(x[j]);
-    } else if (OP == OP_NSTEP) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = cg < ph.width ? s_[j] * x[j] : 0.0f;
-    } else if (OP == OP_P1STEP) {
-      float d8[8];
-      if (cg < ph.width) unpack8(ld16(ph.aux1, m, ph.ld1, cg), ph.aux1_bf16, d8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        r[j] = cg < ph.width ? s_[j] * x[j] * ph.a_mul : 0.0f;
-        r2[j] = cg < ph.width ? 100.0f * (1.0f - s_[j]) * d8[j] * x[j] : 0.0f;
-      }
-    } else if (OP == OP_P2STEP) {
-      float z8[8];
-      const bool inj = ph.aux1 != nullptr && cg < ph.width;
-      if (inj) unpack8(ld16(ph.aux1, m, ph.ld1, cg), ph.aux1_bf16, z8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = cg < ph.width ? fmaf(s_[j], x[j], inj ? z8[j] : 0.0f) : 0.0f;
     } else if (OP == OP_RELU) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = fmaxf(x[j], 0.0f);
@@ -253,57 +338,212 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = x[j];
     } else if (OP == OP_MASK) {
-      if (ph.aux0 && cg < ph.width) {
+      if (ph.aux0 && in) {
         float h8[8];
-        unpack8(ld16(ph.aux0, m, ph.ld0, cg), ph.aux0_bf16, h8);
+        unpack8t(q0[gi], T::aux0_bf16, h8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = x[j];
       }
+    } else {   // OP_NSTEP / OP_P1STEP / OP_P2STEP: softplus'(z) = 1 - 2^-a' from the saved activation
+      float s_[8];
+      if (in) {
+        float a8[8];
+        unpack8t(q0[gi], T::aux0_bf16, a8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_[j] = 0.0f;
+      }
+      if (OP == OP_NSTEP) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
+      } else if (OP == OP_P1STEP) {
+        float d8[8];
+        if (in) {
+          unpack8t(q1[gi], T::aux1_bf16, d8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d8[j] = 0.0f;
+        }
+        const float am = ph.a_mul;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          r[j] = s_[j] * x[j] * am;
+          r2[j] = 100.0f * (1.0f - s_[j]) * d8[j] * x[j];
+        }
+      } else {
+        float z8[8];
+        if (ph.aux1 && in) {
+          unpack8t(q1[gi], T::aux1_bf16, z8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z8[j] = 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(s_[j], x[j], z8[j]);
+      }
     }
     // ragged edge: columns >= width carry the skip tail or zero padding
-    if (cg + 8 > ph.width) {
+    if (cg + 8 > width) ragged_tail(ph, m, cg, r, OP == OP_P1STEP ? r2 : nullptr);
+    uint32_t p[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg + j;
-        if (c >= ph.width) {
-          const int tcol = c - ph.width;
-          r[j] = (ph.tail && tcol < ph.tail_w) ? ld16_one(ph.tail, m * ph.ldt + tcol, ph.tail_bf16) * ph.tail_mul : 0.0f;
-          if (OP == OP_P1STEP) r2[j] = 0.0f;
+    for (int i = 0; i < 4; ++i) p[i] = T::bf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
+    if (ph.a_out) tc::tmem_st4(tA + (uint32_t)(4 * g), p);
+    if (pa) {
+      if (OP == OP_P2STEP) {               // stored pre-scaled (z-bar * dsc / kB2: the weight gradient's operand)
+        pa[gi * 128] = make_uint4(pack_b2(r[0] * om, r[1] * om), pack_b2(r[2] * om, r[3] * om), pack_b2(r[4] * om, r[5] * om),
+                                  pack_b2(r[6] * om, r[7] * om));
+      } else if (T::o16a_bf16 != T::bf16) {   // fp16 operand in tensor memory, bf16 copy in HBM
+        pa[gi * 128] = make_uint4(pack_b2(r[0], r[1]), pack_b2(r[2], r[3]), pack_b2(r[4], r[5]), pack_b2(r[6], r[7]));
+      } else {
+        pa[gi * 128] = make_uint4(p[0], p[1], p[2], p[3]);
+      }
+    }
+    if (OP == OP_SOFTPLUS && pc)
+      pc[gi * 128] = make_uint4(pack_b2(r[0], r[1]), pack_b2(r[2], r[3]), pack_b2(r[4], r[5]), pack_b2(r[6], r[7]));
+    if (OP == OP_P1STEP && pb)
+      pb[gi * 128] = make_uint4(pack_b2(r2[0], r2[1]), pack_b2(r2[2], r2[3]), pack_b2(r2[4], r2[5]), pack_b2(r2[6], r2[7]));
+  }
+}
+
+// Fast path of run_op for REGULAR phases (Phase::fast, set by launch()): every column of an active warp is a valid output
+// (width a multiple of 64, nothing written beyond it), no fp32 side output, no rank-1 term, no scratch, no skip tail.
+// Most layers are regular; the hot loop then has no per-element predicates at all.
+template <int OP>
+__device__ __forceinline__ void run_op_fast(const Phase& ph, const float (&v)[4][8], int half, const uint4 (&q0)[4],
+                                            const uint4 (&q1)[4], const float* sb, long long m, int c0, uint32_t tA) {
+  using T = OpTraits<OP>;
+  const float dsc = ph.dsc;
+  const int cb = c0 + 32 * half;
+  uint4* pa = ph.o16a ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16a) + blk_base(m, ph.ldo16a, c0, half)) : nullptr;
+  uint4* pc = (OP == OP_SOFTPLUS && ph.o16c)
+                  ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16c) + blk_base(m, ph.ldo16c, c0, half)) : nullptr;
+  uint4* pb = (OP == OP_P1STEP && ph.o16b)
+                  ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16b) + blk_base(m, ph.ldo16b, c0, half)) : nullptr;
+  const float om = ph.o16a_mul, am = ph.a_mul;
+  const bool a_out = ph.a_out != 0;
+  const bool has1 = ph.aux1 != nullptr, has0 = ph.aux0 != nullptr;
+#pragma unroll
+  for (int gi = 0; gi < 4; ++gi) {
+    float x[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + cb + 8 * gi), b1 = *reinterpret_cast<const float4*>(sb + cb + 8 * gi + 4);
+      x[0] = fmaf(v[gi][0], dsc, b0.x); x[1] = fmaf(v[gi][1], dsc, b0.y); x[2] = fmaf(v[gi][2], dsc, b0.z);
+      x[3] = fmaf(v[gi][3], dsc, b0.w); x[4] = fmaf(v[gi][4], dsc, b1.x); x[5] = fmaf(v[gi][5], dsc, b1.y);
+      x[6] = fmaf(v[gi][6], dsc, b1.z); x[7] = fmaf(v[gi][7], dsc, b1.w);
+    }
+    float r[8], r2[8];
+    if (OP == OP_SOFTPLUS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = softplus2(x[j]);
+    } else if (OP == OP_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaxf(x[j], 0.0f);
+    } else if (OP == OP_LINEAR) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = x[j];
+    } else if (OP == OP_MASK) {
+      if (has0) {
+        float h8[8];
+        unpack8t(q0[gi], T::aux0_bf16, h8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = x[j];
+      }
+    } else {
+      float a8[8], s_[8];
+      unpack8t(q0[gi], T::aux0_bf16, a8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);
+      if (OP == OP_NSTEP) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
+      } else if (OP == OP_P1STEP) {
+        float d8[8];
+        unpack8t(q1[gi], T::aux1_bf16, d8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sx = s_[j] * x[j];
+          r[j] = sx * am;
+          r2[j] = 100.0f * d8[j] * (x[j] - sx);          // 100 (1 - S) delta x
+        }
+      } else {
+        if (has1) {
+          float z8[8];
+          unpack8t(q1[gi], T::aux1_bf16, z8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = fmaf(s_[j], x[j], z8[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
         }
       }
     }
     uint32_t p[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = kBf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
-    if (ph.a_out) tc::tmem_st4(tA + (uint32_t)(4 * g), p);
-    if (ph.o16a) {
-      if (ph.o16a_mul != 1.0f || (ph.o16a_bf16 != 0) != kBf16) {
-        uint32_t pm[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          pm[i] = ph.o16a_bf16 ? pack_b2(r[2 * i] * ph.o16a_mul, r[2 * i + 1] * ph.o16a_mul)
-                               : pack_h2(r[2 * i] * ph.o16a_mul, r[2 * i + 1] * ph.o16a_mul);
-        st16(ph.o16a, m, ph.ldo16a, cg, pm);
+    for (int i = 0; i < 4; ++i) p[i] = T::bf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
+    if (a_out) tc::tmem_st4(tA + (uint32_t)(4 * (half * 4 + gi)), p);
+    if (pa) {
+      if (OP == OP_P2STEP) {
+        pa[gi * 128] = make_uint4(pack_b2(r[0] * om, r[1] * om), pack_b2(r[2] * om, r[3] * om), pack_b2(r[4] * om, r[5] * om),
+                                  pack_b2(r[6] * om, r[7] * om));
+      } else if (T::o16a_bf16 != T::bf16) {
+        pa[gi * 128] = make_uint4(pack_b2(r[0], r[1]), pack_b2(r[2], r[3]), pack_b2(r[4], r[5]), pack_b2(r[6], r[7]));
       } else {
-        st16(ph.o16a, m, ph.ldo16a, cg, p);
+        pa[gi * 128] = make_uint4(p[0], p[1], p[2], p[3]);
       }
     }
-    if (ph.o16c) {
-      uint32_t pc[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) pc[i] = ph.o16c_bf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
-      st16(ph.o16c, m, ph.ldo16c, cg, pc);
-    }
-    if (OP == OP_P1STEP && ph.o16b) {
-      uint32_t p2[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) p2[i] = pack_b2(r2[2 * i], r2[2 * i + 1]);
-      st16(ph.o16b, m, ph.ldo16b, cg, p2);
-    }
+    if (OP == OP_SOFTPLUS && pc)
+      pc[gi * 128] = make_uint4(pack_b2(r[0], r[1]), pack_b2(r[2], r[3]), pack_b2(r[4], r[5]), pack_b2(r[6], r[7]));
+    if (OP == OP_P1STEP && pb)
+      pb[gi * 128] = make_uint4(pack_b2(r2[0], r2[1]), pack_b2(r2[2], r2[3]), pack_b2(r2[4], r2[5]), pack_b2(r2[6], r2[7]));
   }
+}
+
+// One (phase, slot) of the epilogue role for one epilogue kind: auxiliary loads of the first half go out before the
+// wait for the accumulator, D is released as soon as its second half sits in registers.
+template <int OP>
+__device__ __forceinline__ bool phase_body(const Phase& ph, bool last, int s, uint32_t tD, uint32_t tA, int c0, long long m,
+                                           long long N, const float* sb, const float* srow, uint16_t* stb, uint32_t bar_d_full,
+                                           uint32_t par, uint32_t bar_d_drained, uint32_t bar_a_ready) {
+  using namespace tc;
+  uint4 q0[4], q1[4];
+  load_aux<OP>(ph, m, c0, 0, q0, q1);
+  const bool ok = mbar_wait(bar_d_full, par);
+  tc_fence_after();
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float v[4][8];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      if (c0 + 32 * half + 8 * gi < ph.n_mma) {
+        tmem_ld8(tD + (uint32_t)(32 * half + 8 * gi), v[gi]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[gi][j] = 0.0f;
+      }
+    }
+    tmem_ld_wait();
+    if (half == 1) {
+      tc_fence_before();
+      mbar_arrive(bar_d_drained);
+      // the slot's next A operand is what it holds already: release the MMA issuer right away
+      if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
+    }
+    if (OP != OP_OUT32 && OP != OP_STASH && ph.fast) {
+      if (c0 < ph.width) run_op_fast<OP>(ph, v, half, q0, q1, sb, m, c0, tA);
+    } else {
+      run_op<OP>(ph, v, half, q0, q1, sb, srow, m, N, c0, tA, stb);
+    }
+    if (half == 0) load_aux<OP>(ph, m, c0, 1, q0, q1);     // second half's operands: in flight during its TMEM load
+  }
+  return ok;
 }
 
 static __global__ void __launch_bounds__(THREADS, 1)
@@ -366,12 +606,10 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
       tc_fence_before();
       mbar_arrive(smem_u32(&a_ready[s]));
     };
-    // this thread's lines of the tensors a phase reads -> L2, one phase ahead
+    // the lines of the tensors a phase reads (this warp's rows and columns) -> L2, one phase ahead
     auto prefetch = [&](const Phase& ph, long long m) {
-      if (ph.aux0 && c0 < ph.width)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(ph.aux0) + m * ph.ld0 + c0));
-      if (ph.aux1 && c0 < ph.width)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(ph.aux1) + m * ph.ld1 + c0));
+      if (ph.aux0) prefetch16(ph.aux0, m, ph.ld0, c0, ph.width, lane);
+      if (ph.aux1) prefetch16(ph.aux1, m, ph.ld1, c0, ph.width, lane);
     };
     if ((long long)blockIdx.x < ntiles) aload(0, blockIdx.x, a.a0, a.a0_ld, a.a0_w);
     if (blockIdx.x + G < ntiles) aload(1, blockIdx.x + G, a.a0, a.a0_ld, a.a0_w);
@@ -387,52 +625,28 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
           const long long m = tile * 128 + row;
           if (!last) {
             prefetch(a.ph[p + 1], m);
-            if (ph.aload && c0 < ph.al_w)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(ph.aload) + m * ph.al_ld + c0));
+            if (ph.aload) prefetch16(ph.aload, m, ph.al_ld, c0, ph.al_w, lane);
           } else {
             const long long tn = tX + (2 + s) * G;
             if (tn < ntiles) {
               prefetch(a.ph[0], tn * 128 + row);
-              if (c0 < a.a0_w)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint16_t*>(a.a0) + (tn * 128 + row) * a.a0_ld + c0));
+              prefetch16(a.a0, tn * 128 + row, a.a0_ld, c0, a.a0_w, lane);
             }
           }
-          ok = mbar_wait(smem_u32(&d_full), dcnt & 1);
-          ++dcnt;
-          tc_fence_after();
           const uint32_t tA = lane_base + 256u + (uint32_t)(s * 128 + hq * 32);
           uint16_t* stb = a.stash ? a.stash + (((size_t)blockIdx.x * 2 + s) * MAX_STASH * 8) * (512 * 8) + (size_t)tid * 8 : nullptr;
-          // the accumulator is drained in two halves of 32 columns; D is released once the second half sits in registers
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            float v[4][8];
-#pragma unroll
-            for (int gi = 0; gi < 4; ++gi) {
-              if (c0 + 32 * half + 8 * gi < ph.n_mma) {
-                tmem_ld8(tD + (uint32_t)(32 * half + 8 * gi), v[gi]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[gi][j] = 0.0f;
-              }
-            }
-            tmem_ld_wait();
-            if (half == 1) {
-              tc_fence_before();
-              mbar_arrive(smem_u32(&d_drained));
-              // the slot's next A operand is what it holds already: release the MMA issuer right away
-              if (!last && !ph.a_out && !ph.aload) mbar_arrive(smem_u32(&a_ready[s]));
-            }
-            switch (ph.op) {
-              case OP_OUT32: run_op<OP_OUT32>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-              case OP_SOFTPLUS: run_op<OP_SOFTPLUS>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-              case OP_NSTEP: run_op<OP_NSTEP>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-              case OP_P1STEP: run_op<OP_P1STEP>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-              case OP_P2STEP: run_op<OP_P2STEP>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-              case OP_RELU: run_op<OP_RELU>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-              case OP_LINEAR: run_op<OP_LINEAR>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-              case OP_STASH: run_op<OP_STASH>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-              default: run_op<OP_MASK>(ph, v, half, sb, sRow, m, a.N, c0, tA, stb); break;
-            }
+          const uint32_t bf = smem_u32(&d_full), bd = smem_u32(&d_drained), ba = smem_u32(&a_ready[s]), par = dcnt & 1;
+          ++dcnt;
+          switch (ph.op) {
+            case OP_OUT32: ok = phase_body<OP_OUT32>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            case OP_SOFTPLUS: ok = phase_body<OP_SOFTPLUS>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            case OP_NSTEP: ok = phase_body<OP_NSTEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            case OP_P1STEP: ok = phase_body<OP_P1STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            case OP_P2STEP: ok = phase_body<OP_P2STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            case OP_RELU: ok = phase_body<OP_RELU>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            case OP_LINEAR: ok = phase_body<OP_LINEAR>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            case OP_STASH: ok = phase_body<OP_STASH>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            default: ok = phase_body<OP_MASK>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
           }
           if (!last) {
             if (ph.a_out) {
@@ -591,6 +805,14 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
   Args a = a_in;
   if (debug_nomix())
     for (int p = 0; p < a.P; ++p) a.ph[p].a_bf16 = a.ph[p].b_bf16 = 0;
+  for (int p = 0; p < a.P; ++p) {
+    Phase& ph = a.ph[p];
+    ph.fast = ((ph.width & 63) == 0 && (!ph.a_out || ph.a_wr == ph.width) && !ph.o32 && !ph.o32b && !ph.r1 && ph.stash_r < 0 &&
+               !ph.tail && ph.op != OP_OUT32 && ph.op != OP_STASH &&
+               (!(ph.op == OP_NSTEP || ph.op == OP_P1STEP || ph.op == OP_P2STEP) || ph.aux0) && (ph.op != OP_P1STEP || ph.aux1))
+                  ? 1 : 0;
+    ph.o32_vec = (ph.o32 && ph.act == 0 && ((uintptr_t)ph.o32 & 15) == 0 && (ph.ldo32 & 3) == 0 && (ph.o32_c0 & 7) == 0) ? 1 : 0;
+  }
   if (a.N <= 0) return 0;
   if (a.P < 1 || a.P > MAX_PHASES || !a.a0 || (a.a0_w & 7) || a.a0_w > 256) return (int)cudaErrorInvalidValue;
   double flops = 0.0, bytes = 0.0;
@@ -602,6 +824,15 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
         (ph.img2_off >= 0 && (ph.img2_off & 255)) || (ph.a_bf16 != ph.b_bf16))
       return (int)cudaErrorInvalidValue;
     if ((ph.op == OP_STASH || ph.stash_r >= 0) && !a.stash) return (int)cudaErrorInvalidValue;
+    {   // storage formats are compiled into the epilogue kinds (OpTraits): the table must agree with them
+      const int op = ph.op;
+      const bool a_bf = (op == OP_P1STEP || op == OP_P2STEP || op == OP_MASK);
+      const bool bad_fmt = (ph.aux0 && (ph.aux0_bf16 != 0) != (op == OP_MASK)) || (ph.aux1 && !ph.aux1_bf16) ||
+                           (ph.o16a && (ph.o16a_bf16 != 0) != (op != OP_SOFTPLUS)) || (ph.o16c && (op != OP_SOFTPLUS || !ph.o16c_bf16)) ||
+                           (ph.o16b && op != OP_P1STEP) || (ph.o16a_mul != 1.0f && op != OP_P2STEP) ||
+                           (ph.a_out && p + 1 < a.P && (a.ph[p + 1].a_bf16 != 0) != a_bf);
+      if (bad_fmt) return (int)cudaErrorInvalidValue;
+    }
     flops += 2.0 * (double)a.N * ph.n_mma * ph.nks * 16 * (ph.img2_off >= 0 ? 2 : 1);
     const double row16 = 2.0 * (double)a.N;
     if (ph.aux0) bytes += row16 * ph.width;

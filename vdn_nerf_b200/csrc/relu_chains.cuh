@@ -27,8 +27,9 @@ static __global__ void rn_extras16_kernel(const float* __restrict__ pts, const f
                                           __half* __restrict__ x16, __nv_bfloat16* __restrict__ xb16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * 64) return;
-  const long long m = idx >> 6;
-  int c = (int)(idx & 63);
+  long long m;
+  int c;
+  ce::blk_decode(idx, 64, &m, &c);      // tile-blocked outputs
   const int nview = (mode != 1) ? 3 * (1 + 2 * L) : 0;
   const int nnrm = (mode != 2) ? 3 : 0;
   float v = 0.0f;
@@ -57,8 +58,9 @@ static __global__ void rn_zlast16_kernel(const float* __restrict__ d_out, const 
                                          long long N, long long Npad, __nv_bfloat16* __restrict__ dst) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * 128) return;
-  const long long m = idx >> 7;
-  const int c = (int)(idx & 127);
+  long long m;
+  int c;
+  ce::blk_decode(idx, 128, &m, &c);
   float v = 0.0f;
   if (m < N && c < w) {
     const float d = d_out[m * w + c], o = out[m * w + c];
@@ -182,9 +184,12 @@ static inline int rn_chain_backward(const RnShape& s, const float* packed, long 
   e = ce::launch(a, st, PROF_CHAIN_TRAIN);
   if (e) return e;
   wg::Builder w(N, dpacked);
-  const int mZL = w.add_map(b.ZL16, 128, 128), mF = w.add_map(b.FB16, 256, 256), mX = w.add_map(b.XB16, 64, 64);
+  const int mZL = w.add_x(b.ZL16, 128, s.d_out), mF = w.add_y(b.FB16, 256, s.F), mX = w.add_y(b.XB16, 64, s.nextra);
   int mH[VDN_MAX_LAYERS], mZ[VDN_MAX_LAYERS];
-  for (int l = 0; l < L - 1; ++l) { mH[l] = w.add_map(b.HB16[l], 256, 256); mZ[l] = w.add_map(b.ZB16[l], 256, 256); }
+  for (int l = 0; l < L - 1; ++l) {
+    mH[l] = w.add_y(b.HB16[l], 256, ly.in_dim[l + 1]);
+    mZ[l] = w.add_x(b.ZB16[l], 256, ly.out_dim[l]);
+  }
   {
     wg::Job* j = w.add_job(s.d_out, ly.in_dim[lo], ly.off_w[lo], ly.in_ld[lo], 1.0f, ly.off_b[lo], 1.0f);
     wg::Builder::add_seg(j, mZL, 0, 1, mH[lo - 1], 0, 1);
@@ -218,8 +223,9 @@ static __global__ void nerf_in16_kernel(const float* __restrict__ pts, const flo
                                         __nv_bfloat16* __restrict__ evb16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * 128) return;
-  const long long m = idx >> 7;
-  const int c = (int)(idx & 127);
+  long long m;
+  int c;
+  ce::blk_decode(idx, 128, &m, &c);
   float v = 0.0f;
   if (m < N) {
     if (c < d_in * (1 + 2 * L)) {
@@ -435,11 +441,11 @@ static inline int nerf_chain_backward(const NerfShape& s, const float* packed, c
   if (e) return e;
   // ---- weight / bias gradients ----
   wg::Builder w(N, dpacked);
-  const int mZO = w.add_map(b.ZO16, 128, 128), mSG = w.add_map(b.SG16, 64, 64), mZV = w.add_map(b.ZV16, 128, 128);
-  const int mZF = w.add_map(b.ZF16, 256, 256), mEV = w.add_map(b.EVB16, 128, 128), mFT = w.add_map(b.FTB16, 256, 256);
-  const int mHV = w.add_map(b.HVB16, 128, 128);
+  const int mZO = w.add_x(b.ZO16, 128, no), mSG = w.add_x(b.SG16, 64, 1), mZV = w.add_x(b.ZV16, 128, s.W / 2);
+  const int mZF = w.add_x(b.ZF16, 256, s.W), mFT = w.add_y(b.FTB16, 256, s.W), mHV = w.add_y(b.HVB16, 128, s.W / 2);
+  const int mEVe = w.add_y(b.EVB16, 128, s.d_e), mEVv = w.add_y(b.EVB16, 128, s.d_ev);   // point / view embedding parts
   int mH[VDN_MAX_LAYERS], mZ[VDN_MAX_LAYERS];
-  for (int l = 0; l < D; ++l) { mH[l] = w.add_map(b.HB16[l], 256, 256); mZ[l] = w.add_map(b.ZB16[l], 256, 256); }
+  for (int l = 0; l < D; ++l) { mH[l] = w.add_y(b.HB16[l], 256, s.W); mZ[l] = w.add_x(b.ZB16[l], 256, s.W); }
   {   // [rgb ; dpt]
     wg::Job* j = w.add_job(no, s.W / 2, ly.off_w[D + 2], ly.in_ld[D + 2], 1.0f, ly.off_b[D + 2], 1.0f);
     wg::Builder::add_seg(j, mZO, 0, 1, mHV, 0, 1);
@@ -448,7 +454,7 @@ static inline int nerf_chain_backward(const NerfShape& s, const float* packed, c
     wg::Job* j = w.add_job(s.W / 2, s.W, ly.off_w[D + 1], ly.in_ld[D + 1], 1.0f, ly.off_b[D + 1], 1.0f);
     wg::Builder::add_seg(j, mZV, 0, 1, mFT, 0, 1);
     wg::Job* j2 = w.add_job(s.W / 2, s.d_ev, ly.off_w[D + 1] + s.W, ly.in_ld[D + 1], 1.0f, -1, 1.0f);
-    wg::Builder::add_seg(j2, mZV, 0, 1, mEV, 96, 1);
+    wg::Builder::add_seg(j2, mZV, 0, 1, mEVv, 96, 1);
   }
   {   // stacked head: feature rows 1 .. W, alpha row 0
     wg::Job* j = w.add_job(s.W, s.W, ly.off_w[D] + ly.in_ld[D], ly.in_ld[D], 1.0f, ly.off_b[D] + 1, 1.0f);
@@ -461,13 +467,13 @@ static inline int nerf_chain_backward(const NerfShape& s, const float* packed, c
   for (int l = D - 1; l >= 0; --l) {
     if (l == 0) {
       wg::Job* j = w.add_job(s.W, s.d_e, ly.off_w[0], ly.in_ld[0], 1.0f, ly.off_b[0], 1.0f);
-      wg::Builder::add_seg(j, mZ[0], 0, 1, mEV, 0, 1);
+      wg::Builder::add_seg(j, mZ[0], 0, 1, mEVe, 0, 1);
     } else {
       wg::Job* j = w.add_job(s.W, s.W, ly.off_w[l], ly.in_ld[l], 1.0f, ly.off_b[l], 1.0f);
       wg::Builder::add_seg(j, mZ[l], 0, 1, mH[l - 1], 0, 1);
       if (s.skip >= 0 && l == s.skip + 1) {
         wg::Job* j2 = w.add_job(s.W, s.d_e, ly.off_w[l] + s.W, ly.in_ld[l], 1.0f, -1, 1.0f);
-        wg::Builder::add_seg(j2, mZ[l], 0, 1, mEV, 0, 1);
+        wg::Builder::add_seg(j2, mZ[l], 0, 1, mEVe, 0, 1);
       }
     }
   }

@@ -3,7 +3,7 @@
 //
 //   reference: SDFNetwork.forward / .gradient (dpt_models/fields.py:72-108) and autograd's double backward through them.
 //
-// Saved tensors (row-major, Npad = N rounded up to 128 rows; "A16" etc. are the names used in DESIGN.md).  The forward
+// Saved tensors (16-bit ones TILE-BLOCKED, chain_engine.cuh; Npad = N rounded up to 128 rows; "A16" etc. are the names used in DESIGN.md).  The forward
 // and the normals pass compute with fp16 operands (10-bit mantissa; the stated <= 2e-3 tolerance on normals needs it), the
 // backward passes with bf16 cotangents (fp32 exponent range) against bf16 hi/lo weight pairs - tcgen05 kind::f16 cannot
 // mix the two formats in one instruction, so the layer inputs are kept in both:
@@ -36,8 +36,9 @@ static __global__ void sdf_embed16_kernel(const float* __restrict__ x, long long
                                           __half* __restrict__ e16, __nv_bfloat16* __restrict__ eb16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * 64) return;
-  const long long m = idx >> 6;
-  const int c = (int)(idx & 63);
+  long long m;
+  int c;
+  ce::blk_decode(idx, 64, &m, &c);      // idx walks the tile-blocked output (chain_engine.cuh)
   float v = 0.0f;
   if (m < N && c < 3 + 6 * L) {
     if (c < 3) {
@@ -58,7 +59,9 @@ static __global__ void sdf_delta_last_kernel(const __half* __restrict__ a16, con
                                              __nv_bfloat16* __restrict__ db16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 columns
   if (idx >= Npad * 32) return;
-  const int c = (int)(idx & 31) * 8;
+  long long m;
+  int c;
+  ce::blk_decode(idx * 8, 256, &m, &c);     // all three tensors are tile-blocked [.., 256]: same position in each
   const uint4 u = *reinterpret_cast<const uint4*>(a16 + idx * 8);
   float a8[8];
   ce::unpack_h8(u, a8);
@@ -79,8 +82,9 @@ static __global__ void sdf_qbar0_kernel(const float* __restrict__ x, long long N
                                         const float* __restrict__ nbar, __nv_bfloat16* __restrict__ q16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * 64) return;
-  const long long m = idx >> 6;
-  const int c = (int)(idx & 63);
+  long long m;
+  int c;
+  ce::blk_decode(idx, 64, &m, &c);
   float v = 0.0f;
   if (m < N && c < 3 + 6 * L) {
     if (c < 3) {
@@ -100,16 +104,18 @@ static __global__ void rows_to_bf16_kernel(const float* __restrict__ src, int ld
                                            long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * ldd) return;
-  const long long m = idx / ldd;
-  const int c = (int)(idx - m * ldd);
+  long long m;
+  int c;
+  ce::blk_decode(idx, ldd, &m, &c);       // dst is tile-blocked [Npad, ldd]
   dst[idx] = __float2bfloat16_rn((src && m < N && c < w) ? src[m * lds + c] * mul : 0.0f);
 }
 static __global__ void rows_to_fp16_kernel(const float* __restrict__ src, int lds, int w, float mul, long long N,
                                            long long Npad, __half* __restrict__ dst, int ldd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * ldd) return;
-  const long long m = idx / ldd;
-  const int c = (int)(idx - m * ldd);
+  long long m;
+  int c;
+  ce::blk_decode(idx, ldd, &m, &c);
   dst[idx] = __float2half_rn((src && m < N && c < w) ? src[m * lds + c] * mul : 0.0f);
 }
 // dst[m, :] = bf16([a[m, 0..wa) | b[m, 0..wb) | 0 ...]) up to ldd columns (null source: zeros), zero rows beyond N
@@ -117,8 +123,9 @@ static __global__ void gather2_bf16_kernel(const float* __restrict__ a, int lda,
                                            int wb, long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * ldd) return;
-  const long long m = idx / ldd;
-  const int c = (int)(idx - m * ldd);
+  long long m;
+  int c;
+  ce::blk_decode(idx, ldd, &m, &c);
   float v = 0.0f;
   if (m < N) {
     if (c < wa) { if (a) v = a[m * lda + c]; }
@@ -130,8 +137,10 @@ static __global__ void gather2_bf16_kernel(const float* __restrict__ a, int lda,
 static __global__ void ones_col_bf16_kernel(long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Npad * ldd) return;
-  const long long m = idx / ldd;
-  dst[idx] = __float2bfloat16_rn((m < N && idx - m * ldd == 0) ? 1.0f : 0.0f);
+  long long m;
+  int c;
+  ce::blk_decode(idx, ldd, &m, &c);
+  dst[idx] = __float2bfloat16_rn((m < N && c == 0) ? 1.0f : 0.0f);
 }
 template <class K, class... A>
 static inline int launch1d(K kern, long long total, cudaStream_t st, A... args) {
@@ -359,18 +368,18 @@ static inline int sdf_chain_backward(const SdfShape& s, const float* packed, con
   // ---- weight and bias gradients: one grouped launch ----
   {
     wg::Builder w(N, dpacked);
-    int mE = w.add_map(b.EB16, 64, 64), mA[VDN_MAX_LAYERS], mD[VDN_MAX_LAYERS], mQ[VDN_MAX_LAYERS + 1], mZ[VDN_MAX_LAYERS];
+    int mE = w.add_y(b.EB16, 64, ly.in_dim[0]), mA[VDN_MAX_LAYERS], mD[VDN_MAX_LAYERS], mQ[VDN_MAX_LAYERS + 1], mZ[VDN_MAX_LAYERS];
     for (int l = 0; l < L - 1; ++l) {
-      mA[l] = w.add_map(b.AB16[l], 256, 256);
-      mZ[l] = w.add_map(b.ZB16[l], 256, 256);
-      if (have_n) mD[l] = w.add_map(b.DB16[l], 256, 256);
+      mA[l] = w.add_y(b.AB16[l], 256, ly.in_dim[l + 1]);
+      mZ[l] = w.add_x(b.ZB16[l], 256, ly.out_dim[l]);
+      if (have_n) mD[l] = w.add_x(b.DB16[l], 256, ly.out_dim[l]);
     }
     if (have_n) {
-      mQ[0] = w.add_map(b.Q16[0], 64, 64);
-      for (int l = 1; l <= L - 1; ++l) mQ[l] = w.add_map(b.Q16[l], 256, 256);
+      mQ[0] = w.add_y(b.Q16[0], 64, ly.in_dim[0]);
+      for (int l = 1; l <= L - 1; ++l) mQ[l] = w.add_y(b.Q16[l], 256, ly.in_dim[l]);
     }
-    const int mF = w.add_map(b.FB16, 256, 256), mS = w.add_map(b.SB, 64, 64);
-    const int mO = have_n ? w.add_map(b.ONESB, 64, 64) : 0;
+    const int mF = w.add_x(b.FB16, 256, nf), mS = w.add_x(b.SB, 64, 1);
+    const int mO = have_n ? w.add_x(b.ONESB, 64, 1) : 0;
     for (int l = 0; l < L - 1; ++l) {     // W-bar_l = [z-bar_l ; delta_l]^T [u_l ; q-bar_l]
       wg::Job* j = w.add_job(ly.out_dim[l], ly.in_dim[l], ly.off_w[l], ly.in_ld[l], 1.0f, ly.off_b[l],
                              ce::kB2 / sdf_dsc(s, l));

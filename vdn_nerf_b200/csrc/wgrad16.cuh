@@ -4,14 +4,18 @@
 //     dW_l[out, in] += scale * sum_p  X_l[p, out] * Y_l[p, in]         (W-bar += z-bar^T u, delta^T q-bar)
 //
 // from the 16-bit operand tensors the chain kernels (chain_engine.cuh) left in HBM: X = a cotangent (bf16) or the
-// normals-pass delta (fp16), Y = the layer input (fp16) or a phase-1 cotangent (bf16), both row-major [points, ld].
+// normals-pass delta, Y = the layer input or a phase-1 cotangent, all bf16 (kind::f16 cannot mix formats), tile-blocked.
 // A "job" is one (layer, output-row block) with up to two (X, Y) segments that share an accumulator
 // (W-bar_l = [z-bar ; delta]^T [u ; q-bar]); the batch is split over the CTAs so that (jobs x splits) fills one wave of
 // the 148 SMs, every CTA streaming its points exactly once:
-//   * operands arrive by TMA TENSOR MAPS (cp.async.bulk.tensor.2d, UTMALDG; 64 x 64 boxes, SWIZZLE_128B, rows beyond N
-//     zero-filled by the TMA unit) - a 64-point stage is 8 boxes = 64 KB, three stages in flight;
-//   * the reduction runs over the points, so both operands are MN-major for tcgen05.mma kind::f16 (fp16 / bf16 mixed
-//     per instruction descriptor), the box image is exactly the canonical MN-major SWIZZLE_128B layout;
+//   * operands arrive by TMA TENSOR MAPS (cp.async.bulk.tensor.4d, UTMALDG) over the tile-blocked 16-bit tensors
+//     ([tile][8-column group][128 rows][8], chain_engine.cuh): one box = 64 points x all needed column groups, so a
+//     64-point stage is two TMA instructions (X and Y, up to 32 KB each), three stages in flight; column groups and
+//     tiles outside a tensor are zero-filled by the TMA unit;
+//   * the reduction runs over the points, so both operands are MN-major for tcgen05.mma kind::f16; the box lands in
+//     shared memory as [column group][64 rows][16 bytes], which is exactly the canonical MN-major NO-SWIZZLE
+//     ("interleaved") operand layout: 8 x 8 core matrices of 128 contiguous bytes, 128 bytes between K groups,
+//     1024 bytes between column groups;
 //   * a 256 x 256 fp32 accumulator (two 128-lane halves x 256 TMEM columns) lives in tensor memory for the whole split
 //     and is added to the packed gradient with red.global.add.v4.f32 (no partial slabs, no reduce launch);
 //   * four warps sum the columns of X from the staged tiles for the bias gradient while the tensor pipe works.
@@ -59,14 +63,14 @@ __device__ __forceinline__ uint32_t idesc_mn(uint32_t M, uint32_t N, int a_bf16,
   return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) |
          ((M >> 4) << 24);
 }
-// MN-major SWIZZLE_128B operand: 64-element (128-byte) chunks of M/N lbo bytes apart, 8-row K groups 1024 bytes apart
-__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major operand without swizzle: core matrices of 8 K-rows x 16 bytes (128 contiguous bytes); the next 8 K-rows are
+// lbo bytes further, the next 8 M/N elements sbo bytes further
+__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)(1024u >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell); layout type 0 = no swizzle
   return d;
 }
 __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -77,9 +81,10 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-               "l"(tm), "r"(x), "r"(y), "r"(bar)
+// box {8 elements, 64 rows, box column groups, 1 tile} at (0, row0, cg0, tile)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int row0, int cg0, int tile, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+               "l"(tm), "r"(0), "r"(row0), "r"(cg0), "r"(tile), "r"(bar)
                : "memory");
 }
 
@@ -93,7 +98,7 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
   const Unit un = a.units[blockIdx.x];
   const Job& jb = a.jobs[un.job];
   const int nchunks = un.c1 - un.c0;
-  const int x_boxes = jb.m_tiles * 2, y_boxes = (jb.n_mma + 63) >> 6;
+  const int x_cg = jb.m_tiles * 16, y_cg = (jb.n_mma + 7) >> 3;     // column groups per stage of X and Y
   const int nit = nchunks * jb.nseg;           // stages to process: chunk-major, segment-minor
 
   if (tid == 0) {
@@ -110,17 +115,15 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
 
   if (tid == 0) {
     // ================= TMA producer =================
-    const uint32_t bytes = (uint32_t)(x_boxes + y_boxes) * 8192u;
+    const uint32_t bytes = (uint32_t)(x_cg + y_cg) * 1024u;
     for (int it = 0; it < nit && ok; ++it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
       const int seg = it % jb.nseg, chunk = un.c0 + it / jb.nseg;
       ok = mbar_wait_backoff(smem_u32(&empty[s]), ph ^ 1, 64);
       const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES, bar = smem_u32(&full[s]);
       mbar_arrive_expect_tx(bar, bytes);
-      const CUtensorMap* xm = &a.maps[jb.xmap[seg]];
-      const CUtensorMap* ym = &a.maps[jb.ymap[seg]];
-      for (int b = 0; b < x_boxes; ++b) tma_load_2d(base + (uint32_t)b * 8192u, xm, jb.xcol[seg] + 64 * b, chunk * 64, bar);
-      for (int b = 0; b < y_boxes; ++b) tma_load_2d(base + 32768u + (uint32_t)b * 8192u, ym, jb.ycol[seg] + 64 * b, chunk * 64, bar);
+      tma_load_4d(base, &a.maps[jb.xmap[seg]], (chunk & 1) * 64, jb.xcol[seg] >> 3, chunk >> 1, bar);
+      tma_load_4d(base + 32768u, &a.maps[jb.ymap[seg]], (chunk & 1) * 64, jb.ycol[seg] >> 3, chunk >> 1, bar);
     }
   } else if (tid == 32) {
     // ================= MMA issuer =================
@@ -134,8 +137,8 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
       for (int mh = 0; mh < jb.m_tiles; ++mh)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_f16_ss(tmem_base + (uint32_t)(mh * 256), desc_mn(base + (uint32_t)(mh * 16384 + ks * 2048), 8192u),
-                      desc_mn(base + 32768u + (uint32_t)(ks * 2048), 8192u), idesc, (it | ks) ? 1u : 0u);
+          umma_f16_ss(tmem_base + (uint32_t)(mh * 256), desc_mn(base + (uint32_t)(mh * 16384 + ks * 256), 128u, 1024u),
+                      desc_mn(base + 32768u + (uint32_t)(ks * 256), 128u, 1024u), idesc, (it | ks) ? 1u : 0u);
       umma_commit(smem_u32(&empty[s]));
     }
     umma_commit(smem_u32(&acc_full));
@@ -151,13 +154,13 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
       // a warp running ahead of the fill would arrive into the wrong barrier phase
       ok = mbar_wait(smem_u32(&full[s]), ph);
       if (ok && want_b && seg == 0 && 2 * t < jb.m_tiles * 128) {
-        const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES + (uint32_t)(t >> 5) * 8192u;
-        const uint32_t u = (uint32_t)(t & 31) >> 2, sub = (uint32_t)(t & 3) * 4u;
+        // X tile in shared memory: [column group][64 rows][16 bytes]; features 2t, 2t+1 = word (t & 3) of group t >> 2
+        const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES + (uint32_t)(t >> 2) * 1024u + (uint32_t)(t & 3) * 4u;
         const bool bf = jb.xbf16[0] != 0;
 #pragma unroll 8
         for (uint32_t k = 0; k < 64; ++k) {
           uint32_t w;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + k * 128u + ((u ^ (k & 7u)) << 4) + sub));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + k * 16u));
           if (bf) {
             bs0 += __uint_as_float(w << 16);
             bs1 += __uint_as_float(w & 0xffff0000u);
@@ -241,20 +244,24 @@ struct Builder {
     memset(&a, 0, sizeof(a));
     a.dpacked = dpacked;
   }
-  // row-major 16-bit tensor [N rows, `cols` valid columns, leading dimension ld elements]
-  int add_map(const void* ptr, int cols, int ld) {
+  // tile-blocked 16-bit tensor of width W (chain_engine.cuh), read with boxes of `box_cg` column groups x 64 rows
+  int add_map(const void* ptr, int W, int box_cg) {
     EncodeTiledFn fn = encode_fn();
-    if (!fn || nmaps >= MAX_MAPS || ((uintptr_t)ptr & 15) || (ld & 7)) { bad = true; return 0; }
-    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)N};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {64, 64};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&a.maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    if (!fn || nmaps >= MAX_MAPS || ((uintptr_t)ptr & 127) || (W & 7) || box_cg < 1 || box_cg > 32) { bad = true; return 0; }
+    const cuuint64_t tiles = (cuuint64_t)((N + 127) / 128);
+    const cuuint64_t dims[4] = {8, 128, (cuuint64_t)(W / 8), tiles};
+    const cuuint64_t strides[3] = {16, 2048, (cuuint64_t)W * 256};
+    const cuuint32_t box[4] = {8, 64, (cuuint32_t)box_cg, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&a.maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { bad = true; return 0; }
     return nmaps++;
   }
+  // X operand of a job with `rows` output rows / Y operand with `cols` output columns
+  int add_x(const void* ptr, int W, int rows) { return add_map(ptr, W, ((rows + 127) / 128) * 16); }
+  int add_y(const void* ptr, int W, int cols) { return add_map(ptr, W, (((cols + 15) & ~15) + 7) / 8); }
   Job* add_job(int rows, int cols, long long dw_off, int dw_ld, float scale, long long db_off, float db_scale) {
     if (njobs >= MAX_JOBS || rows < 1 || rows > 256 || cols < 1 || cols > 256) { bad = true; return &a.jobs[0]; }
     Job* j = &a.jobs[njobs++];
@@ -277,7 +284,7 @@ struct Builder {
     for (int j = 0; j < njobs; ++j) {
       const Job& jb = a.jobs[j];
       if (jb.nseg < 1 || jb.nseg > 2) return (int)cudaErrorInvalidValue;
-      cost[j] = (double)jb.nseg * (jb.m_tiles * 2 + (jb.n_mma + 63) / 64);
+      cost[j] = (double)jb.nseg * (jb.m_tiles * 16 + (jb.n_mma + 7) / 8);
       total += cost[j];
     }
     // splits per job proportional to its bytes, at least one, at most one per 64-point chunk, sum <= number of SMs
