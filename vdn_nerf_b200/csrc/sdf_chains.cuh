@@ -6,9 +6,10 @@
 // Saved tensors (16-bit ones TILE-BLOCKED, chain_engine.cuh; Npad = N rounded up to 128 rows; "A16" etc. are the names used in DESIGN.md).  The forward
 // and the normals pass compute with fp16 operands (10-bit mantissa; the stated <= 2e-3 tolerance on normals needs it), the
 // backward passes with bf16 cotangents (fp32 exponent range) against bf16 hi/lo weight pairs - tcgen05 kind::f16 cannot
-// mix the two formats in one instruction, so the layer inputs are kept in both:
+// mix the two formats in one instruction; HBM copies are bf16 throughout (softplus' recomputed from a bf16 a' is as
+// accurate as from fp16, tests/test_analytic_cpu.py), only the forward's own operands stay fp16 (in tensor memory):
 //   forward blob   E16 / EB16 [Npad, 64] fp16 / bf16   kB2 * embedding (layer-0 input; kB2 = beta / ln2: base-2 softplus units)
-//                  A16_l / AB16_l [Npad,256]           l = 0..L-2: a'_l = kB2 * softplus(z_l); the layer before the skip
+//                  AB16_l [Npad,256] bf16              l = 0..L-2: a'_l = kB2 * softplus(z_l); the layer before the skip
 //                                                      connection holds [a' | kB2 * e] = sqrt2 * kB2 * (skip-layer input)
 //   normals blob   D16L [Npad,256] fp16   delta of the last hidden layer (first operand of the normals chain)
 //                  DB16_l [Npad,256] bf16 delta_l = softplus'(z_l) * d sdf / d h_l  (softplus' = 1 - 2^-a')
@@ -54,7 +55,7 @@ static __global__ void sdf_embed16_kernel(const float* __restrict__ x, long long
 }
 
 // delta of the last hidden layer: D16[m, c] = fp16((1 - 2^-A16[m, c]) * w[c]),  w = first row of the last weight
-static __global__ void sdf_delta_last_kernel(const __half* __restrict__ a16, const float* __restrict__ wrow,
+static __global__ void sdf_delta_last_kernel(const __nv_bfloat16* __restrict__ a16, const float* __restrict__ wrow,
                                              long long Npad, int width, __half* __restrict__ d16,
                                              __nv_bfloat16* __restrict__ db16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 columns
@@ -64,7 +65,7 @@ static __global__ void sdf_delta_last_kernel(const __half* __restrict__ a16, con
   ce::blk_decode(idx * 8, 256, &m, &c);     // all three tensors are tile-blocked [.., 256]: same position in each
   const uint4 u = *reinterpret_cast<const uint4*>(a16 + idx * 8);
   float a8[8];
-  ce::unpack_h8(u, a8);
+  ce::unpack_b8(u, a8);
   uint32_t p[4], pb[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -153,7 +154,6 @@ static inline int launch1d(K kern, long long total, cudaStream_t st, A... args) 
 struct SdfChainBufs {
   long long Npad;
   __half* E16; __nv_bfloat16* EB16;
-  __half* A16[VDN_MAX_LAYERS];
   __nv_bfloat16* AB16[VDN_MAX_LAYERS];
   __half* D16L;
   __nv_bfloat16* DB16[VDN_MAX_LAYERS];
@@ -164,7 +164,7 @@ struct SdfChainBufs {
   __nv_bfloat16* FB16; __nv_bfloat16* SB; __nv_bfloat16* ONESB;
   float* EB; float* ES;
 };
-static inline long long sdf_chain_blob_floats(int L, long long N) { return pad128(N) * (64 + (long long)(L - 1) * 256); }
+static inline long long sdf_chain_blob_floats(int L, long long N) { return pad128(N) * (64 + (long long)(L - 1) * 128); }
 static inline long long sdf_chain_blobg_floats(int L, long long N) { return pad128(N) * (128 + (long long)(L - 1) * 128 + 96); }
 static inline long long sdf_chain_ws_floats(int L, long long N) {
   return pad128(N) * (32 + 3LL * (L - 1) * 128 + 128 + 32 + 32 + 96);
@@ -175,10 +175,7 @@ static inline void sdf_chain_carve(int L, long long N, float* blob, float* blobg
   if (blob) {
     b->E16 = reinterpret_cast<__half*>(blob);
     b->EB16 = reinterpret_cast<__nv_bfloat16*>(blob + Np * 32);
-    for (int l = 0; l < L - 1; ++l) {
-      b->A16[l] = reinterpret_cast<__half*>(blob + Np * 64 + (long long)l * Np * 256);
-      b->AB16[l] = reinterpret_cast<__nv_bfloat16*>(blob + Np * 64 + (long long)l * Np * 256 + Np * 128);
-    }
+    for (int l = 0; l < L - 1; ++l) b->AB16[l] = reinterpret_cast<__nv_bfloat16*>(blob + Np * 64 + (long long)l * Np * 128);
   }
   if (blobg) {
     b->D16L = reinterpret_cast<__half*>(blobg);
@@ -227,10 +224,7 @@ static inline int sdf_chain_forward(const SdfShape& s, const float* packed, cons
     p.op = ce::OP_SOFTPLUS; p.width = ly.out_dim[l]; p.dsc = sdf_dsc(s, l);
     p.bias_off = ly.off_b[l]; p.bias_mul = ce::kB2;
     p.a_out = 1; p.a_wr = 256;
-    if (save) {
-      p.o16a = b.A16[l]; p.ldo16a = 256; p.o16a_bf16 = 0;
-      p.o16c = b.AB16[l]; p.ldo16c = 256; p.o16c_bf16 = 1;
-    }
+    if (save) { p.o16a = b.AB16[l]; p.ldo16a = 256; p.o16a_bf16 = 1; }
     if (l + 1 == s.skip) { p.tail = b.E16; p.ldt = 64; p.tail_w = s.d_e; p.tail_mul = 1.0f; p.tail_bf16 = 0; }
   }
   const int lo = L - 1;
@@ -257,7 +251,7 @@ static inline int sdf_chain_normals(const SdfShape& s, const float* packed, cons
                                     const SdfChainBufs& b, float* normals, cudaStream_t st) {
   const MlpLayout& ly = *s.ly;
   const int L = s.L;
-  int e = launch1d(sdf_delta_last_kernel, b.Npad * 32, st, (const __half*)b.A16[L - 2], packed + ly.off_w[L - 1], b.Npad,
+  int e = launch1d(sdf_delta_last_kernel, b.Npad * 32, st, (const __nv_bfloat16*)b.AB16[L - 2], packed + ly.off_w[L - 1], b.Npad,
                    ly.out_dim[L - 2], b.D16L, b.DB16[L - 2]);
   if (e) return e;
   ce::Args a;
@@ -272,7 +266,7 @@ static inline int sdf_chain_normals(const SdfShape& s, const float* packed, cons
     p.dsc = sdf_dsc(s, l);
     if (l > 0) {
       p.op = ce::OP_NSTEP; p.width = ly.out_dim[l - 1];
-      p.aux0 = b.A16[l - 1]; p.ld0 = 256;
+      p.aux0 = b.AB16[l - 1]; p.ld0 = 256; p.aux0_bf16 = 1;
       p.a_out = 1; p.a_wr = 256;
       p.o16a = b.DB16[l - 1]; p.ldo16a = 256; p.o16a_bf16 = 1;
       if (l == s.skip) { p.o32 = b.DES; p.ldo32 = 48; p.o32_c0 = ly.out_dim[l - 1]; p.o32_w = s.d_e; }
@@ -312,7 +306,7 @@ static inline int sdf_chain_backward(const SdfShape& s, const float* packed, con
       p = ce::make_phase();
       ce::set_mma_bf16(&p, ly.off_ib[l], ly.off_ib2[l], ly.out_ld[l], 0, 0, ly.out_dim[l], ly.in_dim[l]);
       p.op = ce::OP_P1STEP; p.width = ly.out_dim[l];
-      p.aux0 = b.A16[l]; p.ld0 = 256; p.aux0_bf16 = 0; p.aux1 = b.DB16[l]; p.ld1 = 256; p.aux1_bf16 = 1;
+      p.aux0 = b.AB16[l]; p.ld0 = 256; p.aux0_bf16 = 1; p.aux1 = b.DB16[l]; p.ld1 = 256; p.aux1_bf16 = 1;
       p.a_mul = sdf_dsc(s, l + 1);
       p.a_out = l < L - 2 ? 1 : 0; p.a_wr = 256;
       p.o16a = b.Q16[l + 1]; p.ldo16a = 256; p.o16a_bf16 = 1;
@@ -348,7 +342,7 @@ static inline int sdf_chain_backward(const SdfShape& s, const float* packed, con
       ce::set_mma_bf16(&p, ly.off_ibt[l], ly.off_ibt2[l], ly.in_ld[l], 0, 0, ly.in_dim[l], k);
       p.op = ce::OP_P2STEP; p.width = ly.out_dim[l - 1]; p.dsc = sdf_dsc(s, l);
       if (l == lo && d_sdf) { p.r1 = d_sdf; p.r1_stride = lds; p.r1_mul = sdf_dsc(s, l) / s.scale; p.r1_row = 0; }
-      p.aux0 = b.A16[l - 1]; p.ld0 = 256; p.aux0_bf16 = 0;
+      p.aux0 = b.AB16[l - 1]; p.ld0 = 256; p.aux0_bf16 = 1;
       if (have_n) { p.aux1 = b.ZG16[l - 1]; p.ld1 = 256; p.aux1_bf16 = 1; }
       p.a_out = (l > 1 || d_x) ? 1 : 0; p.a_wr = 256;
       p.o16a = b.ZB16[l - 1]; p.ldo16a = 256; p.o16a_bf16 = 1; p.o16a_mul = sdf_dsc(s, l - 1) * ce::kInvB2;
