@@ -308,6 +308,7 @@ def run_ours(args):
     ops.set_precision(args.precision)
     pk = peaks()
     depth = args.workload == "train_wdepth"
+    pose = args.workload == "train_pose"
     conf = configs.CONFIGS["womsk_white_wdepth" if depth else "womsk_white"]
     mods = configs.build_networks(conf, fields, seed=0, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -366,7 +367,7 @@ def run_ours(args):
             line["dtype"] = "f16"
         cpu_kind = "grid"
     else:
-        B = args.rays
+        B = args.rays if args.global_batch <= 0 else max(1, args.global_batch // world)
         rend = NeuSRenderer(*mods, **conf["neus_renderer"])
         params = [p for m in mods if m is not None for p in m.parameters()]
         o, d, near, far = (t.to(dev) for t in vo.synthetic_rays(B, seed=1234 + rank))
@@ -374,9 +375,14 @@ def run_ours(args):
         gt = torch.full((B, 96), 0.5, device=dev) if depth else None
         bg = torch.ones(1, 3, device=dev)
         sync = vdist.FlatGradAllReduce(params) if world > 1 else None
+        if pose:            # BASELINE configs[4]: gradients also reach the rays (stand-in for the so(3) pose refinement)
+            o.requires_grad_(True)
+            d.requires_grad_(True)
 
         def fn(i):
             torch.manual_seed(2 + i)
+            if pose:
+                o.grad = d.grad = None
             train_step(rend, params, o, d, near, far, rgb, gt_feats=gt, background_rgb=bg, cos_anneal_ratio=1.0,
                        grad_sync=sync, global_batch=B * world)
         gstep = None
@@ -390,7 +396,8 @@ def run_ours(args):
             torch.manual_seed(2)
             try:
                 gstep = GraphedTrainStep(rend, params, o, d, near, far, rgb, gt_feats=gt, background_rgb=bg,
-                                         cos_anneal_ratio=1.0, warmup=2, grad_sync=sync, global_batch=B * world)
+                                         cos_anneal_ratio=1.0, warmup=2, grad_sync=sync, global_batch=B * world,
+                                         ray_grads=pose)
                 per_replay = int(gstep.launches_per_replay)
             except Exception as ex:                     # noqa: BLE001 - any capture failure means "run eagerly"
                 print("CUDA graph capture failed, running eagerly: %r" % (ex,), file=sys.stderr)
@@ -434,7 +441,7 @@ def run_ours(args):
             fam[nm] = (msn.value, sp.value, fl.value, by.value)
         lib.vdn_prof_enable(0)
         gemm_ms = sum(v[0] for v in fam.values())
-        alg = alg_flops_per_ray(depth) * B
+        alg = alg_flops_per_ray(depth) * B      # (ray gradients of configs[4] add the small input-gradient GEMMs only)
         ach = alg / (gemm_ms * 1e-3) / 1e12
         tensor_view = {"achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                        "algorithmic_flops_per_step": alg, "executed_flops_per_step": sum(v[2] for v in fam.values()),
@@ -480,8 +487,12 @@ def run_ours(args):
         roof.update(common)
         line.update({"metric": "train_rays_per_s", "unit": "rays/s", "value": value, "ms_per_step": ms / args.steps,
                      "config": {"workload": "womsk_white%s training step (BASELINE configs[%d]): render fwd + driver "
-                                            "loss + bwd%s" % ("_wdepth" if depth else "", 2 if depth else 1,
-                                                              " + NCCL grad all-reduce" if world > 1 else ""),
+                                            "loss + bwd%s%s" % ("_wdepth" if depth else "", 2 if depth else (4 if pose else 1),
+                                                                " incl. ray gradients (learnable poses)" if pose else "",
+                                                                " + NCCL grad all-reduce" if world > 1 else ""),
+                                "fused_chains": bool(ops.get_chain()) and args.precision == "tf32",
+                                "operand_formats": "fp16 forward / normals chains, bf16 backward chains and weight "
+                                                   "gradient, fp32 accumulate" if args.precision == "tf32" else "fp32",
                                 "rays_per_step_per_gpu": B, "global_batch": B * world, "n_samples": 64,
                                 "n_importance": 64, "n_outside": 32, "mode": args.precision, "cuda_graph": bool(gstep),
                                 "l2": "256 MiB flush between timed iterations"},
@@ -516,8 +527,8 @@ def run_ours(args):
                 # the reference's own eager CUDA path on this same GPU; reported, not a target
                 line["reference_cuda_eager"] = reference_cuda_eager(B, depth)
         line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-                     "scaling": "weak", "vs_baseline": None,
-                     "dtype": line.get("dtype", "tf32" if args.precision == "tf32" else "f32"),
+                     "scaling": "strong" if (cpu_kind == "grid" or args.global_batch > 0) else "weak", "vs_baseline": None,
+                     "dtype": line.get("dtype", "bf16" if args.precision == "tf32" else "f32"),
                      "data": "synthetic", "gpu_launches": int(launches), "clocks": clocks})
         order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline",
@@ -534,7 +545,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "train_wdepth", "grid"])
+    ap.add_argument("--workload", default="train", choices=["train", "train_wdepth", "train_pose", "grid"],
+                    help="train: BASELINE configs[1]; train_wdepth: configs[2] (use --global-batch 4096); grid: configs[3]; "
+                         "train_pose: configs[4] (ray gradients; sweep --rays 2048..16384 per GPU)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="total rays per step, split evenly over the ranks (strong scaling); 0: --rays per GPU (weak)")
     ap.add_argument("--rays", type=int, default=512, help="rays per step per GPU")
     ap.add_argument("--resolution", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -183,6 +183,24 @@ int vdn_composite_bwd(long long B, int S, int NB, int F, const float* o, const f
                       float* d_sdf, float* d_nrm, float* d_col, float* d_feat, float* d_sigma_bg, float* d_rgb_bg,
                       float* d_feat_bg, float* d_dists_bg, float* d_var_partial, float* d_dirs, void* stream);
 
+/* ---- callers on either side of the path (SURVEY.md 8(f) "next" rows) ------------------------------------ */
+/* torch.optim.Adam's update (dpt_runner.py:88, 251-253; no weight decay, no amsgrad) for n_tensors parameter tensors in one
+ * launch.  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays of n_tensors entries (<= 96) holding device
+ * pointers and element counts (numel 0 skips a tensor); hyper_dev is a DEVICE array {lr, beta1, beta2, eps, 1 - beta1,
+ * 1 - beta2, then for every tensor i: 1 - beta1^t_i, 1 - beta2^t_i} (torch keeps one step counter per parameter). */
+int vdn_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const int* numel, const float* hyper_dev, void* stream);
+/* Masked L1 colour loss of the driver (dpt_runner.py:228-232): sums[3] = {sum |c - t| m, sum ((c - t) m)^2, sum m},
+ * d_color[B,3] = sign(c - t) m (mask nullable: ones). */
+int vdn_color_loss(const float* color, const float* true_rgb, const float* mask, long long B, float* sums, float* d_color,
+                   void* stream);
+/* Rays of one camera (dpt_models/poses.py:189-212): rays_d = R normalize(Kinv [px, py, 1]), rays_o = t with pose = [R | t]
+ * (3 x 4, device), Kinv 3 x 3 (device); the backward returns the cotangent of the pose (12 floats, overwritten). */
+int vdn_raygen_fwd(const float* px, const float* py, long long B, const float* kinv, const float* pose, float* rays_o,
+                   float* rays_d, void* stream);
+int vdn_raygen_bwd(const float* px, const float* py, long long B, const float* kinv, const float* d_rays_o,
+                   const float* d_rays_d, float* d_pose, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

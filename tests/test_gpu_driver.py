@@ -1,0 +1,235 @@
+"""GPU tests of the rows next to the path and of the parity holes the round-1 review listed:
+fused Adam vs torch.optim.Adam, the colour-loss kernel, device-side ray generation with learnable poses,
+reference-layout checkpoints rendered to parity, render_core_outside staged against the oracle, ray gradients in the
+tensor-core mode, the asynchronous fault poll and the device guard."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vdn_oracle as vo
+from tests import util
+from tests.test_gpu_parity import DEV, _core_loss, make_renderer
+from vdn_nerf_b200 import _lib, configs, driver, fields, ops
+from vdn_nerf_b200.training import driver_loss, train_step
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def white():
+    fx = util.load_fixture("womsk_white")
+    mods, conf = util.build("womsk_white", device=DEV)
+    return fx, mods, conf
+
+
+def test_fused_adam_matches_torch_adam_over_10_steps():
+    g = torch.Generator().manual_seed(0)
+    shapes = [(256, 39), (256,), (217, 256), (1,), (3, 128)]
+    p_ref = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+    p_new = [torch.nn.Parameter(p.detach().clone()) for p in p_ref]
+    opt_ref = torch.optim.Adam(p_ref, lr=5e-4)
+    opt_new = driver.FusedAdam(p_new, lr=5e-4)
+    for it in range(10):
+        lr = 5e-4 * driver.lr_factor(it + 1, 5, 100, 0.05)          # the driver rewrites g['lr'] every step
+        for grp in opt_ref.param_groups:
+            grp["lr"] = lr
+        opt_new.param_groups[0]["lr"] = lr
+        grads = [torch.randn(*s, generator=g).to(DEV) * (0.1 + it) for s in shapes]
+        for a, b, gr in zip(p_ref, p_new, grads):
+            a.grad, b.grad = gr.clone(), gr.clone()
+        if it == 4:
+            p_ref[3].grad = None                                     # a parameter without gradient is skipped
+            p_new[3].grad = None
+        opt_ref.step()
+        opt_new.step()
+    for a, b in zip(p_ref, p_new):
+        assert util.relerr(b, a) < 2e-6
+    sd = opt_new.state_dict()
+    assert set(sd.keys()) == {"state", "param_groups"} and sd["param_groups"][0]["betas"] == (0.9, 0.999)
+    st_ref = opt_ref.state_dict()["state"]
+    assert util.relerr(sd["state"][0]["exp_avg_sq"], st_ref[0]["exp_avg_sq"]) < 2e-6
+
+
+def test_color_loss_kernel_matches_the_driver_formula():
+    g = torch.Generator().manual_seed(1)
+    B = 777
+    color = torch.rand(B, 3, generator=g).to(DEV).requires_grad_(True)
+    rgb = torch.rand(B, 3, generator=g).to(DEV)
+    for mask in (None, (torch.rand(B, 1, generator=g) > 0.4).float().to(DEV)):
+        m = torch.ones(B, 1, device=DEV) if mask is None else mask
+        err = (color - rgb) * m
+        want = torch.nn.functional.l1_loss(err, torch.zeros_like(err), reduction="sum") / (m.sum() + 1e-5)
+        want_psnr = 20.0 * torch.log10(1.0 / (((color - rgb) ** 2 * m).sum() / (m.sum() * 3.0 + 1e-5)).sqrt())
+        (gw,) = torch.autograd.grad(want, color)
+        got, psnr = driver.color_loss(color, rgb, mask)
+        (gg,) = torch.autograd.grad(got, color)
+        assert util.relerr(got, want) < 1e-5 and util.relerr(gg, gw) < 1e-6 and util.relerr(psnr, want_psnr) < 1e-4
+
+
+def test_gpu_ray_generation_and_pose_gradients_match_the_reference_formulas():
+    g = torch.Generator().manual_seed(2)
+    n_img, H, W, B = 3, 48, 64, 500
+    init = torch.eye(4).repeat(n_img, 1, 1)
+    init[:, :3, :3] = torch.stack([driver.so3_exp(torch.randn(3, generator=g) * 0.3) for _ in range(n_img)])
+    init[:, :3, 3] = torch.randn(n_img, 3, generator=g)
+    K = torch.tensor([[60.0, 0, W / 2, 0], [0, 60.0, H / 2, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    images = torch.rand(n_img, H, W, 3, generator=g).to(DEV)
+    masks = torch.ones(n_img, H, W, 3, device=DEV)
+    net = driver.LearnPose(n_img, True, True, init).to(DEV)
+    with torch.no_grad():
+        net.r[1] = torch.tensor([0.02, -0.01, 0.03], device=DEV)
+        net.t[1] = torch.tensor([0.01, 0.02, -0.03], device=DEV)
+    gen = driver.GpuRaysGenerator(images, masks, K.to(DEV), net, learnable=True)
+    gg = torch.Generator(device=DEV).manual_seed(5)
+    o, d, m, c = gen.gen_random_rays_at(1, B, generator=gg)
+    # the reference's arithmetic (poses.py:199-207) in plain torch on the same pixels
+    gg = torch.Generator(device=DEV).manual_seed(5)
+    px = torch.randint(0, W, [B], device=DEV, generator=gg)
+    py = torch.randint(0, H, [B], device=DEV, generator=gg)
+    pose = net(1)
+    p = torch.stack([px, py, torch.ones_like(py)], dim=-1).float()
+    p = torch.matmul(torch.inverse(K.to(DEV))[None, :3, :3], p[:, :, None]).squeeze()
+    v = p / torch.linalg.norm(p, ord=2, dim=-1, keepdim=True)
+    v = torch.matmul(pose[None, :3, :3], v[:, :, None]).squeeze()
+    o_ref = pose[None, :3, 3].expand(v.shape)
+    assert util.relerr(d, v) < 1e-6 and util.relerr(o, o_ref) < 1e-6
+    assert torch.equal(c, images[1][(py, px)])
+    wo, wd = torch.randn(B, 3, generator=g).to(DEV), torch.randn(B, 3, generator=g).to(DEV)
+    gr_ref = torch.autograd.grad((o_ref * wo).sum() + (v * wd).sum(), [net.r, net.t], retain_graph=True)
+    gr_new = torch.autograd.grad((o * wo).sum() + (d * wd).sum(), [net.r, net.t])
+    for a, b in zip(gr_new, gr_ref):
+        assert util.relerr(a, b) < 2e-5
+    near, far = driver.near_far_from_sphere(o, d)
+    assert torch.allclose(far - near, torch.full_like(near, 2.0))
+
+
+def test_reference_layout_checkpoint_round_trip_renders_to_parity(white, tmp_path):
+    """A checkpoint dict with the reference's keys (dpt_runner.py:369-378) and the reference classes' state_dict keys is
+    loaded into freshly constructed (differently seeded) modules of this package, which must then render exactly what
+    the oracle renders from the same weights."""
+    fx, _, conf = white
+    ops.set_precision("fp32")
+    src = configs.build_networks(conf, fields, seed=123)             # "trained" weights: another seed, on the CPU
+    from oracle import stage_ref
+    if stage_ref.available():                                       # key names straight from the reference classes
+        rf, _, _ = stage_ref.import_reference()
+        ref_mods = configs.build_networks(conf, rf, seed=123)
+        for a, b in zip(src, ref_mods):
+            if a is not None:
+                assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+                assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+        src = ref_mods
+    path = str(tmp_path / "ckpt_000123.pth")
+    driver.save_checkpoint(path, src[0], src[1], src[2], src[3], src[4], None, 123)
+    dst = configs.build_networks(conf, fields, seed=7, device=DEV)
+    it = driver.load_checkpoint(path, dst[0], dst[1], dst[2], dst[3], dst[4], map_location=DEV)
+    assert it == 123
+    cpu_mods = configs.build_networks(conf, fields, seed=123)
+    nets = vo.nets_from_modules(*cpu_mods, conf)
+    o, d, near, far = (util.t(fx[k]) for k in ("rays_o", "rays_d", "near", "far"))
+    want = vo.render(nets, o, d, near, far, perturb_overwrite=0, background_rgb=torch.ones(1, 3), cos_anneal_ratio=0.5)
+    rend = make_renderer(dst, conf)
+    with torch.no_grad():
+        got = rend.render(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), perturb_overwrite=0,
+                          background_rgb=torch.ones(1, 3, device=DEV), cos_anneal_ratio=0.5)
+    assert util.relerr(got["color_fine"], want["color_fine"]) < 2e-4
+    assert util.relerr(got["weight_sum"], want["weight_sum"]) < 2e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tf32", 2e-3)])
+def test_render_core_outside_staged_vs_oracle(white, precision, tol):
+    """renderer.py:100-145: alpha, sampled colour and mid-z of the background pass on the golden merged z."""
+    fx, mods, conf = white
+    ops.set_precision(precision)
+    try:
+        rend = make_renderer(mods, conf)
+        o, d = util.t(fx["rays_o"], DEV), util.t(fx["rays_d"], DEV)
+        z_fine, z_bg = util.t(fx["render/fine_z_vals"], DEV), util.t(fx["render/z_vals"], DEV)
+        B = o.shape[0]
+        # merged, sorted sample depths as render() builds them: fine samples followed by the outside samples
+        far = util.t(fx["far"], DEV)
+        _, z_out = rend._coarse_z(util.t(fx["near"], DEV), far, B, 0)
+        z_feed, _ = torch.sort(torch.cat([z_fine, z_out], dim=-1), dim=-1)
+        with torch.no_grad():
+            got = rend.render_core_outside(o, d, z_feed, 2.0 / rend.n_samples, mods[0], background_rgb=None)
+        cpu_mods, _ = util.build("womsk_white")
+        nets = util.oracle_nets(cpu_mods, conf)
+        want = vo.render_core_outside(nets, o.cpu(), d.cpu(), z_feed.cpu(), 2.0 / rend.n_samples)
+        assert util.relerr(got["z_vals"], want["z_vals"]) < 1e-6
+        assert util.relerr(got["z_vals"], fx["render/z_vals"]) < 1e-6       # what render() returns as z_vals
+        assert util.relerr(got["alpha"], want["alpha"]) < tol
+        assert util.relerr(got["sampled_color"], want["sampled_color"]) < tol
+        assert got["weights"].shape == (B, z_feed.shape[1]) and torch.isfinite(got["color"]).all()
+    finally:
+        ops.set_precision("fp32")
+
+
+def test_tf32_ray_gradients_through_render_core(white):
+    """Learnable-pose path (BASELINE cfg 5) in the tensor-core mode: gradients reach the rays through the fused chains."""
+    fx, mods, conf = white
+    ops.set_precision("tf32")
+    try:
+        rend = make_renderer(mods, conf)
+        o, d = util.t(fx["rays_o"], DEV).requires_grad_(True), util.t(fx["rays_d"], DEV).requires_grad_(True)
+        z = util.t(fx["render/fine_z_vals"], DEV)
+        for m in mods:
+            if m is not None:
+                m.zero_grad()
+        core = rend.render_core(o, d, z, 2.0 / rend.n_samples, mods[1], mods[2], mods[3], mods[4],
+                                background_rgb=torch.ones(1, 3, device=DEV), cos_anneal_ratio=0.5)
+        _core_loss(core, o.shape[0], DEV).backward()
+        e_o, e_d = util.relerr(o.grad, fx["core_grad/rays_o"]), util.relerr(d.grad, fx["core_grad/rays_d"])
+        print(f"tensor-core ray gradients: rays_o {e_o:.2e} rays_d {e_d:.2e}")
+        assert e_o < 2e-2 and e_d < 2e-2
+        # and through the full render() with the background field
+        near, far = util.t(fx["near"], DEV), util.t(fx["far"], DEV)
+        o.grad = d.grad = None
+        out = rend.render(o, d, near, far, perturb_overwrite=0, background_rgb=torch.ones(1, 3, device=DEV),
+                          cos_anneal_ratio=0.5)
+        driver_loss(out, torch.full((o.shape[0], 3), 0.5, device=DEV)).backward()
+        assert torch.isfinite(o.grad).all() and torch.isfinite(d.grad).all() and float(d.grad.abs().max()) > 0
+        torch.cuda.synchronize()
+        assert ops.tc_fault() == 0
+    finally:
+        ops.set_precision("fp32")
+
+
+def test_fault_poll_and_device_guard(white):
+    fx, mods, conf = white
+    ops.poll_fault()                 # enqueues a copy
+    torch.cuda.synchronize()
+    ops.poll_fault()                 # reads a clean flag: no raise
+    ops._FLAG[torch.cuda.current_device()].fill_(1)          # simulate a barrier time-out
+    ops.poll_fault()
+    torch.cuda.synchronize()
+    with pytest.raises(_lib.VdnLibraryError):
+        ops.poll_fault()
+    assert ops.tc_fault() == 0       # reported and reset
+    with pytest.raises(_lib.VdnLibraryError):
+        ops.sdf_value(mods[1].handle(), torch.zeros(4, 3))           # CPU tensor: no silent fallback
+
+
+def test_train_loop_with_fused_adam_decreases_the_loss(white):
+    """Ten optimiser-ready steps (render + loss + backward + fused Adam with the driver's schedule) in the tensor-core mode."""
+    fx, _, conf = white
+    ops.set_precision("tf32")
+    try:
+        mods = configs.build_networks(conf, fields, seed=0, device=DEV)
+        rend = make_renderer(mods, conf)
+        params = [p for m in mods if m is not None for p in m.parameters()]
+        opt = driver.FusedAdam(params, lr=5e-4)
+        o, d, near, far = (util.t(fx[k], DEV) for k in ("rays_o", "rays_d", "near", "far"))
+        rgb = torch.full((o.shape[0], 3), 0.5, device=DEV)
+        losses = []
+        for it in range(10):
+            opt.param_groups[0]["lr"] = 5e-4 * driver.lr_factor(it + 50, 5, 1000, 0.05)
+            loss, _ = train_step(rend, params, o, d, near, far, rgb, background_rgb=torch.ones(1, 3, device=DEV),
+                                 cos_anneal_ratio=driver.cos_anneal_ratio(it, 5), perturb_overwrite=0)
+            opt.step()
+            losses.append(float(loss))
+        print("losses", [round(v, 5) for v in losses])
+        assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+        torch.cuda.synchronize()
+        assert ops.tc_fault() == 0
+    finally:
+        ops.set_precision("fp32")

@@ -65,6 +65,10 @@ SIGNATURES = {
     "vdn_bg_prep": (I, [P, P, P, I, P, I, F, L, P, P, P, P]),
     "vdn_composite_fwd": (I, [L, I, I, I] + [P] * 14 + [F] + [P] * 7 + [P]),
     "vdn_composite_bwd": (I, [L, I, I, I] + [P] * 14 + [F] + [P] * 15 + [P]),
+    "vdn_adam_step": (I, [I, P, P, P, P, P, P, P]),
+    "vdn_color_loss": (I, [P, P, P, L, P, P, P]),
+    "vdn_raygen_fwd": (I, [P, P, L, P, P, P, P, P]),
+    "vdn_raygen_bwd": (I, [P, P, L, P, P, P, P, P]),
 }
 
 _lib = None

@@ -62,8 +62,7 @@ extern "C" int vdn_rendernet_layer_dims(const int* cfg, int* in_dims, int* out_d
 extern "C" long long vdn_rendernet_blob_floats(const int* cfg, long long N) {
   RnCfg c;
   if (parse_rn_cfg(cfg, &c)) return -1;
-  const long long a = N * c.ldIn + (long long)(c.L - 1) * N * c.ldH, b = rn_chain_blob_floats(c.L, N);
-  return a > b ? a : b;
+  return rn_chain_ok(c) ? rn_chain_blob_floats(c.L, N) : N * c.ldIn + (long long)(c.L - 1) * N * c.ldH;
 }
 
 // Input-column rotation of the packed layers (layer 0 is stored as [feature | extras]); returns the number of layers.
@@ -120,8 +119,7 @@ extern "C" long long vdn_rendernet_bwd_ws_floats(const int* cfg, long long N) {
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
-  const long long a = 2 * N * c.ldH + N * c.ly.out_ld[c.L - 1] + S * maxw + 256 * maxo + 64, b = rn_chain_ws_floats(c.L, N);
-  return a > b ? a : b;
+  return rn_chain_ok(c) ? rn_chain_ws_floats(c.L, N) : 2 * N * c.ldH + N * c.ly.out_ld[c.L - 1] + S * maxw + 256 * maxo + 64;
 }
 
 // d_out: [N, d_out] contiguous cotangent of the network output; `out` is the forward output.
@@ -260,8 +258,7 @@ extern "C" int vdn_nerf_layer_dims(const int* cfg, int* in_dims, int* out_dims) 
 extern "C" long long vdn_nerf_blob_floats(const int* cfg, long long N) {
   NerfCfg c;
   if (parse_nerf_cfg(cfg, &c)) return -1;
-  const long long a = nerf_blob_floats(c, N), b = nerf_chain_blob_floats(c.D, N);
-  return a > b ? a : b;
+  return nerf_chain_ok(c) ? nerf_chain_blob_floats(c.D, N) : nerf_blob_floats(c, N);
 }
 
 // Output rotation per packed layer for vdn_mlp_pack (the stacked [alpha ; feature] head presents its features first).
@@ -340,10 +337,9 @@ extern "C" long long vdn_nerf_bwd_ws_floats(const int* cfg, long long N) {
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
-  const long long a = 2 * N * c.ldH + N * c.ly.out_ld[c.D] + N * c.ldHV + N * c.ly.out_ld[c.D + 2] + N * c.ldV +
-                      2 * N * c.ldE + S * maxw + 256 * maxo + 64;
-  const long long b = nerf_chain_ws_floats(c.D, N);
-  return a > b ? a : b;
+  if (nerf_chain_ok(c)) return nerf_chain_ws_floats(c.D, N);
+  return 2 * N * c.ldH + N * c.ly.out_ld[c.D] + N * c.ldHV + N * c.ly.out_ld[c.D + 2] + N * c.ldV + 2 * N * c.ldE + S * maxw +
+         256 * maxo + 64;
 }
 
 // d_pts (nullable): [N, d_in]; d_views (nullable): [N, 3].

@@ -147,8 +147,7 @@ extern "C" int vdn_sdf_layer_dims(const int* cfg, int* in_dims, int* out_dims) {
 extern "C" long long vdn_sdf_blob_floats(const int* cfg, long long N, int save) {
   SdfCfg c;
   if (parse_sdf_cfg(cfg, 1.0f, &c)) return -1;
-  const long long a = sdf_blob_floats(c, N, save), b = sdf_chain_blob_floats(c.L, N);   // either path fits
-  return a > b ? a : b;
+  return sdf_chain_ok(c) ? sdf_chain_blob_floats(c.L, N) : sdf_blob_floats(c, N, save);   // layout of the path the calls take
 }
 
 extern "C" int vdn_sdf_layer_orot(const int* cfg, int* orot) {
@@ -162,8 +161,7 @@ extern "C" int vdn_sdf_layer_orot(const int* cfg, int* orot) {
 extern "C" long long vdn_sdf_blobg_floats(const int* cfg, long long N) {
   SdfCfg c;
   if (parse_sdf_cfg(cfg, 1.0f, &c)) return -1;
-  const long long a = sdf_blobg_floats(c, N), b = sdf_chain_blobg_floats(c.L, N);
-  return a > b ? a : b;
+  return sdf_chain_ok(c) ? sdf_chain_blobg_floats(c.L, N) : sdf_blobg_floats(c, N);
 }
 
 static int sdf_forward_impl(const SdfCfg& c, const float* packed, const float* x, long long N, float* sdf, int lds,
@@ -309,10 +307,9 @@ extern "C" long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N) {
     if (w > maxw) maxw = w;
     if (c.ly.out_ld[l] > maxo) maxo = c.ly.out_ld[l];
   }
-  const long long a = 3 * N * c.ldH + (long long)(c.L - 1) * N * c.ldH + N * c.ly.out_ld[c.L - 1] + 3 * N * c.ldE +
-                      S * maxw + 256 * maxo + 64;
-  const long long b = sdf_chain_ws_floats(c.L, N);
-  return a > b ? a : b;
+  if (sdf_chain_ok(c)) return sdf_chain_ws_floats(c.L, N);
+  return 3 * N * c.ldH + (long long)(c.L - 1) * N * c.ldH + N * c.ly.out_ld[c.L - 1] + 3 * N * c.ldE + S * maxw + 256 * maxo +
+         64;
 }
 
 extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed, const float* x, long long N,

@@ -130,6 +130,13 @@ def poll_fault() -> None:
 # Packed parameters
 # ----------------------------------------------------------------------------------------------------
 _FORCE_REPACK = False
+_PARAM_EPOCH = 0        # bumped by in-place parameter updates that bypass autograd's version counters (driver.FusedAdam)
+
+
+def bump_param_epoch() -> None:
+    """Invalidate every packed-weight cache: call after writing parameters through raw pointers."""
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1
 
 
 def force_repack(on: bool) -> None:
@@ -196,7 +203,7 @@ class PackedMLP:
         return ptr_array(ptrs)
 
     def packed(self) -> torch.Tensor:
-        key = tuple((p.data_ptr(), p._version) for p in self.params)
+        key = (_PARAM_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self.params)
         if key != self._key or self._packed is None or _FORCE_REPACK:
             dev = self.params[0].device
             for p in self.params:

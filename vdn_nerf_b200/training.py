@@ -84,16 +84,22 @@ class GraphedTrainStep:
     packing launches are part of the graph (`ops.force_repack`)."""
 
     def __init__(self, renderer, params, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None,
-                 cos_anneal_ratio=1.0, perturb_overwrite=-1, igr_weight=0.1, warmup=3, grad_sync=None, global_batch=None):
+                 cos_anneal_ratio=1.0, perturb_overwrite=-1, igr_weight=0.1, warmup=3, grad_sync=None, global_batch=None,
+                 ray_grads=False):
         from . import ops
         self.params = list(params)
         self._static = [None if t is None else t.detach().clone()
                         for t in (rays_o, rays_d, near, far, true_rgb, gt_feats, background_rgb)]
+        if ray_grads:       # learnable poses (BASELINE cfg 5): the step also back-propagates to the rays
+            self._static[0].requires_grad_(True)
+            self._static[1].requires_grad_(True)
         kw = dict(cos_anneal_ratio=cos_anneal_ratio, perturb_overwrite=perturb_overwrite, igr_weight=igr_weight,
                   grad_sync=grad_sync, global_batch=global_batch)
 
         def run():
             o, d, n, f, rgb, gt, bg = self._static
+            if ray_grads:
+                o.grad = d.grad = None
             return train_step(renderer, self.params, o, d, n, f, rgb, gt_feats=gt, background_rgb=bg, **kw)
 
         side = torch.cuda.Stream()
@@ -112,11 +118,13 @@ class GraphedTrainStep:
             ops.force_repack(False)
         self.launches_per_replay = ops.launch_count() - c0     # kernels of this library inside the graph
         self._grads = [p.grad for p in self.params]            # graph-pool tensors every replay writes into
+        self.ray_grads = (self._static[0].grad, self._static[1].grad) if ray_grads else None
 
     def __call__(self, rays_o, rays_d, near, far, true_rgb, gt_feats=None, background_rgb=None):
-        for dst, src in zip(self._static, (rays_o, rays_d, near, far, true_rgb, gt_feats, background_rgb)):
-            if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
-                dst.copy_(src, non_blocking=True)
+        with torch.no_grad():
+            for dst, src in zip(self._static, (rays_o, rays_d, near, far, true_rgb, gt_feats, background_rgb)):
+                if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
         # an optimiser's zero_grad(set_to_none=True) (the default, as in dpt_runner.py:251) detaches the graph's gradient
         # tensors from the parameters: put them back, the replay writes into exactly these
         for p, g in zip(self.params, self._grads):
