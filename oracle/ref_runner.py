@@ -75,13 +75,14 @@ def run(device: str, rays: int, steps: int, warmup: int, depth: bool, threads: i
     if device == "cuda":
         torch.set_default_tensor_type("torch.FloatTensor")
     mods, rend, params = build(conf, "cpu")
+    rays_cpu = vo.synthetic_rays(rays)               # seeded CPU generator: the same rays as the CUDA arm of bench.py
     if device == "cuda":
         torch.set_default_tensor_type("torch.cuda.FloatTensor")
         mods = tuple(m.cuda() if m is not None else None for m in mods)
         rf, rr, _ = stage_ref.import_reference()
         rend = rr.NeuSRenderer(*mods, **conf["neus_renderer"])
         params = [p for m in mods if m is not None for p in m.parameters()]
-    o, d, near, far = (t.to(device) for t in vo.synthetic_rays(rays))
+    o, d, near, far = (t.to(device) for t in rays_cpu)
     rgb = torch.full((rays, 3), 0.5, device=device)
     gt = torch.full((rays, 96), 0.5, device=device) if depth else None
     bg = torch.ones(1, 3, device=device)

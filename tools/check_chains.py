@@ -82,7 +82,7 @@ def compare(title, ref, got, tol_out, tol_grad, l2_grad):
     return bad
 
 
-def three_way(fn, tol_out=2e-3, tol_grad=1e-2, l2_grad=False, name=""):
+def three_way(fn, tol_out=2e-3, tol_grad=2e-2, l2_grad=False, name=""):
     ops.set_precision("fp32")
     ref = fn()
     ops.set_precision("tf32")

@@ -402,95 +402,123 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
   }
 }
 
-// Fast path of run_op for REGULAR phases (Phase::fast, set by launch()): every column of an active warp is a valid output
-// (width a multiple of 64, nothing written beyond it), no fp32 side output, no rank-1 term, no scratch, no skip tail.
-// Most layers are regular; the hot loop then has no per-element predicates at all.
+// Fast path for REGULAR phases (Phase::fast, set by launch()): every column of an active warp is a valid output (width a
+// multiple of 64, nothing written beyond it), no fp32 side output, no rank-1 term, no scratch, no skip tail - most
+// layers.  The 64 columns of a thread are streamed group by group: eight accumulator values and the 16-byte auxiliary
+// operands of group g + 1 are fetched while group g is computed, so ~80 registers are live and nothing spills (the
+// first version kept 32 + 32 prefetched registers per half and lost a quarter of its issue slots to local-memory
+// traffic).  D is released when the last group has left tensor memory.
 template <int OP>
-__device__ __forceinline__ void run_op_fast(const Phase& ph, const float (&v)[4][8], int half, const uint4 (&q0)[4],
-                                            const uint4 (&q1)[4], const float* sb, long long m, int c0, uint32_t tA) {
+__device__ __forceinline__ void fast_group(const Phase& ph, const float (&v)[8], const uint4& q0, const uint4& q1, const float* sb,
+                                           int g, uint32_t tA, uint4* pa, uint4* pb, float dsc, float om, float am, bool a_out,
+                                           bool has0, bool has1) {
   using T = OpTraits<OP>;
-  const float dsc = ph.dsc;
-  const int cb = c0 + 32 * half;
-  uint4* pa = ph.o16a ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16a) + blk_base(m, ph.ldo16a, c0, half)) : nullptr;
-  uint4* pb = (OP == OP_P1STEP && ph.o16b)
-                  ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16b) + blk_base(m, ph.ldo16b, c0, half)) : nullptr;
-  const float om = ph.o16a_mul, am = ph.a_mul;
-  const bool a_out = ph.a_out != 0;
-  const bool has1 = ph.aux1 != nullptr, has0 = ph.aux0 != nullptr;
+  float x[8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + 8 * g), b1 = *reinterpret_cast<const float4*>(sb + 8 * g + 4);
+    x[0] = fmaf(v[0], dsc, b0.x); x[1] = fmaf(v[1], dsc, b0.y); x[2] = fmaf(v[2], dsc, b0.z); x[3] = fmaf(v[3], dsc, b0.w);
+    x[4] = fmaf(v[4], dsc, b1.x); x[5] = fmaf(v[5], dsc, b1.y); x[6] = fmaf(v[6], dsc, b1.z); x[7] = fmaf(v[7], dsc, b1.w);
+  }
+  float r[8], r2[8];
+  if (OP == OP_SOFTPLUS) {
 #pragma unroll
-  for (int gi = 0; gi < 4; ++gi) {
-    float x[8];
-    {
-      const float4 b0 = *reinterpret_cast<const float4*>(sb + cb + 8 * gi), b1 = *reinterpret_cast<const float4*>(sb + cb + 8 * gi + 4);
-      x[0] = fmaf(v[gi][0], dsc, b0.x); x[1] = fmaf(v[gi][1], dsc, b0.y); x[2] = fmaf(v[gi][2], dsc, b0.z);
-      x[3] = fmaf(v[gi][3], dsc, b0.w); x[4] = fmaf(v[gi][4], dsc, b1.x); x[5] = fmaf(v[gi][5], dsc, b1.y);
-      x[6] = fmaf(v[gi][6], dsc, b1.z); x[7] = fmaf(v[gi][7], dsc, b1.w);
-    }
-    float r[8], r2[8];
-    if (OP == OP_SOFTPLUS) {
+    for (int j = 0; j < 8; ++j) r[j] = softplus2(x[j]);
+  } else if (OP == OP_RELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = softplus2(x[j]);
-    } else if (OP == OP_RELU) {
+    for (int j = 0; j < 8; ++j) r[j] = fmaxf(x[j], 0.0f);
+  } else if (OP == OP_LINEAR) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = fmaxf(x[j], 0.0f);
-    } else if (OP == OP_LINEAR) {
+    for (int j = 0; j < 8; ++j) r[j] = x[j];
+  } else if (OP == OP_MASK) {
+    if (has0) {
+      float h8[8];
+      unpack_b8(q0, h8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
+    } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = x[j];
-    } else if (OP == OP_MASK) {
-      if (has0) {
-        float h8[8];
-        unpack8t(q0[gi], T::aux0_bf16, h8);
+    }
+  } else {
+    float a8[8], s_[8];
+    unpack_b8(q0, a8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
-      } else {
+    for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);          // softplus'(z) = 1 - 2^-a'
+    if (OP == OP_NSTEP) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = x[j];
+      for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
+    } else if (OP == OP_P1STEP) {
+      float d8[8];
+      unpack_b8(q1, d8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sx = s_[j] * x[j];
+        r[j] = sx * am;
+        r2[j] = 100.0f * d8[j] * (x[j] - sx);          // 100 (1 - S) delta x
       }
     } else {
-      float a8[8], s_[8];
-      unpack8t(q0[gi], T::aux0_bf16, a8);
+      if (has1) {
+        float z8[8];
+        unpack_b8(q1, z8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);
-      if (OP == OP_NSTEP) {
+        for (int j = 0; j < 8; ++j) r[j] = fmaf(s_[j], x[j], z8[j]);
+      } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
-      } else if (OP == OP_P1STEP) {
-        float d8[8];
-        unpack8t(q1[gi], T::aux1_bf16, d8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float sx = s_[j] * x[j];
-          r[j] = sx * am;
-          r2[j] = 100.0f * d8[j] * (x[j] - sx);          // 100 (1 - S) delta x
-        }
-      } else {
-        if (has1) {
-          float z8[8];
-          unpack8t(q1[gi], T::aux1_bf16, z8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = fmaf(s_[j], x[j], z8[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
-        }
       }
     }
+  }
+  if (a_out) {
     uint32_t p[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) p[i] = T::bf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
-    if (a_out) tc::tmem_st4(tA + (uint32_t)(4 * (half * 4 + gi)), p);
-    if (pa) {
-      if (OP == OP_P2STEP) {
-        pa[gi * 128] = make_uint4(pack_b2(r[0] * om, r[1] * om), pack_b2(r[2] * om, r[3] * om), pack_b2(r[4] * om, r[5] * om),
-                                  pack_b2(r[6] * om, r[7] * om));
-      } else if (T::o16a_bf16 != T::bf16) {
-        pa[gi * 128] = make_uint4(pack_b2(r[0], r[1]), pack_b2(r[2], r[3]), pack_b2(r[4], r[5]), pack_b2(r[6], r[7]));
-      } else {
-        pa[gi * 128] = make_uint4(p[0], p[1], p[2], p[3]);
-      }
+    tc::tmem_st4(tA + (uint32_t)(4 * g), p);
+    if (pa && T::bf16 && OP != OP_P2STEP) pa[g * 128] = make_uint4(p[0], p[1], p[2], p[3]);
+  }
+  if (pa && (!a_out || !T::bf16 || OP == OP_P2STEP)) {
+    const float o = OP == OP_P2STEP ? om : 1.0f;          // phase 2 stores z-bar pre-scaled for the weight gradient
+    pa[g * 128] = make_uint4(pack_b2(r[0] * o, r[1] * o), pack_b2(r[2] * o, r[3] * o), pack_b2(r[4] * o, r[5] * o),
+                             pack_b2(r[6] * o, r[7] * o));
+  }
+  if (OP == OP_P1STEP && pb)
+    pb[g * 128] = make_uint4(pack_b2(r2[0], r2[1]), pack_b2(r2[2], r2[3]), pack_b2(r2[4], r2[5]), pack_b2(r2[6], r2[7]));
+}
+
+template <int OP>
+__device__ __forceinline__ void fast_phase(const Phase& ph, bool last, uint32_t tD, uint32_t tA, int c0, long long m,
+                                           const float* sb, uint32_t bar_d_full, uint32_t par, uint32_t bar_d_drained,
+                                           uint32_t bar_a_ready, bool* ok) {
+  using namespace tc;
+  using T = OpTraits<OP>;
+  const bool has0 = T::aux0 && ph.aux0 != nullptr, has1 = T::aux1 && ph.aux1 != nullptr;
+  const uint4* p0 = has0 ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux0) + blk_base(m, ph.ld0, c0, 0)) : nullptr;
+  const uint4* p1 = has1 ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux1) + blk_base(m, ph.ld1, c0, 0)) : nullptr;
+  uint4* pa = ph.o16a ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16a) + blk_base(m, ph.ldo16a, c0, 0)) : nullptr;
+  uint4* pb = (OP == OP_P1STEP && ph.o16b)
+                  ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16b) + blk_base(m, ph.ldo16b, c0, 0)) : nullptr;
+  const float dsc = ph.dsc, om = ph.o16a_mul, am = ph.a_mul;
+  const bool a_out = ph.a_out != 0;
+  uint4 qa[2], qb[2];
+  qa[0] = qa[1] = qb[0] = qb[1] = make_uint4(0u, 0u, 0u, 0u);
+  if (has0) qa[0] = __ldg(p0);
+  if (has1) qb[0] = __ldg(p1);
+  *ok = mbar_wait(bar_d_full, par);
+  tc_fence_after();
+  float v[2][8];
+  tmem_ld8(tD, v[0]);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    tmem_ld_wait();                                   // group g has arrived in v[g & 1]
+    if (g < 7) {
+      tmem_ld8(tD + (uint32_t)(8 * (g + 1)), v[(g + 1) & 1]);
+      if (has0) qa[(g + 1) & 1] = __ldg(p0 + (g + 1) * 128);
+      if (has1) qb[(g + 1) & 1] = __ldg(p1 + (g + 1) * 128);
+    } else {
+      tc_fence_before();
+      mbar_arrive(bar_d_drained);                     // the accumulator has left tensor memory
+      if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
     }
-    if (OP == OP_P1STEP && pb)
-      pb[gi * 128] = make_uint4(pack_b2(r2[0], r2[1]), pack_b2(r2[2], r2[3]), pack_b2(r2[4], r2[5]), pack_b2(r2[6], r2[7]));
+    fast_group<OP>(ph, v[g & 1], qa[g & 1], qb[g & 1], sb + c0, g, tA, pa, pb, dsc, om, am, a_out, has0, has1);
   }
 }
 
@@ -501,6 +529,17 @@ __device__ __forceinline__ bool phase_body(const Phase& ph, bool last, int s, ui
                                            long long N, const float* sb, const float* srow, uint16_t* stb, uint32_t bar_d_full,
                                            uint32_t par, uint32_t bar_d_drained, uint32_t bar_a_ready) {
   using namespace tc;
+  if (OP != OP_OUT32 && OP != OP_STASH && ph.fast) {
+    bool ok = true;
+    if (c0 < ph.width) {
+      fast_phase<OP>(ph, last, tD, tA, c0, m, sb, bar_d_full, par, bar_d_drained, bar_a_ready, &ok);
+    } else {                     // this warp's columns are not outputs of the phase: keep the barrier protocol in step
+      ok = mbar_wait(bar_d_full, par);
+      mbar_arrive(bar_d_drained);
+      if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
+    }
+    return ok;
+  }
   uint4 q0[4], q1[4];
   load_aux<OP>(ph, m, c0, 0, q0, q1);
   const bool ok = mbar_wait(bar_d_full, par);
@@ -524,11 +563,7 @@ __device__ __forceinline__ bool phase_body(const Phase& ph, bool last, int s, ui
       // the slot's next A operand is what it holds already: release the MMA issuer right away
       if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
     }
-    if (OP != OP_OUT32 && OP != OP_STASH && ph.fast) {
-      if (c0 < ph.width) run_op_fast<OP>(ph, v, half, q0, q1, sb, m, c0, tA);
-    } else {
-      run_op<OP>(ph, v, half, q0, q1, sb, srow, m, N, c0, tA, stb);
-    }
+    run_op<OP>(ph, v, half, q0, q1, sb, srow, m, N, c0, tA, stb);
     if (half == 0) load_aux<OP>(ph, m, c0, 1, q0, q1);     // second half's operands: in flight during its TMEM load
   }
   return ok;

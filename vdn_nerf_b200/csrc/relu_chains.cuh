@@ -25,48 +25,49 @@ struct RnShape {
 static __global__ void rn_extras16_kernel(const float* __restrict__ pts, const float* __restrict__ nrm,
                                           const float* __restrict__ view, int L, int mode, long long N, long long Npad,
                                           __half* __restrict__ x16, __nv_bfloat16* __restrict__ xb16) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * 64) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * 8) return;
   long long m;
-  int c;
-  ce::blk_decode(idx, 64, &m, &c);      // tile-blocked outputs
+  int c0;
+  ce::blk_decode(i * 8, 64, &m, &c0);
   const int nview = (mode != 1) ? 3 * (1 + 2 * L) : 0;
   const int nnrm = (mode != 2) ? 3 : 0;
-  float v = 0.0f;
-  if (m < N && c < 3 + nview + nnrm) {
-    if (c < 3) {
-      v = pts[m * 3 + c];
-    } else if (c < 3 + nview) {
-      c -= 3;
-      if (c < 3) {
-        v = view[m * 3 + c];
-      } else {
-        const int k = (c - 3) / 6, rem = (c - 3) - 6 * k, j = rem % 3;
-        const float y = view[m * 3 + j] * (float)(1 << k);
-        v = rem < 3 ? sinf(y) : cosf(y);
-      }
-    } else {
-      v = nrm[m * 3 + (c - 3 - nview)];
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float r = 0.0f;
+    if (m < N && c < 3 + nview + nnrm) {
+      if (c < 3) r = pts[m * 3 + c];
+      else if (c < 3 + nview) r = embed_col(view + m * 3, 3, L, c - 3, 1.0f);
+      else r = nrm[m * 3 + (c - 3 - nview)];
     }
+    v[j] = r;
   }
-  x16[idx] = __float2half_rn(v);
-  xb16[idx] = __float2bfloat16_rn(v);
+  store8_h(x16, i, v);
+  store8_b(xb16, i, v);
 }
 
 // ZL16[m, c] = bf16(d_out[m, c] * act'(out[m, c])) for c < w, zero padded to 128 columns.  kind 0: sigmoid, 1: relu
 static __global__ void rn_zlast16_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int w, int kind,
                                          long long N, long long Npad, __nv_bfloat16* __restrict__ dst) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * 128) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * 16) return;
   long long m;
-  int c;
-  ce::blk_decode(idx, 128, &m, &c);
-  float v = 0.0f;
-  if (m < N && c < w) {
-    const float d = d_out[m * w + c], o = out[m * w + c];
-    v = kind == 0 ? d * ((1.0f - o) * o) : (o > 0.0f ? d : 0.0f);
+  int c0;
+  ce::blk_decode(i * 8, 128, &m, &c0);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float r = 0.0f;
+    if (m < N && c < w) {
+      const float d = d_out[m * w + c], o = out[m * w + c];
+      r = kind == 0 ? d * ((1.0f - o) * o) : (o > 0.0f ? d : 0.0f);
+    }
+    v[j] = r;
   }
-  dst[idx] = __float2bfloat16_rn(v);
+  store8_b(dst, i, v);
 }
 
 struct RnChainBufs {
@@ -104,12 +105,10 @@ static inline int rn_chain_forward(const RnShape& s, const float* packed, const 
                                    const RnChainBufs& b, cudaStream_t st) {
   const MlpLayout& ly = *s.ly;
   const int L = s.L;
-  int e = launch1d(rn_extras16_kernel, b.Npad * 64, st, points, normals, view_dirs, s.multires_view, s.mode, N, b.Npad, b.X16,
+  int e = launch1d(rn_extras16_kernel, b.Npad * 8, st, points, normals, view_dirs, s.multires_view, s.mode, N, b.Npad, b.X16,
                    b.XB16);
   if (e) return e;
-  e = launch1d(rows_to_fp16_kernel, b.Npad * 256, st, feats, ldf, s.F, 1.0f, N, b.Npad, b.F16, 256);
-  if (e) return e;
-  e = launch1d(rows_to_bf16_kernel, b.Npad * 256, st, feats, ldf, s.F, 1.0f, N, b.Npad, b.FB16, 256);
+  e = launch1d(rows_to_16_kernel, b.Npad * 32, st, feats, ldf, s.F, 1.0f, N, b.Npad, b.F16, b.FB16, 256);   // one read, both formats
   if (e) return e;
   ce::Args a;
   ce::init_args(&a);
@@ -148,7 +147,7 @@ static inline int rn_chain_backward(const RnShape& s, const float* packed, long 
                                     const float* out, const float* d_out, float* dpacked, float* d_cin, cudaStream_t st) {
   const MlpLayout& ly = *s.ly;
   const int L = s.L, lo = L - 1;
-  int e = launch1d(rn_zlast16_kernel, b.Npad * 128, st, d_out, out, s.d_out, s.squeeze_out ? 0 : 1, N, b.Npad, b.ZL16);
+  int e = launch1d(rn_zlast16_kernel, b.Npad * 16, st, d_out, out, s.d_out, s.squeeze_out ? 0 : 1, N, b.Npad, b.ZL16);
   if (e) return e;
   ce::Args a;
   ce::init_args(&a);
@@ -221,34 +220,24 @@ struct NerfShape {
 static __global__ void nerf_in16_kernel(const float* __restrict__ pts, const float* __restrict__ views, int d_in, int L,
                                         int Lv, long long N, long long Npad, __half* __restrict__ ev16,
                                         __nv_bfloat16* __restrict__ evb16) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * 128) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * 16) return;
   long long m;
-  int c;
-  ce::blk_decode(idx, 128, &m, &c);
-  float v = 0.0f;
-  if (m < N) {
-    if (c < d_in * (1 + 2 * L)) {
-      if (c < d_in) {
-        v = pts[m * d_in + c];
-      } else {
-        const int k = (c - d_in) / (2 * d_in), rem = (c - d_in) - 2 * d_in * k, j = rem % d_in;
-        const float y = pts[m * d_in + j] * (float)(1 << k);
-        v = rem < d_in ? sinf(y) : cosf(y);
-      }
-    } else if (c >= 96 && c - 96 < 3 * (1 + 2 * Lv)) {
-      const int cc = c - 96;
-      if (cc < 3) {
-        v = views[m * 3 + cc];
-      } else {
-        const int k = (cc - 3) / 6, rem = (cc - 3) - 6 * k, j = rem % 3;
-        const float y = views[m * 3 + j] * (float)(1 << k);
-        v = rem < 3 ? sinf(y) : cosf(y);
-      }
+  int c0;
+  ce::blk_decode(i * 8, 128, &m, &c0);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float r = 0.0f;
+    if (m < N) {
+      if (c < 96) r = embed_col(pts + m * d_in, d_in, L, c, 1.0f);
+      else r = embed_col(views + m * 3, 3, Lv, c - 96, 1.0f);
     }
+    v[j] = r;
   }
-  ev16[idx] = __float2half_rn(v);
-  evb16[idx] = __float2bfloat16_rn(v);
+  store8_h(ev16, i, v);
+  store8_b(evb16, i, v);
 }
 
 struct NerfChainBufs {
@@ -297,7 +286,7 @@ static inline int nerf_chain_forward(const NerfShape& s, const float* packed, co
                                      cudaStream_t st) {
   const MlpLayout& ly = *s.ly;
   const int D = s.D;
-  int e = launch1d(nerf_in16_kernel, b.Npad * 128, st, pts, views, s.d_in, s.multires, s.multires_view, N, b.Npad, b.EV16,
+  int e = launch1d(nerf_in16_kernel, b.Npad * 16, st, pts, views, s.d_in, s.multires, s.multires_view, N, b.Npad, b.EV16,
                    b.EVB16);
   if (e) return e;
   ce::Args a;
@@ -368,10 +357,10 @@ static inline int nerf_chain_backward(const NerfShape& s, const float* packed, c
   const MlpLayout& ly = *s.ly;
   const int D = s.D;
   const int no = s.rgb_dims + s.dpt_dim;
-  int e = launch1d(gather2_bf16_kernel, b.Npad * 128, st, d_rgb, s.rgb_dims, s.rgb_dims, s.dpt_dim > 0 ? d_dpt : nullptr,
+  int e = launch1d(gather2_bf16_kernel, b.Npad * 16, st, d_rgb, s.rgb_dims, s.rgb_dims, s.dpt_dim > 0 ? d_dpt : nullptr,
                    s.dpt_dim, s.dpt_dim, N, b.Npad, b.ZO16, 128);
   if (e) return e;
-  e = launch1d(rows_to_bf16_kernel, b.Npad * 64, st, d_sigma, 1, 1, 1.0f, N, b.Npad, b.SG16, 64);
+  e = launch1d(rows_to_16_kernel, b.Npad, st, d_sigma, 1, 1, 1.0f, N, b.Npad, (__half*)nullptr, b.SG16, 8);
   if (e) return e;
   ce::Args a;
   ce::init_args(&a);
@@ -441,7 +430,7 @@ static inline int nerf_chain_backward(const NerfShape& s, const float* packed, c
   if (e) return e;
   // ---- weight / bias gradients ----
   wg::Builder w(N, dpacked);
-  const int mZO = w.add_x(b.ZO16, 128, no), mSG = w.add_x(b.SG16, 64, 1), mZV = w.add_x(b.ZV16, 128, s.W / 2);
+  const int mZO = w.add_x(b.ZO16, 128, no), mSG = w.add_x(b.SG16, 8, 1), mZV = w.add_x(b.ZV16, 128, s.W / 2);
   const int mZF = w.add_x(b.ZF16, 256, s.W), mFT = w.add_y(b.FTB16, 256, s.W), mHV = w.add_y(b.HVB16, 128, s.W / 2);
   const int mEVe = w.add_y(b.EVB16, 128, s.d_e), mEVv = w.add_y(b.EVB16, 128, s.d_ev);   // point / view embedding parts
   int mH[VDN_MAX_LAYERS], mZ[VDN_MAX_LAYERS];

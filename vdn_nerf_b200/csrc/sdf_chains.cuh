@@ -16,7 +16,7 @@
 //                  DE0, DES [Npad,48] fp32  d sdf / d e through layer 0 and through the skip connection
 //   backward ws    Q16_0 [Npad,64], Q16_l [Npad,256] bf16  q-bar_l (phase 1);  ZG16_l bf16 injected cotangents;
 //                  ZB16_l bf16  z-bar_l * (dsc_l / kB2)  (phase 2; pre-scaled so that ZB^T AB16 = z-bar^T u);
-//                  FB16 [Npad,256] bf16 feature cotangent; SB / ONESB [Npad,64] bf16 (column 0: d_sdf / kB2, ones)
+//                  FB16 [Npad,256] bf16 feature cotangent; SB / ONESB [Npad,8] bf16 (column 0: d_sdf / kB2, ones)
 // Nothing else of a layer reaches HBM: softplus'(z) and softplus''(z) * a are recomputed from A16 / AB16 and DB16.
 #pragma once
 #include "chain_engine.cuh"
@@ -32,116 +32,138 @@ extern int g_chain;    // api.cu: fused training chains enabled (tensor-core mod
 inline long long pad128(long long n) { return (n + 127) / 128 * 128; }
 
 // ---- pointwise producers of the 16-bit chain inputs -----------------------------------------------------
-// E16[m, c] = fp16(kB2 * e_c(x * scale)), zero beyond d_e and beyond row N  (embedder.py:15-36, d = 3)
-static __global__ void sdf_embed16_kernel(const float* __restrict__ x, long long N, long long Npad, int L, float scale,
-                                          __half* __restrict__ e16, __nv_bfloat16* __restrict__ eb16) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * 64) return;
-  long long m;
-  int c;
-  ce::blk_decode(idx, 64, &m, &c);      // idx walks the tile-blocked output (chain_engine.cuh)
-  float v = 0.0f;
-  if (m < N && c < 3 + 6 * L) {
-    if (c < 3) {
-      v = x[m * 3 + c] * scale;
-    } else {
-      const int k = (c - 3) / 6, rem = (c - 3) - 6 * k, j = rem % 3;
-      const float y = x[m * 3 + j] * scale * (float)(1 << k);
-      v = rem < 3 ? sinf(y) : cosf(y);
-    }
-  }
-  e16[idx] = __float2half_rn(v * ce::kB2);
-  eb16[idx] = __float2bfloat16_rn(v * ce::kB2);
+// All of them write TILE-BLOCKED tensors (chain_engine.cuh) with one 16-byte store per thread: thread i owns the eight
+// columns of blocked position 8 i, consecutive threads are consecutive rows, so a warp writes 512 contiguous bytes.
+__device__ __forceinline__ void store8_h(__half* dst, long long i, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(ce::pack_h2(v[0], v[1]), ce::pack_h2(v[2], v[3]), ce::pack_h2(v[4], v[5]),
+                                                      ce::pack_h2(v[6], v[7]));
+}
+__device__ __forceinline__ void store8_b(__nv_bfloat16* dst, long long i, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(ce::pack_b2(v[0], v[1]), ce::pack_b2(v[2], v[3]), ce::pack_b2(v[4], v[5]),
+                                                      ce::pack_b2(v[6], v[7]));
+}
+// column c of the positional embedding of a d-dimensional point x (embedder.py:15-36): [x | sin(2^k x) | cos(2^k x)]_k
+__device__ __forceinline__ float embed_col(const float* x, int d, int L, int c, float scale) {
+  if (c >= d * (1 + 2 * L)) return 0.0f;
+  if (c < d) return x[c] * scale;
+  const int k = (c - d) / (2 * d), rem = (c - d) - 2 * d * k, j = rem < d ? rem : rem - d;
+  const float y = x[j] * scale * (float)(1 << k);
+  return rem < d ? sinf(y) : cosf(y);
 }
 
-// delta of the last hidden layer: D16[m, c] = fp16((1 - 2^-A16[m, c]) * w[c]),  w = first row of the last weight
+// E16 / EB16 [Npad, 64] = fp16 / bf16 (kB2 * e(x * scale)), zero beyond d_e and beyond row N  (d = 3)
+static __global__ void sdf_embed16_kernel(const float* __restrict__ x, long long N, long long Npad, int L, float scale,
+                                          __half* __restrict__ e16, __nv_bfloat16* __restrict__ eb16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * 8) return;
+  long long m;
+  int c;
+  ce::blk_decode(i * 8, 64, &m, &c);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = m < N ? embed_col(x + m * 3, 3, L, c + j, scale) * ce::kB2 : 0.0f;
+  store8_h(e16, i, v);
+  store8_b(eb16, i, v);
+}
+
+// delta of the last hidden layer: D16L / DB16 [m, c] = fp16 / bf16 ((1 - 2^-AB16[m, c]) * w[c]), w = first row of the last weight
 static __global__ void sdf_delta_last_kernel(const __nv_bfloat16* __restrict__ a16, const float* __restrict__ wrow,
                                              long long Npad, int width, __half* __restrict__ d16,
                                              __nv_bfloat16* __restrict__ db16) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 columns
-  if (idx >= Npad * 32) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 columns
+  if (i >= Npad * 32) return;
   long long m;
   int c;
-  ce::blk_decode(idx * 8, 256, &m, &c);     // all three tensors are tile-blocked [.., 256]: same position in each
-  const uint4 u = *reinterpret_cast<const uint4*>(a16 + idx * 8);
-  float a8[8];
-  ce::unpack_b8(u, a8);
-  uint32_t p[4], pb[4];
+  ce::blk_decode(i * 8, 256, &m, &c);     // all three tensors are tile-blocked [.., 256]: same position in each
+  float a8[8], v[8];
+  ce::unpack_b8(*reinterpret_cast<const uint4*>(a16 + i * 8), a8);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float d0 = c + 2 * i < width ? (1.0f - exp2f(-a8[2 * i])) * wrow[c + 2 * i] : 0.0f;
-    const float d1 = c + 2 * i + 1 < width ? (1.0f - exp2f(-a8[2 * i + 1])) * wrow[c + 2 * i + 1] : 0.0f;
-    p[i] = ce::pack_h2(d0, d1);
-    pb[i] = ce::pack_b2(d0, d1);
-  }
-  *reinterpret_cast<uint4*>(d16 + idx * 8) = make_uint4(p[0], p[1], p[2], p[3]);
-  *reinterpret_cast<uint4*>(db16 + idx * 8) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+  for (int j = 0; j < 8; ++j) v[j] = c + j < width ? (1.0f - exp2f(-a8[j])) * wrow[c + j] : 0.0f;
+  store8_h(d16, i, v);
+  store8_b(db16, i, v);
 }
 
 // Q16_0[m, c] = bf16((J_e n-bar)[c]): forward-mode product with the embedding Jacobian (pointwise.cuh embed_jvp_kernel)
 static __global__ void sdf_qbar0_kernel(const float* __restrict__ x, long long N, long long Npad, int L, float scale,
                                         const float* __restrict__ nbar, __nv_bfloat16* __restrict__ q16) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * 64) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * 8) return;
   long long m;
-  int c;
-  ce::blk_decode(idx, 64, &m, &c);
-  float v = 0.0f;
-  if (m < N && c < 3 + 6 * L) {
-    if (c < 3) {
-      v = nbar[m * 3 + c];
-    } else {
-      const int k = (c - 3) / 6, rem = (c - 3) - 6 * k, j = rem % 3;
-      const float f = (float)(1 << k);
-      const float y = x[m * 3 + j] * scale * f;
-      v = (rem < 3 ? f * cosf(y) : -f * sinf(y)) * nbar[m * 3 + j];
+  int c0;
+  ce::blk_decode(i * 8, 64, &m, &c0);
+  float v[8];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int c = c0 + jj;
+    float r = 0.0f;
+    if (m < N && c < 3 + 6 * L) {
+      if (c < 3) {
+        r = nbar[m * 3 + c];
+      } else {
+        const int k = (c - 3) / 6, rem = (c - 3) - 6 * k, j = rem % 3;
+        const float f = (float)(1 << k);
+        const float y = x[m * 3 + j] * scale * f;
+        r = (rem < 3 ? f * cosf(y) : -f * sinf(y)) * nbar[m * 3 + j];
+      }
     }
+    v[jj] = r;
   }
-  q16[idx] = __float2bfloat16_rn(v);
+  store8_b(q16, i, v);
 }
 
-// dst[m, c] = bf16(src[m * lds + c] * mul) for c < w (zero beyond, zero rows beyond N; src null: zeros), c < ldd
-static __global__ void rows_to_bf16_kernel(const float* __restrict__ src, int lds, int w, float mul, long long N,
-                                           long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * ldd) return;
+// dst_h / dst_b [m, c] = fp16 / bf16 (src[m * lds + c] * mul) for c < w (zero beyond, zero rows beyond N; src null: zeros);
+// either destination may be null.  W = width of the blocked tensors (multiple of 8).
+static __global__ void rows_to_16_kernel(const float* __restrict__ src, int lds, int w, float mul, long long N, long long Npad,
+                                         __half* __restrict__ dst_h, __nv_bfloat16* __restrict__ dst_b, int W) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * (W / 8)) return;
   long long m;
   int c;
-  ce::blk_decode(idx, ldd, &m, &c);       // dst is tile-blocked [Npad, ldd]
-  dst[idx] = __float2bfloat16_rn((src && m < N && c < w) ? src[m * lds + c] * mul : 0.0f);
-}
-static __global__ void rows_to_fp16_kernel(const float* __restrict__ src, int lds, int w, float mul, long long N,
-                                           long long Npad, __half* __restrict__ dst, int ldd) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * ldd) return;
-  long long m;
-  int c;
-  ce::blk_decode(idx, ldd, &m, &c);
-  dst[idx] = __float2half_rn((src && m < N && c < w) ? src[m * lds + c] * mul : 0.0f);
-}
-// dst[m, :] = bf16([a[m, 0..wa) | b[m, 0..wb) | 0 ...]) up to ldd columns (null source: zeros), zero rows beyond N
-static __global__ void gather2_bf16_kernel(const float* __restrict__ a, int lda, int wa, const float* __restrict__ b, int ldb,
-                                           int wb, long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * ldd) return;
-  long long m;
-  int c;
-  ce::blk_decode(idx, ldd, &m, &c);
-  float v = 0.0f;
-  if (m < N) {
-    if (c < wa) { if (a) v = a[m * lda + c]; }
-    else if (c < wa + wb) { if (b) v = b[m * ldb + (c - wa)]; }
+  ce::blk_decode(i * 8, W, &m, &c);
+  float v[8];
+  const float* r = src ? src + m * lds + c : nullptr;
+  if (r && m < N && c + 8 <= w && ((((uintptr_t)r) & 15) == 0)) {
+    const float4 a = *reinterpret_cast<const float4*>(r), b = *reinterpret_cast<const float4*>(r + 4);
+    v[0] = a.x * mul; v[1] = a.y * mul; v[2] = a.z * mul; v[3] = a.w * mul;
+    v[4] = b.x * mul; v[5] = b.y * mul; v[6] = b.z * mul; v[7] = b.w * mul;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (r && m < N && c + j < w) ? r[j] * mul : 0.0f;
   }
-  dst[idx] = __float2bfloat16_rn(v);
+  if (dst_h) store8_h(dst_h, i, v);
+  if (dst_b) store8_b(dst_b, i, v);
+}
+// dst[m, :] = bf16([a[m, 0..wa) | b[m, 0..wb) | 0 ...]) up to W columns (null source: zeros), zero rows beyond N
+static __global__ void gather2_bf16_kernel(const float* __restrict__ a, int lda, int wa, const float* __restrict__ b, int ldb,
+                                           int wb, long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int W) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * (W / 8)) return;
+  long long m;
+  int c0;
+  ce::blk_decode(i * 8, W, &m, &c0);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float r = 0.0f;
+    if (m < N) {
+      if (c < wa) { if (a) r = a[m * lda + c]; }
+      else if (c < wa + wb) { if (b) r = b[m * ldb + (c - wa)]; }
+    }
+    v[j] = r;
+  }
+  store8_b(dst, i, v);
 }
 // dst[m, 0] = bf16(1) for m < N, everything else zero: the "ones" operand that turns a column sum into a GEMM row
-static __global__ void ones_col_bf16_kernel(long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int ldd) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Npad * ldd) return;
+static __global__ void ones_col_bf16_kernel(long long N, long long Npad, __nv_bfloat16* __restrict__ dst, int W) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad * (W / 8)) return;
   long long m;
   int c;
-  ce::blk_decode(idx, ldd, &m, &c);
-  dst[idx] = __float2bfloat16_rn((m < N && c == 0) ? 1.0f : 0.0f);
+  ce::blk_decode(i * 8, W, &m, &c);
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (m < N && c == 0) v[0] = 1.0f;
+  store8_b(dst, i, v);
 }
 template <class K, class... A>
 static inline int launch1d(K kern, long long total, cudaStream_t st, A... args) {
@@ -210,7 +232,7 @@ static inline int sdf_chain_forward(const SdfShape& s, const float* packed, cons
                                     float* feat, int ldf, float out_mul, int save, const SdfChainBufs& b, cudaStream_t st) {
   const MlpLayout& ly = *s.ly;
   const int L = s.L;
-  int e = launch1d(sdf_embed16_kernel, b.Npad * 64, st, x, N, b.Npad, s.multires, s.scale, b.E16, b.EB16);
+  int e = launch1d(sdf_embed16_kernel, b.Npad * 8, st, x, N, b.Npad, s.multires, s.scale, b.E16, b.EB16);
   if (e) return e;
   ce::Args a;
   ce::init_args(&a);
@@ -294,7 +316,7 @@ static inline int sdf_chain_backward(const SdfShape& s, const float* packed, con
   int e;
   // ---- phase 1: backward of the normals pass, l = 0 .. L-2 ----
   if (have_n) {
-    e = launch1d(sdf_qbar0_kernel, b.Npad * 64, st, x, N, b.Npad, s.multires, s.scale, d_normals, b.Q16[0]);
+    e = launch1d(sdf_qbar0_kernel, b.Npad * 8, st, x, N, b.Npad, s.multires, s.scale, d_normals, b.Q16[0]);
     if (e) return e;
     ce::Args a;
     ce::init_args(&a);
@@ -320,12 +342,12 @@ static inline int sdf_chain_backward(const SdfShape& s, const float* packed, con
   // ---- phase 2: ordinary backward with the injected cotangents, l = L-1 .. 1 (.. 0 for the point gradient) ----
   const int lo = L - 1;
   const int nf = ly.out_dim[lo] - 1;
-  e = launch1d(rows_to_bf16_kernel, b.Npad * 256, st, d_feat, ldf, nf, 1.0f, N, b.Npad, b.FB16, 256);
+  e = launch1d(rows_to_16_kernel, b.Npad * 32, st, d_feat, ldf, nf, 1.0f, N, b.Npad, (__half*)nullptr, b.FB16, 256);
   if (e) return e;
-  e = launch1d(rows_to_bf16_kernel, b.Npad * 64, st, d_sdf, lds, 1, ce::kInvB2 / s.scale, N, b.Npad, b.SB, 64);
+  e = launch1d(rows_to_16_kernel, b.Npad, st, d_sdf, lds, 1, ce::kInvB2 / s.scale, N, b.Npad, (__half*)nullptr, b.SB, 8);
   if (e) return e;
   if (have_n) {
-    e = launch1d(ones_col_bf16_kernel, b.Npad * 64, st, N, b.Npad, b.ONESB, 64);
+    e = launch1d(ones_col_bf16_kernel, b.Npad, st, N, b.Npad, b.ONESB, 8);
     if (e) return e;
   }
   {
@@ -372,8 +394,8 @@ static inline int sdf_chain_backward(const SdfShape& s, const float* packed, con
       mQ[0] = w.add_y(b.Q16[0], 64, ly.in_dim[0]);
       for (int l = 1; l <= L - 1; ++l) mQ[l] = w.add_y(b.Q16[l], 256, ly.in_dim[l]);
     }
-    const int mF = w.add_x(b.FB16, 256, nf), mS = w.add_x(b.SB, 64, 1);
-    const int mO = have_n ? w.add_x(b.ONESB, 64, 1) : 0;
+    const int mF = w.add_x(b.FB16, 256, nf), mS = w.add_x(b.SB, 8, 1);
+    const int mO = have_n ? w.add_x(b.ONESB, 8, 1) : 0;
     for (int l = 0; l < L - 1; ++l) {     // W-bar_l = [z-bar_l ; delta_l]^T [u_l ; q-bar_l]
       wg::Job* j = w.add_job(ly.out_dim[l], ly.in_dim[l], ly.off_w[l], ly.in_ld[l], 1.0f, ly.off_b[l],
                              ce::kB2 / sdf_dsc(s, l));

@@ -8,7 +8,7 @@
 // A "job" is one (layer, output-row block) with up to two (X, Y) segments that share an accumulator
 // (W-bar_l = [z-bar ; delta]^T [u ; q-bar]); the batch is split over the CTAs so that (jobs x splits) fills one wave of
 // the 148 SMs, every CTA streaming its points exactly once:
-//   * operands arrive by TMA TENSOR MAPS (cp.async.bulk.tensor.4d, UTMALDG) over the tile-blocked 16-bit tensors
+//   * operands arrive by TMA TENSOR MAPS (cp.async.bulk.tensor.3d, UTMALDG) over the tile-blocked 16-bit tensors
 //     ([tile][8-column group][128 rows][8], chain_engine.cuh): one box = 64 points x all needed column groups, so a
 //     64-point stage is two TMA instructions (X and Y, up to 32 KB each), three stages in flight; column groups and
 //     tiles outside a tensor are zero-filled by the TMA unit;
@@ -81,10 +81,13 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// box {8 elements, 64 rows, box column groups, 1 tile} at (0, row0, cg0, tile)
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int row0, int cg0, int tile, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
-               "l"(tm), "r"(0), "r"(row0), "r"(cg0), "r"(tile), "r"(bar)
+// The tile-blocked tensor [tile][column group][128 rows][8 x 16 bit] is described to the TMA unit as a 3-D tensor of
+// 32-bit words {512 words = 128 rows x 16 bytes, column groups, tiles}: a box {256 words = 64 rows, box column groups, 1}
+// at (4 * row0, cg0, tile) moves 1 KB contiguous runs (a 16-byte innermost box dimension would be the slowest shape the
+// TMA unit handles).
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int row0, int cg0, int tile, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tm), "r"(row0 * 4), "r"(cg0), "r"(tile), "r"(bar)
                : "memory");
 }
 
@@ -122,8 +125,8 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
       ok = mbar_wait_backoff(smem_u32(&empty[s]), ph ^ 1, 64);
       const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES, bar = smem_u32(&full[s]);
       mbar_arrive_expect_tx(bar, bytes);
-      tma_load_4d(base, &a.maps[jb.xmap[seg]], (chunk & 1) * 64, jb.xcol[seg] >> 3, chunk >> 1, bar);
-      tma_load_4d(base + 32768u, &a.maps[jb.ymap[seg]], (chunk & 1) * 64, jb.ycol[seg] >> 3, chunk >> 1, bar);
+      tma_load_3d(base, &a.maps[jb.xmap[seg]], (chunk & 1) * 64, jb.xcol[seg] >> 3, chunk >> 1, bar);
+      tma_load_3d(base + 32768u, &a.maps[jb.ymap[seg]], (chunk & 1) * 64, jb.ycol[seg] >> 3, chunk >> 1, bar);
     }
   } else if (tid == 32) {
     // ================= MMA issuer =================
@@ -249,12 +252,12 @@ struct Builder {
     EncodeTiledFn fn = encode_fn();
     if (!fn || nmaps >= MAX_MAPS || ((uintptr_t)ptr & 127) || (W & 7) || box_cg < 1 || box_cg > 32) { bad = true; return 0; }
     const cuuint64_t tiles = (cuuint64_t)((N + 127) / 128);
-    const cuuint64_t dims[4] = {8, 128, (cuuint64_t)(W / 8), tiles};
-    const cuuint64_t strides[3] = {16, 2048, (cuuint64_t)W * 256};
-    const cuuint32_t box[4] = {8, 64, (cuuint32_t)box_cg, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(&a.maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const cuuint64_t dims[3] = {512, (cuuint64_t)(W / 8), tiles};
+    const cuuint64_t strides[2] = {2048, (cuuint64_t)W * 256};
+    const cuuint32_t box[3] = {256, (cuuint32_t)box_cg, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&a.maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { bad = true; return 0; }
     return nmaps++;
