@@ -386,11 +386,11 @@ def run_ours(args):
             train_step(rend, params, o, d, near, far, rgb, gt_feats=gt, background_rgb=bg, cos_anneal_ratio=1.0,
                        grad_sync=sync, global_batch=B * world)
         gstep = None
-        if not args.no_cuda_graph and world == 1:
+        if not args.no_cuda_graph and (world == 1 or not args.no_graph_nccl):
             # the whole step (render + loss + backward) captured once, replayed per step: one graph launch instead of
             # ~250 kernel launches; the kernels and their work are unchanged.  Falls back to eager launches if the
-            # capture is refused.  Multi-GPU runs stay eager: capturing the step together with its two NCCL all-reduces
-            # hung in the round-1 trial (2 GPUs), see DESIGN.md section 5.
+            # capture is refused.  Multi-GPU steps are captured together with their two NCCL all-reduces
+            # (capture_error_mode="thread_local", see training.GraphedTrainStep).
             from vdn_nerf_b200.training import GraphedTrainStep
             fn(0)                                       # eager warm-up: one-time library initialisation outside the capture
             torch.manual_seed(2)
@@ -535,8 +535,16 @@ def run_ours(args):
                  "reference_cuda_eager", "clocks"]
         print(json.dumps({k: line[k] for k in order if k in line}))
     if world > 1:
+        # A CUDA graph that captured NCCL collectives keeps communicator resources alive; tearing the process group down
+        # under it was seen to block.  Results are printed: leave through a barrier and a hard exit instead.
         import torch.distributed as dist
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        try:
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os._exit(0)
 
 
 def main():
@@ -553,6 +561,9 @@ def main():
     ap.add_argument("--rays", type=int, default=512, help="rays per step per GPU")
     ap.add_argument("--resolution", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph-nccl", action="store_true",
+                    help="multi-GPU: launch the step eagerly instead of replaying a CUDA graph that captured the step "
+                         "together with its NCCL all-reduces")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's eager-CUDA leg (subprocess)")
     ap.add_argument("--no-cuda-graph", action="store_true",
                     help="training workloads: launch every kernel eagerly instead of replaying the captured step")

@@ -367,3 +367,42 @@ def sdf_normals_emulated(p, x, spec: vo.SDFSpec) -> torch.Tensor:
         de = de + G[skip][:, W[skip].shape[1] - d_e:] * INV_SQRT2
     J = embed_jac(y, spec.multires)
     return torch.einsum("nc,ncj->nj", de, J)
+
+
+def sdf_normals_chain_emulated(p, x, spec: vo.SDFSpec) -> torch.Tensor:
+    """Normals through the FUSED chains' arithmetic (csrc/sdf_chains.cuh): forward as `sdf_chain_emulated`; what is saved
+    per layer is a'_l = log2(1 + 2^t_l) rounded to bf16 (the only copy that reaches HBM), softplus'(z_l) is recomputed
+    from it as 1 - 2^-a'; delta_l and the weights enter the reverse-pass MMAs as fp16, fp32 accumulation."""
+    f16 = lambda a: a.to(torch.float16).to(torch.float32)
+    b16 = lambda a: a.to(torch.bfloat16).to(torch.float32)
+    L = spec.n_lin
+    skip = spec.skip_in[0] if len(spec.skip_in) else -1
+    y = (x * spec.scale).to(torch.float32)
+    e = vo.embed(y, spec.multires).to(torch.float32) * B2
+    d_e = e.shape[1]
+    h = f16(e)
+    saved = []
+    for l in range(L - 1):
+        W = f16(vo.effective_weight(p, f"lin{l}").to(torch.float32))
+        b = p[f"lin{l}.bias"].to(torch.float32) * B2
+        if l == skip:
+            h = torch.cat([h, f16(e)], dim=1)
+        t = (h @ W.t()) * (INV_SQRT2 if l == skip else 1.0) + b
+        a = softplus_base2(t)
+        saved.append(b16(a))
+        h = f16(a)
+    Wf = [vo.effective_weight(p, f"lin{l}").to(torch.float32) for l in range(L)]
+    a = Wf[L - 1][0:1, :].expand(x.shape[0], -1)
+    de_skip = None
+    for l in range(L - 2, -1, -1):
+        od = Wf[l].shape[0]
+        S = 1.0 - torch.exp2(-saved[l][:, :od])
+        delta = f16(S * a[:, :od])
+        a = delta @ f16(Wf[l])
+        if l == skip:
+            a = a * INV_SQRT2
+            de_skip = a[:, Wf[l].shape[1] - d_e:]
+            a = a[:, : Wf[l].shape[1] - d_e]
+    de = a + (de_skip if de_skip is not None else 0.0)
+    J = embed_jac(y, spec.multires)
+    return torch.einsum("nc,ncj->nj", de, J)

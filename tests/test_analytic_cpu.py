@@ -165,3 +165,20 @@ def test_chain_kernel_arithmetic_within_tensor_core_tolerance():
     errn = float((gotn - wantn).abs().max() / wantn.abs().max())
     print(f"tensor-core normals (CPU emulation) rel err {errn:.2e}")
     assert errn < 2e-3
+
+
+def test_fused_chain_normals_arithmetic_with_bf16_saved_activations():
+    """The fused training chains keep ONE copy of every layer's activation in HBM, in bf16, and recompute softplus' from
+    it (csrc/sdf_chains.cuh).  Emulated on the CPU at the reference's initialisation: the normals stay within the 2e-3
+    tensor-core tolerance, no worse than with the tf32 layer-wise pass."""
+    from tests import util
+    mods, conf = util.build("womsk_white")
+    nets64 = util.oracle_nets(mods, conf, dtype=torch.float64)
+    nets32 = util.oracle_nets(mods, conf, dtype=torch.float32)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(4096, 3, generator=g) * 2.4 - 1.2
+    wantn = vo.sdf_gradient(nets64.sdf, x.double(), nets64.sdf_spec).detach().squeeze(1)
+    gotn = ar.sdf_normals_chain_emulated(nets32.sdf, x, nets32.sdf_spec).double()
+    errn = float((gotn - wantn).abs().max() / wantn.abs().max())
+    print(f"fused-chain normals (CPU emulation, bf16 saved activations) rel err {errn:.2e}")
+    assert errn < 2e-3

@@ -112,7 +112,10 @@ class GraphedTrainStep:
         ops.force_repack(True)
         c0 = ops.launch_count()
         try:
-            with torch.cuda.graph(self.graph):
+            # with NCCL collectives inside, the capture must not poison the process-wide stream state: the process
+            # group's watchdog thread queries events concurrently, which is illegal under the default "global" mode
+            mode = "thread_local" if grad_sync is not None else "global"
+            with torch.cuda.graph(self.graph, capture_error_mode=mode):
                 self.loss, self.out = run()
         finally:
             ops.force_repack(False)
