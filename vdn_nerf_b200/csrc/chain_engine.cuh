@@ -502,6 +502,13 @@ __device__ __forceinline__ void fast_phase(const Phase& ph, bool last, uint32_t 
   qa[0] = qa[1] = qb[0] = qb[1] = make_uint4(0u, 0u, 0u, 0u);
   if (has0) qa[0] = __ldg(p0);
   if (has1) qb[0] = __ldg(p1);
+  // the lines of the next groups -> L1 (they sit in L2 since the previous phase's prefetch): an L2 hit costs ~0.4 us,
+  // more than a group's worth of work, and registers for a deeper look-ahead do not exist
+#pragma unroll
+  for (int g = 1; g < 4; ++g) {
+    if (has0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + g * 128));
+    if (has1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + g * 128));
+  }
   *ok = mbar_wait(bar_d_full, par);
   tc_fence_after();
   float v[2][8];
@@ -513,6 +520,10 @@ __device__ __forceinline__ void fast_phase(const Phase& ph, bool last, uint32_t 
       tmem_ld8(tD + (uint32_t)(8 * (g + 1)), v[(g + 1) & 1]);
       if (has0) qa[(g + 1) & 1] = __ldg(p0 + (g + 1) * 128);
       if (has1) qb[(g + 1) & 1] = __ldg(p1 + (g + 1) * 128);
+      if (g + 4 < 8) {
+        if (has0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + (g + 4) * 128));
+        if (has1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + (g + 4) * 128));
+      }
     } else {
       tc_fence_before();
       mbar_arrive(bar_d_drained);                     // the accumulator has left tensor memory
