@@ -201,6 +201,16 @@ int vdn_raygen_fwd(const float* px, const float* py, long long B, const float* k
 int vdn_raygen_bwd(const float* px, const float* py, long long B, const float* kinv, const float* d_rays_o,
                    const float* d_rays_d, float* d_pose, void* stream);
 
+/* Marching cubes on the device-resident field u[nx, ny, nz] (replaces the host library call at renderer.py:36; inside =
+ * u > threshold).  vdn_mc_count writes the triangle count of every cell ((nx-1)(ny-1)(nz-1) ints); the caller forms the
+ * exclusive prefix sum `offsets`; vdn_mc_emit writes, per triangle corner, the key of the cut grid edge (3 * linear index
+ * of its lower end point + axis) and the interpolated position in grid-index coordinates.  tri_count[256],
+ * tri_table[256*16], edge_corner[12], edge_axis[12]: the generated case table (vdn_nerf_b200/mcubes_table.py), device. */
+int vdn_mc_count(const float* u, int nx, int ny, int nz, float threshold, const int* tri_count, int* counts, void* stream);
+int vdn_mc_emit(const float* u, int nx, int ny, int nz, float threshold, const int* tri_count, const int* tri_table,
+                const int* edge_corner, const int* edge_axis, const long long* offsets, long long* keys, float* pos,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ SIGNATURES = {
     "vdn_color_loss": (I, [P, P, P, L, P, P, P]),
     "vdn_raygen_fwd": (I, [P, P, L, P, P, P, P, P]),
     "vdn_raygen_bwd": (I, [P, P, L, P, P, P, P, P]),
+    "vdn_mc_count": (I, [P, I, I, I, F, P, P, P]),
+    "vdn_mc_emit": (I, [P, I, I, I, F, P, P, P, P, P, P, P, P]),
 }
 
 _lib = None

@@ -733,3 +733,46 @@ def grid_sdf(h: SdfHandle, xs, ys, zs, i0, i1, out_mul, u_slab):
     blob = torch.empty(int(lib.vdn_sdf_blob_floats(h.cfg, count, 0)), device=dev, dtype=torch.float32)
     check(lib.vdn_grid_sdf(h.cfg, h.scale, _p(packed), _p(xs), _p(ys), _p(zs), ny, nz, i0, i1, float(out_mul),
                            _p(u_slab), _p(pts), _p(blob), _stream()), "vdn_grid_sdf")
+
+
+# ----------------------------------------------------------------------------------------------------
+# Marching cubes on the device
+# ----------------------------------------------------------------------------------------------------
+_MC_TABLES = {}
+
+
+def _mc_tables(dev):
+    key = str(dev)
+    if key not in _MC_TABLES:
+        from .mcubes_table import EDGE_AXIS, TRI_COUNT, TRI_TABLE
+        _MC_TABLES[key] = (torch.from_numpy(TRI_COUNT.copy()).to(dev), torch.from_numpy(TRI_TABLE.reshape(-1).copy()).to(dev),
+                           torch.tensor([a for a, _ in EDGE_AXIS], dtype=torch.int32, device=dev),
+                           torch.tensor([ax for _, ax in EDGE_AXIS], dtype=torch.int32, device=dev))
+    return _MC_TABLES[key]
+
+
+def marching_cubes(u: torch.Tensor, threshold: float = 0.0):
+    """Isosurface of the device-resident field u[nx, ny, nz] at `threshold` (inside = u > threshold), like
+    `mcubes.marching_cubes` (reference renderer.py:36): (vertices [V,3] float32 in grid-index coordinates, triangles [F,3]
+    int64, outward oriented), both on the device.  Vertices shared by neighbouring triangles are welded."""
+    lib = _lib.load()
+    u = _prep(u)
+    nx, ny, nz = u.shape
+    dev = u.device
+    cnt, tab, ec, ea = _mc_tables(dev)
+    cells = (nx - 1) * (ny - 1) * (nz - 1)
+    counts = torch.empty(cells, device=dev, dtype=torch.int32)
+    check(lib.vdn_mc_count(_p(u), nx, ny, nz, float(threshold), _p(cnt), _p(counts), _stream()), "vdn_mc_count")
+    incl = torch.cumsum(counts, 0, dtype=torch.int64)
+    total = int(incl[-1])                                 # the output size is data dependent: one host read
+    if total == 0:
+        return torch.zeros(0, 3, device=dev), torch.zeros(0, 3, device=dev, dtype=torch.int64)
+    offsets = incl - counts
+    keys = torch.empty(total * 3, device=dev, dtype=torch.int64)
+    pos = torch.empty(total * 3, 3, device=dev, dtype=torch.float32)
+    check(lib.vdn_mc_emit(_p(u), nx, ny, nz, float(threshold), _p(cnt), _p(tab), _p(ec), _p(ea), _p(offsets), _p(keys),
+                          _p(pos), _stream()), "vdn_mc_emit")
+    uniq, inv = torch.unique(keys, return_inverse=True)
+    verts = torch.empty(uniq.numel(), 3, device=dev, dtype=torch.float32)
+    verts[inv] = pos                                      # duplicates of a key carry the identical position
+    return verts, inv.reshape(-1, 3)

@@ -289,11 +289,12 @@ class NeuSRenderer:
         }
 
     def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
-        """renderer.py:441-446 with the fused grid query; marching cubes stays with `mcubes` on the host."""
-        import mcubes
-        u = extract_fields_sdf(self.sdf_network, bound_min, bound_max, resolution, negate=True).cpu().numpy()
-        vertices, triangles = mcubes.marching_cubes(u, threshold)
-        b_max_np = bound_max.detach().cpu().numpy()
-        b_min_np = bound_min.detach().cpu().numpy()
-        vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
-        return vertices, triangles
+        """renderer.py:441-446: (vertices [V,3] float, triangles [F,3] int) numpy arrays in world coordinates.  The field is
+        queried by the fused grid kernel and meshed ON THE DEVICE (`ops.marching_cubes`): neither the 4 res^3-byte field nor
+        a host marching-cubes library is involved; only the mesh crosses PCIe."""
+        u = extract_fields_sdf(self.sdf_network, bound_min, bound_max, resolution, negate=True)
+        vertices, triangles = ops.marching_cubes(u, threshold)
+        b_max = torch.as_tensor(bound_max, dtype=torch.float32, device=vertices.device)
+        b_min = torch.as_tensor(bound_min, dtype=torch.float32, device=vertices.device)
+        vertices = vertices / (resolution - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]
+        return vertices.cpu().numpy(), triangles.cpu().numpy()
