@@ -511,25 +511,36 @@ __device__ __forceinline__ void fast_phase(const Phase& ph, bool last, uint32_t 
   }
   *ok = mbar_wait(bar_d_full, par);
   tc_fence_after();
-  float v[2][8];
+  // groups 0..3 stream through two 8-value buffers; when group 4 arrives the remaining three are fetched at once and the
+  // accumulator is released at half time, so the other tile's MMAs overlap the second half of this epilogue
+  float v[2][8], w[3][8];
   tmem_ld8(tD, v[0]);
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
-    tmem_ld_wait();                                   // group g has arrived in v[g & 1]
-    if (g < 7) {
+    if (g <= 4) tmem_ld_wait();                       // group g has arrived (groups 5..7 arrive together with 4)
+    if (g < 4) {
       tmem_ld8(tD + (uint32_t)(8 * (g + 1)), v[(g + 1) & 1]);
+    } else if (g == 4) {
+      tmem_ld8(tD + 40u, w[0]);
+      tmem_ld8(tD + 48u, w[1]);
+      tmem_ld8(tD + 56u, w[2]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_d_drained);                     // the accumulator has left tensor memory
+      if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
+    }
+    if (g < 7) {
       if (has0) qa[(g + 1) & 1] = __ldg(p0 + (g + 1) * 128);
       if (has1) qb[(g + 1) & 1] = __ldg(p1 + (g + 1) * 128);
       if (g + 4 < 8) {
         if (has0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + (g + 4) * 128));
         if (has1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + (g + 4) * 128));
       }
-    } else {
-      tc_fence_before();
-      mbar_arrive(bar_d_drained);                     // the accumulator has left tensor memory
-      if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
     }
-    fast_group<OP>(ph, v[g & 1], qa[g & 1], qb[g & 1], sb + c0, g, tA, pa, pb, dsc, om, am, a_out, has0, has1);
+    if (g <= 4)
+      fast_group<OP>(ph, v[g & 1], qa[g & 1], qb[g & 1], sb + c0, g, tA, pa, pb, dsc, om, am, a_out, has0, has1);
+    else
+      fast_group<OP>(ph, w[g - 5], qa[g & 1], qb[g & 1], sb + c0, g, tA, pa, pb, dsc, om, am, a_out, has0, has1);
   }
 }
 
