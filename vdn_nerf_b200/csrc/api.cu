@@ -123,5 +123,5 @@ extern "C" int vdn_embed_bwd(const float* x, long long N, int d, int multires, c
   VDN_LAUNCH(embed_vjp_kernel, (unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream, x, d, N, d, multires, 1.0f, d_out,
                                                                                   d_e, nullptr, 0, 0.0f, 1.0f, d_x, d,
                                                                                   0);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }

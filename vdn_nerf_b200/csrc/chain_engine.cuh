@@ -79,16 +79,18 @@ struct Phase {
   int a_out;             // 1: the epilogue writes the slot (A of the next phase)
   int a_wr;              // number of A columns written (multiple of 8, zero padded beyond width + tail)
   float a_mul;           // OP_P1STEP: scale of the A written
-  const void* aux0; int ld0; int aux0_bf16;
-  const void* aux1; int ld1; int aux1_bf16;
-  void* o16a; int ldo16a; float o16a_mul; int o16a_bf16;   // 16-bit copy of the A values (times o16a_mul)
-  void* o16b; int ldo16b;                   // second 16-bit output (OP_P1STEP), bf16
+  const void* aux0; int ld0;
+  const void* aux1; int ld1;
+  void* o16a; int ldo16a; float o16a_mul;   // fp16 copy of the A values (times o16a_mul)
+  void* o16b; int ldo16b;                   // second fp16 output (OP_P1STEP)
   float* o32; int ldo32; int o32_c0, o32_w; float o32_mul; int act;   // fp32 store of act(x) for columns [o32_c0, o32_c0 + o32_w)
+  int o32_unscale;       // the fp32 output is a cotangent: multiply by 1 / sigma
   int o32_vec;           // set by launch(): full groups of that store may use 16-byte accesses
   int fast;              // set by launch(): regular phase, run_op_fast applies
   float* o32b; int ldo32b; int o32b_c0, o32b_w;                       // second fp32 store of x (no activation), other columns
-  const void* tail; int ldt; int tail_w; float tail_mul; int tail_bf16;   // A columns [width, width + tail_w) from here
+  const void* tail; int ldt; int tail_w; float tail_mul;   // A columns [width, width + tail_w) from here
   const float* r1; int r1_stride; float r1_mul; int r1_row;   // rank-1 term, r1_row in {0, 1}
+  int r1_scaled;         // the rank-1 coefficient is an unscaled fp32 cotangent: multiply by sigma
   int stash_w, stash_r;  // stash index written (OP_STASH) / read (-1: none)
   const void* aload; int al_ld, al_w;       // after this phase: load [128 x al_w] 16-bit values into the slot (A of the next)
 };
@@ -100,12 +102,20 @@ struct Args {
   const void* a0; int a0_ld, a0_w;          // A operand of phase 0
   long long row_off[2]; int row_len[2];     // rank-1 row vectors (float offsets into packed, -1: none)
   uint16_t* stash;                          // fp16 scratch [grid][2][MAX_STASH][8][512][8] (stays in L2)
+  const float* sigma;                       // backward passes: device {sigma, 1 / sigma}, the power-of-two loss scale the
+                                            // fp16 cotangents of this launch carry (null: 1)
   Phase ph[MAX_PHASES];
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// saturating variant for cotangents: a value beyond the fp16 range becomes +-65504 instead of infinity
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ uint32_t pack_b2(float lo, float hi) {
@@ -206,25 +216,27 @@ static __device__ __noinline__ void ragged_tail(const Phase& ph, long long m, in
     const int c = cg + j;
     if (c >= ph.width) {
       const int tcol = c - ph.width;
-      r[j] = (ph.tail && tcol < ph.tail_w) ? ld16_one(ph.tail, m, ph.ldt, tcol, ph.tail_bf16) * ph.tail_mul : 0.0f;
+      r[j] = (ph.tail && tcol < ph.tail_w) ? ld16_one(ph.tail, m, ph.ldt, tcol, 0) * ph.tail_mul : 0.0f;
       if (r2) r2[j] = 0.0f;
     }
   }
 }
 
-// Operand / storage formats are fixed per epilogue kind (launch() checks the table against them), so the hot loop has
-// no run-time format branches: the A operand written to tensor memory is fp16 in the forward-type passes (OP_SOFTPLUS,
-// OP_NSTEP, OP_RELU, OP_LINEAR) and bf16 in the backward-type passes (OP_P1STEP, OP_P2STEP, OP_MASK); everything that
-// goes to or comes from HBM (aux0, aux1, o16a, o16b) is bf16 - the weight-gradient kernel needs one format for both
-// operands, and softplus' = 1 - 2^-a' recomputed from a bf16 a' costs no accuracy (tests/test_analytic_cpu.py).
+// Every 16-bit tensor of the chains is fp16: the A operands in tensor memory, the weight images, and everything that
+// goes to or comes from HBM (aux0, aux1, o16a, o16b) - the weight-gradient kernel needs one format for both operands.
+// Forward quantities fit fp16's range as they are (a' = kB2 softplus(z), ReLU activations).  Cotangents (OP_P1STEP,
+// OP_P2STEP, OP_MASK) do not - d loss / d z is ~1e-6 - so a backward launch carries ONE power-of-two loss scale sigma
+// (Args::sigma, computed on the device from the largest incoming cotangent): every cotangent tensor of the launch is
+// sigma times the true one, fp32 outputs are multiplied by 1 / sigma on the way out, and conversions saturate instead
+// of overflowing.  Eleven significant bits instead of bf16's eight, and one MMA pass instead of a hi/lo weight pair.
 template <int OP> struct OpTraits {
-  static constexpr bool bf16 = (OP == OP_P1STEP || OP == OP_P2STEP || OP == OP_MASK);       // format of the A written
+  static constexpr bool bwd = (OP == OP_P1STEP || OP == OP_P2STEP || OP == OP_MASK);       // A is a scaled cotangent
   static constexpr bool aux0 = (OP == OP_NSTEP || OP == OP_P1STEP || OP == OP_P2STEP || OP == OP_MASK);
   static constexpr bool aux1 = (OP == OP_P1STEP || OP == OP_P2STEP);
-  static constexpr bool aux0_bf16 = true;
-  static constexpr bool aux1_bf16 = true;
-  static constexpr bool o16a_bf16 = true;
 };
+template <int OP> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  return OpTraits<OP>::bwd ? pack_h2_sat(lo, hi) : pack_h2(lo, hi);
+}
 
 // element offset of (row m, column c0 + 32 half) in a tile-blocked tensor of width W; group gi adds gi * 1024
 __device__ __forceinline__ long long blk_base(long long m, int W, int c0, int half) {
@@ -247,9 +259,6 @@ __device__ __forceinline__ void load_aux(const Phase& ph, long long m, int c0, i
       if (c0 + 32 * half + 8 * gi < ph.width) q1[gi] = __ldg(p + gi * 128);
   }
 }
-__device__ __forceinline__ void unpack8t(const uint4& u, bool bf16, float (&f)[8]) {   // bf16 is a compile-time constant
-  if (bf16) unpack_b8(u, f); else unpack_h8(u, f);
-}
 
 // One phase's element-wise work for one thread: its row m, columns c0 + 32 half .. + 31 (four groups of eight; the
 // accumulator is drained and processed in two halves so that 32 + ~50 registers suffice: a thread of a 576-thread CTA
@@ -257,14 +266,14 @@ __device__ __forceinline__ void unpack8t(const uint4& u, bool bf16, float (&f)[8
 template <int OP>
 __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], int half, const uint4 (&q0)[4],
                                        const uint4 (&q1)[4], const float* sb, const float* srow, long long m, long long N,
-                                       int c0, uint32_t tA, uint16_t* stash_base) {
+                                       int c0, uint32_t tA, uint16_t* stash_base, float sig, float isig) {
   using T = OpTraits<OP>;
   const int ncols = ph.a_out ? ph.a_wr : ph.width;      // columns this phase touches
   const int width = ph.width;
   const float dsc = ph.dsc;
   const bool rowok = m < N;
   const bool has_r1 = ph.r1 != nullptr;
-  const float r1v = (has_r1 && rowok) ? ph.r1[m * ph.r1_stride] * ph.r1_mul : 0.0f;   // padded rows stay exactly zero
+  const float r1v = (has_r1 && rowok) ? ph.r1[m * ph.r1_stride] * ph.r1_mul * (ph.r1_scaled ? sig : 1.0f) : 0.0f;   // padded rows stay exactly zero
   const float* rr = srow + ph.r1_row * 256;
   const int cb = c0 + 32 * half;
   // destinations of this half (tile-blocked 16-bit copies; fp32 row-major side output)
@@ -275,6 +284,7 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
   const bool o32b_on = ph.o32b && rowok;
   float4* pv = (o32_on && ph.o32_vec) ? reinterpret_cast<float4*>(ph.o32 + m * ph.ldo32 + (cb - ph.o32_c0)) : nullptr;
   const float om = ph.o16a_mul;
+  const float o32_mul = ph.o32_unscale ? ph.o32_mul * isig : ph.o32_mul;
 #pragma unroll
   for (int gi = 0; gi < 4; ++gi) {
     const int g = half * 4 + gi;
@@ -308,11 +318,11 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
     // fp32 side outputs of x (final outputs, skip-connection tails)
     if (o32_on && cg + 8 > ph.o32_c0 && cg < ph.o32_c0 + ph.o32_w) {
       if (pv && cg >= ph.o32_c0 && cg + 8 <= ph.o32_c0 + ph.o32_w) {      // o32_vec: no activation, unit scale handled below
-        const float mul = ph.o32_mul;
+        const float mul = o32_mul;
         pv[2 * gi] = make_float4(x[0] * mul, x[1] * mul, x[2] * mul, x[3] * mul);
         pv[2 * gi + 1] = make_float4(x[4] * mul, x[5] * mul, x[6] * mul, x[7] * mul);
       } else {
-        o32_scalar(ph.o32, ph.ldo32, ph.o32_c0, ph.o32_w, ph.act, ph.o32_mul, m, cg, x[0], x[1], x[2], x[3], x[4], x[5], x[6],
+        o32_scalar(ph.o32, ph.ldo32, ph.o32_c0, ph.o32_w, ph.act, o32_mul, m, cg, x[0], x[1], x[2], x[3], x[4], x[5], x[6],
                    x[7]);
       }
     }
@@ -334,7 +344,7 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
     } else if (OP == OP_MASK) {
       if (ph.aux0 && in) {
         float h8[8];
-        unpack8t(q0[gi], T::aux0_bf16, h8);
+        unpack_h8(q0[gi], h8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
       } else {
@@ -345,7 +355,7 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
       float s_[8];
       if (in) {
         float a8[8];
-        unpack8t(q0[gi], T::aux0_bf16, a8);
+        unpack_h8(q0[gi], a8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);
       } else {
@@ -358,7 +368,7 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
       } else if (OP == OP_P1STEP) {
         float d8[8];
         if (in) {
-          unpack8t(q1[gi], T::aux1_bf16, d8);
+          unpack_h8(q1[gi], d8);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) d8[j] = 0.0f;
@@ -372,7 +382,7 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
       } else {
         float z8[8];
         if (ph.aux1 && in) {
-          unpack8t(q1[gi], T::aux1_bf16, z8);
+          unpack_h8(q1[gi], z8);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) z8[j] = 0.0f;
@@ -385,20 +395,18 @@ __device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], 
     if (cg + 8 > width) ragged_tail(ph, m, cg, r, OP == OP_P1STEP ? r2 : nullptr);
     uint32_t p[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = T::bf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) p[i] = pack2<OP>(r[2 * i], r[2 * i + 1]);
     if (ph.a_out) tc::tmem_st4(tA + (uint32_t)(4 * g), p);
     if (pa) {
       if (OP == OP_P2STEP) {               // stored pre-scaled (z-bar * dsc / kB2: the weight gradient's operand)
-        pa[gi * 128] = make_uint4(pack_b2(r[0] * om, r[1] * om), pack_b2(r[2] * om, r[3] * om), pack_b2(r[4] * om, r[5] * om),
-                                  pack_b2(r[6] * om, r[7] * om));
-      } else if (T::o16a_bf16 != T::bf16) {   // fp16 operand in tensor memory, bf16 copy in HBM
-        pa[gi * 128] = make_uint4(pack_b2(r[0], r[1]), pack_b2(r[2], r[3]), pack_b2(r[4], r[5]), pack_b2(r[6], r[7]));
+        pa[gi * 128] = make_uint4(pack2<OP>(r[0] * om, r[1] * om), pack2<OP>(r[2] * om, r[3] * om),
+                                  pack2<OP>(r[4] * om, r[5] * om), pack2<OP>(r[6] * om, r[7] * om));
       } else {
         pa[gi * 128] = make_uint4(p[0], p[1], p[2], p[3]);
       }
     }
     if (OP == OP_P1STEP && pb)
-      pb[gi * 128] = make_uint4(pack_b2(r2[0], r2[1]), pack_b2(r2[2], r2[3]), pack_b2(r2[4], r2[5]), pack_b2(r2[6], r2[7]));
+      pb[gi * 128] = make_uint4(pack2<OP>(r2[0], r2[1]), pack2<OP>(r2[2], r2[3]), pack2<OP>(r2[4], r2[5]), pack2<OP>(r2[6], r2[7]));
   }
 }
 
@@ -432,7 +440,7 @@ __device__ __forceinline__ void fast_group(const Phase& ph, const float (&v)[8],
   } else if (OP == OP_MASK) {
     if (has0) {
       float h8[8];
-      unpack_b8(q0, h8);
+      unpack_h8(q0, h8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
     } else {
@@ -441,7 +449,7 @@ __device__ __forceinline__ void fast_group(const Phase& ph, const float (&v)[8],
     }
   } else {
     float a8[8], s_[8];
-    unpack_b8(q0, a8);
+    unpack_h8(q0, a8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);          // softplus'(z) = 1 - 2^-a'
     if (OP == OP_NSTEP) {
@@ -449,7 +457,7 @@ __device__ __forceinline__ void fast_group(const Phase& ph, const float (&v)[8],
       for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
     } else if (OP == OP_P1STEP) {
       float d8[8];
-      unpack_b8(q1, d8);
+      unpack_h8(q1, d8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float sx = s_[j] * x[j];
@@ -459,7 +467,7 @@ __device__ __forceinline__ void fast_group(const Phase& ph, const float (&v)[8],
     } else {
       if (has1) {
         float z8[8];
-        unpack_b8(q1, z8);
+        unpack_h8(q1, z8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = fmaf(s_[j], x[j], z8[j]);
       } else {
@@ -468,20 +476,19 @@ __device__ __forceinline__ void fast_group(const Phase& ph, const float (&v)[8],
       }
     }
   }
-  if (a_out) {
-    uint32_t p[4];
+  uint32_t p[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = T::bf16 ? pack_b2(r[2 * i], r[2 * i + 1]) : pack_h2(r[2 * i], r[2 * i + 1]);
-    tc::tmem_st4(tA + (uint32_t)(4 * g), p);
-    if (pa && T::bf16 && OP != OP_P2STEP) pa[g * 128] = make_uint4(p[0], p[1], p[2], p[3]);
-  }
-  if (pa && (!a_out || !T::bf16 || OP == OP_P2STEP)) {
-    const float o = OP == OP_P2STEP ? om : 1.0f;          // phase 2 stores z-bar pre-scaled for the weight gradient
-    pa[g * 128] = make_uint4(pack_b2(r[0] * o, r[1] * o), pack_b2(r[2] * o, r[3] * o), pack_b2(r[4] * o, r[5] * o),
-                             pack_b2(r[6] * o, r[7] * o));
+  for (int i = 0; i < 4; ++i) p[i] = pack2<OP>(r[2 * i], r[2 * i + 1]);
+  if (a_out) tc::tmem_st4(tA + (uint32_t)(4 * g), p);
+  if (pa) {
+    if (OP == OP_P2STEP)          // phase 2 stores z-bar pre-scaled for the weight gradient
+      pa[g * 128] = make_uint4(pack2<OP>(r[0] * om, r[1] * om), pack2<OP>(r[2] * om, r[3] * om), pack2<OP>(r[4] * om, r[5] * om),
+                               pack2<OP>(r[6] * om, r[7] * om));
+    else
+      pa[g * 128] = make_uint4(p[0], p[1], p[2], p[3]);
   }
   if (OP == OP_P1STEP && pb)
-    pb[g * 128] = make_uint4(pack_b2(r2[0], r2[1]), pack_b2(r2[2], r2[3]), pack_b2(r2[4], r2[5]), pack_b2(r2[6], r2[7]));
+    pb[g * 128] = make_uint4(pack2<OP>(r2[0], r2[1]), pack2<OP>(r2[2], r2[3]), pack2<OP>(r2[4], r2[5]), pack2<OP>(r2[6], r2[7]));
 }
 
 template <int OP>
@@ -549,7 +556,7 @@ __device__ __forceinline__ void fast_phase(const Phase& ph, bool last, uint32_t 
 template <int OP>
 __device__ __forceinline__ bool phase_body(const Phase& ph, bool last, int s, uint32_t tD, uint32_t tA, int c0, long long m,
                                            long long N, const float* sb, const float* srow, uint16_t* stb, uint32_t bar_d_full,
-                                           uint32_t par, uint32_t bar_d_drained, uint32_t bar_a_ready) {
+                                           uint32_t par, uint32_t bar_d_drained, uint32_t bar_a_ready, float sig, float isig) {
   using namespace tc;
   if (OP != OP_OUT32 && OP != OP_STASH && ph.fast) {
     bool ok = true;
@@ -585,7 +592,7 @@ __device__ __forceinline__ bool phase_body(const Phase& ph, bool last, int s, ui
       // the slot's next A operand is what it holds already: release the MMA issuer right away
       if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
     }
-    run_op<OP>(ph, v, half, q0, q1, sb, srow, m, N, c0, tA, stb);
+    run_op<OP>(ph, v, half, q0, q1, sb, srow, m, N, c0, tA, stb, sig, isig);
     if (half == 0) load_aux<OP>(ph, m, c0, 1, q0, q1);     // second half's operands: in flight during its TMEM load
   }
   return ok;
@@ -636,6 +643,7 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t tD = lane_base + (uint32_t)c0;
     uint32_t dcnt = 0;
+    const float sig = a.sigma ? __ldg(a.sigma) : 1.0f, isig = a.sigma ? __ldg(a.sigma + 1) : 1.0f;
     // [128 x w] 16-bit values, row-major in HBM -> slot s (packed columns 0 ..), then signal the slot
     auto aload = [&](int s, long long tile, const void* src, int ld, int w) {
       const long long m = tile * 128 + row;               // < Npad: the buffers are padded to whole tiles
@@ -683,15 +691,15 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
           const uint32_t bf = smem_u32(&d_full), bd = smem_u32(&d_drained), ba = smem_u32(&a_ready[s]), par = dcnt & 1;
           ++dcnt;
           switch (ph.op) {
-            case OP_OUT32: ok = phase_body<OP_OUT32>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
-            case OP_SOFTPLUS: ok = phase_body<OP_SOFTPLUS>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
-            case OP_NSTEP: ok = phase_body<OP_NSTEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
-            case OP_P1STEP: ok = phase_body<OP_P1STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
-            case OP_P2STEP: ok = phase_body<OP_P2STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
-            case OP_RELU: ok = phase_body<OP_RELU>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
-            case OP_LINEAR: ok = phase_body<OP_LINEAR>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
-            case OP_STASH: ok = phase_body<OP_STASH>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
-            default: ok = phase_body<OP_MASK>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba); break;
+            case OP_OUT32: ok = phase_body<OP_OUT32>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            case OP_SOFTPLUS: ok = phase_body<OP_SOFTPLUS>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            case OP_NSTEP: ok = phase_body<OP_NSTEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            case OP_P1STEP: ok = phase_body<OP_P1STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            case OP_P2STEP: ok = phase_body<OP_P2STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            case OP_RELU: ok = phase_body<OP_RELU>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            case OP_LINEAR: ok = phase_body<OP_LINEAR>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            case OP_STASH: ok = phase_body<OP_STASH>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            default: ok = phase_body<OP_MASK>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
           }
           if (!last) {
             if (ph.a_out) {
@@ -831,7 +839,7 @@ inline size_t stash_floats(long long N) { return (size_t)grid_for(N) * 2 * MAX_S
 static inline int debug_sync(cudaStream_t st, const char* what, int tag) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("VDN_SYNC"); on = (e && e[0] == '1') ? 1 : 0; }
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = (cudaError_t)::vdn::take_launch_error();
   if (on && e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (on && e != cudaSuccess) fprintf(stderr, "[vdn] %s (tag %d) failed: %s\n", what, tag, cudaGetErrorString(e));
   return (int)e;
@@ -843,6 +851,16 @@ static inline bool debug_nomix() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("VDN_NOMIX"); on = (e && e[0] == '1') ? 1 : 0; }
   return on == 1;
+}
+
+// invalid table / descriptor (a bug in the caller, fatal for the call): say where
+static inline int bad_value(const char* where, int detail) {
+  fprintf(stderr, "[vdn] invalid value: %s (%d)\n", where, detail);
+  return (int)cudaErrorInvalidValue;
+}
+static inline int trace_err(int e, const char* where) {
+  if (e) fprintf(stderr, "[vdn] %s: CUDA error %d (%s)\n", where, e, cudaGetErrorString((cudaError_t)e));
+  return e;
 }
 
 // Validates the table (the kernel trusts it) and launches.  Returns a cudaError_t value.
@@ -859,7 +877,7 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
     ph.o32_vec = (ph.o32 && ph.act == 0 && ((uintptr_t)ph.o32 & 15) == 0 && (ph.ldo32 & 3) == 0 && (ph.o32_c0 & 7) == 0) ? 1 : 0;
   }
   if (a.N <= 0) return 0;
-  if (a.P < 1 || a.P > MAX_PHASES || !a.a0 || (a.a0_w & 7) || a.a0_w > 256) return (int)cudaErrorInvalidValue;
+  if (a.P < 1 || a.P > MAX_PHASES || !a.a0 || (a.a0_w & 7) || a.a0_w > 256) return bad_value("chain args", a.P);
   double flops = 0.0, bytes = 0.0;
   for (int p = 0; p < a.P; ++p) {
     const Phase& ph = a.ph[p];
@@ -867,16 +885,12 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
         ph.width > ph.n_mma || (ph.a_out && (p == a.P - 1 || (ph.a_wr & 7) || ph.a_wr > 256)) ||
         (ph.aload && (ph.a_out || p == a.P - 1 || (ph.al_w & 7))) || (ph.img_off & 255) ||
         (ph.img2_off >= 0 && (ph.img2_off & 255)) || (ph.a_bf16 != ph.b_bf16))
-      return (int)cudaErrorInvalidValue;
-    if ((ph.op == OP_STASH || ph.stash_r >= 0) && !a.stash) return (int)cudaErrorInvalidValue;
-    {   // storage formats are compiled into the epilogue kinds (OpTraits): the table must agree with them
-      const int op = ph.op;
-      const bool a_bf = (op == OP_P1STEP || op == OP_P2STEP || op == OP_MASK);
-      const bool bad_fmt = (ph.aux0 && !ph.aux0_bf16) || (ph.aux1 && !ph.aux1_bf16) || (ph.o16a && !ph.o16a_bf16) ||
-                           (ph.o16b && op != OP_P1STEP) || (ph.o16a_mul != 1.0f && op != OP_P2STEP) ||
-                           (ph.a_out && p + 1 < a.P && (a.ph[p + 1].a_bf16 != 0) != a_bf);
-      if (bad_fmt) return (int)cudaErrorInvalidValue;
-    }
+      return bad_value("chain phase shape", p);
+    if ((ph.op == OP_STASH || ph.stash_r >= 0) && !a.stash) return bad_value("chain phase stash", p);
+    // every operand is fp16 (OpTraits); cotangent scaling needs the launch's sigma
+    if (ph.a_bf16 || ph.b_bf16 || (ph.o16b && ph.op != OP_P1STEP) || (ph.o16a_mul != 1.0f && ph.op != OP_P2STEP) ||
+        ((ph.r1_scaled || ph.o32_unscale) && !a.sigma))
+      return bad_value("chain phase format", p);
     flops += 2.0 * (double)a.N * ph.n_mma * ph.nks * 16 * (ph.img2_off >= 0 ? 2 : 1);
     const double row16 = 2.0 * (double)a.N;
     if (ph.aux0) bytes += row16 * ph.width;

@@ -13,19 +13,32 @@
 
 #define VDN_LAUNCH_CHECK()                                \
   do {                                                    \
-    cudaError_t _e = cudaGetLastError();                  \
-    if (_e != cudaSuccess) return (int)_e;                \
+    const int _e = ::vdn::take_launch_error();            \
+    if (_e) return _e;                                    \
   } while (0)
 
 namespace vdn {
 
 extern std::atomic<long long> g_launches;  // defined in api.cu; read through vdn_launch_count()
 
+// Launch errors are collected per thread by VDN_LAUNCH itself and fetched with take_launch_error(): the thread's CUDA
+// "last error" may hold a stale, harmless error left by another library of the process, which must not be reported
+// as a failure of this one.
+inline thread_local int g_launch_error = 0;
+inline int take_launch_error() {
+  const int e = g_launch_error;
+  g_launch_error = 0;
+  return e;
+}
+
 // Every kernel launch of the library goes through this macro so the launch count is exact.
-#define VDN_LAUNCH(kernel, grid, block, smem, stream, ...)         \
-  do {                                                             \
-    ++::vdn::g_launches;                                           \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+#define VDN_LAUNCH(kernel, grid, block, smem, stream, ...)                                     \
+  do {                                                                                         \
+    ++::vdn::g_launches;                                                                       \
+    (void)cudaGetLastError();                                                                  \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                \
+    const cudaError_t _le = cudaGetLastError();                                                \
+    if (_le != cudaSuccess && !::vdn::g_launch_error) ::vdn::g_launch_error = (int)_le;        \
   } while (0)
 
 constexpr float kInvSqrt2 = 0.70710678118654752440f;

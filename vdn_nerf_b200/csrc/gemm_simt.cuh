@@ -428,7 +428,7 @@ inline int launch_gemm_nt_simt(int M, int N, int K, const Operand& A, const floa
   prof_begin(PROF_GEMM_NT, st, 2.0 * M * N * K, operand_bytes(A, M) + epilogue_bytes(E, M, N));
   VDN_LAUNCH(gemm_nt_kernel, grid, GEMM_THREADS, 0, st, M, N, K, A, B, ldb, E);
   prof_end(PROF_GEMM_NT, st);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 // Number of row splits used for a wgrad over M rows (also the number of partial slabs needed).
@@ -453,12 +453,12 @@ inline int launch_wgrad(int M, int N, int K, const Operand& A0, const Operand& X
   prof_begin(PROF_WGRAD, st, 2.0 * M * N * K * (A1 ? 2 : 1), operand_bytes(A0, M) + operand_bytes(X0, M));
   VDN_LAUNCH(gemm_tn_kernel, grid, GEMM_THREADS, 0, st, M, N, K, A0, X0, A1 ? *A1 : A0, X1 ? *X1 : X0, A1 ? 2 : 1,
                                                 partials, ldp, rows_per_split);
-  int e = (int)cudaGetLastError();
+  int e = (int)(cudaError_t)::vdn::take_launch_error();
   if (e) return e;
   int total = N * K;
   VDN_LAUNCH(reduce_partials_kernel, (total + 255) / 256, 256, 0, st, partials, S, N, K, ldp, dW, ldd, accumulate);
   prof_end(PROF_WGRAD, st);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 // out[n] (+)= sum_m pro(A)[m,n];  `partials` must hold wgrad_splits(M)*N floats.
@@ -478,10 +478,10 @@ inline int launch_colsum(int M, int N, const Operand& A, float* partials, float*
   const int rows_per_split = (M + S - 1) / S;
   dim3 grid((N + 127) / 128, S);
   VDN_LAUNCH(colsum_partial_kernel, grid, 256, 0, st, M, N, A, partials, rows_per_split);
-  int e = (int)cudaGetLastError();
+  int e = (int)(cudaError_t)::vdn::take_launch_error();
   if (e) return e;
   VDN_LAUNCH(reduce_partials_kernel, (N + 255) / 256, 256, 0, st, partials, S, 1, N, N, out, N, accumulate);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 }  // namespace vdn

@@ -582,7 +582,7 @@ static inline int launch_gemm_nt_tc(int M, int N, int K, const Operand& A, const
   VDN_LAUNCH(gemm_nt_tc_kernel, grid, TC_THREADS, smem, st, M, n_main, nkb, A, B.img, B.img_rows, B.row0, E,
              epilogue_vec_ok(E) ? 1 : 0, wextra, g_tc_fault, dbg);
   prof_end(PROF_TC, st);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 inline int launch_gemm_nt(int M, int N, int K, const Operand& A, const WeightRef& B, const Epilogue& E,

@@ -317,13 +317,13 @@ static inline int launch_wgrad_tc(int M, int N, int K, const Operand& A0, const 
   } else {
     const int ldp = (K + 3) & ~3;
     VDN_LAUNCH(gemm_tn_tc_kernel, grid, TN_THREADS, smem, st, M, N, K, A0, X0, partials, ldp, rows, 0, db, g_tc_fault);
-    int e = (int)cudaGetLastError();
+    int e = (int)(cudaError_t)::vdn::take_launch_error();
     if (e) return e;
     const int total = N * K;
     VDN_LAUNCH(reduce_partials_kernel, (total + 255) / 256, 256, 0, st, partials, S, N, K, ldp, dW, ldd, 0);
   }
   prof_end(PROF_WGRAD, st);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 // Mode dispatch for the weight gradient (single operand pair).  db (nullable): bias gradient, db[n] += sum_m A0[m,n];

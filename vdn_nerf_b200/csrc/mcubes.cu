@@ -68,7 +68,7 @@ extern "C" int vdn_mc_count(const float* u, int nx, int ny, int nz, float thresh
   const long long cells = (long long)(nx - 1) * (ny - 1) * (nz - 1);
   VDN_LAUNCH(mc_count_kernel, (unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream, u, nx, ny, nz, threshold, tri_count,
              counts);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_mc_emit(const float* u, int nx, int ny, int nz, float threshold, const int* tri_count, const int* tri_table,
@@ -78,5 +78,5 @@ extern "C" int vdn_mc_emit(const float* u, int nx, int ny, int nz, float thresho
   const long long cells = (long long)(nx - 1) * (ny - 1) * (nz - 1);
   VDN_LAUNCH(mc_emit_kernel, (unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream, u, nx, ny, nz, threshold, tri_count,
              tri_table, edge_corner, edge_axis, offsets, keys, pos);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }

@@ -58,7 +58,7 @@ inline int launch_embed_rows(const float* x, int ldx, long long N, int d, int L,
   if (total <= 0) return 0;
   VDN_LAUNCH(embed_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, st, x, ldx, N, d, L, scale, e, lde, u, ldu, ucol,
              uscale, u_pad_to);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 // out[m, j] (+)= oscale * sum_c de[m,c] * d e_c / d y_j  (= J_e^T de), j < d.   de rows have ld ldde.
@@ -180,7 +180,7 @@ inline int launch_gather2_rows(const float* a, int lda, int wa, float sa, const 
   const long long tot = N * ldd;
   if (tot <= 0) return 0;
   VDN_LAUNCH(gather2_rows_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, a, lda, wa, sa, b, ldb, wb, sb, N, dst, ldd);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 // dst[m, 0] = a ? a[m] : 0 and dst[m, wreal..ldd) = 0: the columns of a stacked-head cotangent that the following GEMM

@@ -641,7 +641,7 @@ extern "C" int vdn_ray_points(const float* o, const float* d, const float* z, lo
   long long tot = B * n;
   if (tot <= 0) return 0;
   VDN_LAUNCH(ray_points_kernel, (unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream, o, d, z, B, n, pts);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_upsample_step(const float* o, const float* d, const float* z_in, int n, const float* sdf_prev,
@@ -657,7 +657,7 @@ extern "C" int vdn_upsample_step(const float* o, const float* d, const float* z_
   VDN_LAUNCH(upsample_kernel, blocks, RAY_WARPS * 32, 0, (cudaStream_t)stream, o, d, z_in, n, sdf_prev, n_prev, sdf_new,
                                                                       n_new_prev, perm_prev, inv_s, n_imp, B, z_out,
                                                                       sdf_out, perm_out, new_z, new_pts, inds_out);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_merge_sorted(const float* za, int n, const float* zb, int m, long long B, float* z_out,
@@ -666,7 +666,7 @@ extern "C" int vdn_merge_sorted(const float* za, int n, const float* zb, int m, 
   if (n < 0 || m < 0 || n + m > RAY_MAXN || n + m < 1) return (int)cudaErrorInvalidValue;
   unsigned blocks = (unsigned)((B + RAY_WARPS - 1) / RAY_WARPS);
   VDN_LAUNCH(merge_sorted_kernel, blocks, RAY_WARPS * 32, 0, (cudaStream_t)stream, za, n, zb, m, B, z_out, perm);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_fine_prep(const float* o, const float* d, const float* z, float sample_dist, long long B, int S,
@@ -675,7 +675,7 @@ extern "C" int vdn_fine_prep(const float* o, const float* d, const float* z, flo
   if (tot <= 0) return 0;
   VDN_LAUNCH(fine_prep_kernel, (unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream, o, d, z, sample_dist, B, S, dists,
                                                                                   mid_z, pts);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_bg_prep(const float* o, const float* d, const float* z_fine, int S, const float* z_outside, int NO,
@@ -685,7 +685,7 @@ extern "C" int vdn_bg_prep(const float* o, const float* d, const float* z_fine, 
   unsigned blocks = (unsigned)((B + RAY_WARPS - 1) / RAY_WARPS);
   VDN_LAUNCH(bg_prep_kernel, blocks, RAY_WARPS * 32, 0, (cudaStream_t)stream, o, d, z_fine, S, z_outside, NO, sample_dist, B,
                                                                      dists, mid_z, pts4);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 static int fill_comp_args(CompArgs* a, long long B, int S, int NB, int F, const float* o, const float* d,
@@ -717,7 +717,7 @@ extern "C" int vdn_composite_fwd(long long B, int S, int NB, int F, const float*
   unsigned blocks = (unsigned)((B + RAY_WARPS - 1) / RAY_WARPS);
   VDN_LAUNCH(composite_fwd_kernel, blocks, RAY_WARPS * 32, 0, (cudaStream_t)stream, a, weights, cdf, inside, color, dfeat,
                                                                            eik_num, eik_den);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_composite_bwd(long long B, int S, int NB, int F, const float* o, const float* d,
@@ -741,5 +741,5 @@ extern "C" int vdn_composite_bwd(long long B, int S, int NB, int F, const float*
   g.d_var_partial = d_var_partial; g.d_dirs = d_dirs;
   unsigned blocks = (unsigned)((B + RAY_WARPS - 1) / RAY_WARPS);
   VDN_LAUNCH(composite_bwd_kernel, blocks, RAY_WARPS * 32, 0, (cudaStream_t)stream, a, g);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }

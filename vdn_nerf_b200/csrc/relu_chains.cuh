@@ -2,9 +2,9 @@
 // dpt_models/fields.py:148-176) and the NeRF++ background field (fields.py:324-355), forward and backward, each pass
 // ONE chain launch + one grouped weight-gradient launch.
 //
-// Forward passes compute with fp16 operands (A in tensor memory, fp16 weight images); what they save is bf16: the
-// post-ReLU activations HB16_l (at once the ReLU mask of the backward chain and an operand of the weight gradient).
-// Backward passes run bf16 cotangents against bf16 hi/lo weight pairs.  Inputs wider than 256 columns (289-wide colour
+// Everything 16-bit is fp16 (chain_engine.cuh): the forward passes save the post-ReLU activations H16_l (at once the
+// ReLU mask of the backward chain and an operand of the weight gradient); the backward passes run cotangents scaled by
+// the call's power-of-two loss scale sigma (sdf_chains.cuh).  Inputs wider than 256 columns (289-wide colour
 // input, 340-wide NeRF skip layer, 283-wide view layer) are split: the narrow part (extras / embedding) runs first as a
 // small MMA whose accumulator is parked in an fp16 scratch (L2 resident) and added in the epilogue of the main part.
 #pragma once
@@ -21,10 +21,10 @@ struct RnShape {
   const MlpLayout* ly;
 };
 
-// X16 / XB16 [Npad, 64]: the extras of the input row (fields.py:154) as fp16 and bf16, zero padded
+// X16 [Npad, 64]: the extras of the input row (fields.py:154), zero padded
 static __global__ void rn_extras16_kernel(const float* __restrict__ pts, const float* __restrict__ nrm,
                                           const float* __restrict__ view, int L, int mode, long long N, long long Npad,
-                                          __half* __restrict__ x16, __nv_bfloat16* __restrict__ xb16) {
+                                          __half* __restrict__ x16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Npad * 8) return;
   long long m;
@@ -45,17 +45,18 @@ static __global__ void rn_extras16_kernel(const float* __restrict__ pts, const f
     v[j] = r;
   }
   store8_h(x16, i, v);
-  store8_b(xb16, i, v);
 }
 
-// ZL16[m, c] = bf16(d_out[m, c] * act'(out[m, c])) for c < w, zero padded to 128 columns.  kind 0: sigmoid, 1: relu
+// ZL16[m, c] = fp16(sigma * d_out[m, c] * act'(out[m, c])) for c < w, zero padded to 128 columns.  kind 0: sigmoid, 1: relu
 static __global__ void rn_zlast16_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int w, int kind,
-                                         long long N, long long Npad, __nv_bfloat16* __restrict__ dst) {
+                                         const float* __restrict__ sigma, long long N, long long Npad,
+                                         __half* __restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Npad * 16) return;
   long long m;
   int c0;
   ce::blk_decode(i * 8, 128, &m, &c0);
+  const float sg = __ldg(sigma);
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -65,38 +66,38 @@ static __global__ void rn_zlast16_kernel(const float* __restrict__ d_out, const 
       const float d = d_out[m * w + c], o = out[m * w + c];
       r = kind == 0 ? d * ((1.0f - o) * o) : (o > 0.0f ? d : 0.0f);
     }
-    v[j] = r;
+    v[j] = r * sg;
   }
-  store8_b(dst, i, v);
+  store8_hs(dst, i, v);
 }
 
 struct RnChainBufs {
   long long Npad;
-  __half* F16; __nv_bfloat16* FB16; __half* X16; __nv_bfloat16* XB16;
-  __nv_bfloat16* HB16[VDN_MAX_LAYERS];
+  __half* F16; __half* X16;
+  __half* H16[VDN_MAX_LAYERS];
   uint16_t* stash;
-  __nv_bfloat16* ZL16; __nv_bfloat16* ZB16[VDN_MAX_LAYERS];
+  __half* ZL16; __half* ZB16[VDN_MAX_LAYERS];
+  float* sig;
 };
 static inline long long rn_chain_blob_floats(int L, long long N) {
-  return pad128(N) * (128 + 128 + 32 + 32 + (long long)(L - 1) * 128) + (long long)ce::stash_floats(N);
+  return pad128(N) * (128 + 32 + (long long)(L - 1) * 128) + (long long)ce::stash_floats(N);
 }
-static inline long long rn_chain_ws_floats(int L, long long N) { return pad128(N) * (64 + (long long)(L - 1) * 128); }
+static inline long long rn_chain_ws_floats(int L, long long N) { return pad128(N) * (64 + (long long)(L - 1) * 128) + 32; }
 static inline void rn_chain_carve(int L, long long N, float* blob, float* ws, RnChainBufs* b) {
   const long long Np = pad128(N);
   b->Npad = Np;
   if (blob) {
     float* p = blob;
     b->F16 = reinterpret_cast<__half*>(p); p += Np * 128;
-    b->FB16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128;
     b->X16 = reinterpret_cast<__half*>(p); p += Np * 32;
-    b->XB16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 32;
-    for (int l = 0; l < L - 1; ++l) { b->HB16[l] = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128; }
+    for (int l = 0; l < L - 1; ++l) { b->H16[l] = reinterpret_cast<__half*>(p); p += Np * 128; }
     b->stash = reinterpret_cast<uint16_t*>(p);
   }
   if (ws) {
     float* p = ws;
-    b->ZL16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 64;
-    for (int l = 0; l < L - 1; ++l) { b->ZB16[l] = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128; }
+    b->ZL16 = reinterpret_cast<__half*>(p); p += Np * 64;
+    for (int l = 0; l < L - 1; ++l) { b->ZB16[l] = reinterpret_cast<__half*>(p); p += Np * 128; }
+    b->sig = p;
   }
 }
 
@@ -105,10 +106,9 @@ static inline int rn_chain_forward(const RnShape& s, const float* packed, const 
                                    const RnChainBufs& b, cudaStream_t st) {
   const MlpLayout& ly = *s.ly;
   const int L = s.L;
-  int e = launch1d(rn_extras16_kernel, b.Npad * 8, st, points, normals, view_dirs, s.multires_view, s.mode, N, b.Npad, b.X16,
-                   b.XB16);
+  int e = launch1d(rn_extras16_kernel, b.Npad * 8, st, points, normals, view_dirs, s.multires_view, s.mode, N, b.Npad, b.X16);
   if (e) return e;
-  e = launch1d(rows_to_16_kernel, b.Npad * 32, st, feats, ldf, s.F, 1.0f, N, b.Npad, b.F16, b.FB16, 256);   // one read, both formats
+  e = launch1d(rows_to_16_kernel, b.Npad * 32, st, feats, ldf, s.F, 1.0f, (const float*)nullptr, N, b.Npad, b.F16, 256);
   if (e) return e;
   ce::Args a;
   ce::init_args(&a);
@@ -129,7 +129,7 @@ static inline int rn_chain_forward(const RnShape& s, const float* packed, const 
     p.op = ce::OP_RELU; p.width = ly.out_dim[l]; p.bias_off = ly.off_b[l];
     if (l == 0) p.stash_r = 0;
     p.a_out = 1; p.a_wr = 256;
-    p.o16a = b.HB16[l]; p.ldo16a = 256; p.o16a_bf16 = 1;
+    p.o16a = b.H16[l]; p.ldo16a = 256;
   }
   {
     const int lo = L - 1;
@@ -147,68 +147,71 @@ static inline int rn_chain_backward(const RnShape& s, const float* packed, long 
                                     const float* out, const float* d_out, float* dpacked, float* d_cin, cudaStream_t st) {
   const MlpLayout& ly = *s.ly;
   const int L = s.L, lo = L - 1;
-  int e = launch1d(rn_zlast16_kernel, b.Npad * 16, st, d_out, out, s.d_out, s.squeeze_out ? 0 : 1, N, b.Npad, b.ZL16);
+  int e = launch_sigma(b.sig, st, d_out, N, s.d_out, s.d_out, 1.0f);
+  if (e) return e;
+  e = launch1d(rn_zlast16_kernel, b.Npad * 16, st, d_out, out, s.d_out, s.squeeze_out ? 0 : 1, (const float*)b.sig, N, b.Npad,
+               b.ZL16);
   if (e) return e;
   ce::Args a;
   ce::init_args(&a);
-  a.N = N; a.packed = packed;
+  a.N = N; a.packed = packed; a.sigma = b.sig;
   a.a0 = b.ZL16; a.a0_ld = 128; a.a0_w = 128;
   int P = 0;
   for (int l = lo; l >= 1; --l) {      // h-bar_{l-1} = z-bar_l W_l, masked by the sign of h_{l-1}
     ce::Phase& p = a.ph[P++];
     p = ce::make_phase();
-    ce::set_mma_bf16(&p, ly.off_ibt[l], ly.off_ibt2[l], ly.in_ld[l], 0, 0, ly.in_dim[l], ly.out_dim[l]);
+    ce::set_mma(&p, ly.off_iht[l], ly.in_ld[l], 0, 0, ly.in_dim[l], ly.out_dim[l]);
     p.op = ce::OP_MASK; p.width = ly.out_dim[l - 1];
-    p.aux0 = b.HB16[l - 1]; p.ld0 = 256; p.aux0_bf16 = 1;
+    p.aux0 = b.H16[l - 1]; p.ld0 = 256;
     p.a_out = (l > 1 || d_cin) ? 1 : 0; p.a_wr = 256;
-    p.o16a = b.ZB16[l - 1]; p.ldo16a = 256; p.o16a_bf16 = 1;
+    p.o16a = b.ZB16[l - 1]; p.ldo16a = 256;
   }
   if (d_cin) {     // cotangent of the input row, [feature | extras] like the packed layer 0
     {
       ce::Phase& p = a.ph[P++];
       p = ce::make_phase();
-      ce::set_mma_bf16(&p, ly.off_ibt[0], ly.off_ibt2[0], ly.in_ld[0], 0, 0, s.F, ly.out_dim[0]);
+      ce::set_mma(&p, ly.off_iht[0], ly.in_ld[0], 0, 0, s.F, ly.out_dim[0]);
       p.op = ce::OP_OUT32; p.width = s.F;
-      p.o32 = d_cin; p.ldo32 = s.ldIn; p.o32_c0 = 0; p.o32_w = s.F;
+      p.o32 = d_cin; p.ldo32 = s.ldIn; p.o32_c0 = 0; p.o32_w = s.F; p.o32_unscale = 1;
     }
     {
       ce::Phase& p = a.ph[P++];
       p = ce::make_phase();
-      ce::set_mma_bf16(&p, ly.off_ibt[0], ly.off_ibt2[0], ly.in_ld[0], s.F, 0, s.nextra, ly.out_dim[0]);
+      ce::set_mma(&p, ly.off_iht[0], ly.in_ld[0], s.F, 0, s.nextra, ly.out_dim[0]);
       p.op = ce::OP_OUT32; p.width = s.nextra;
-      p.o32 = d_cin + s.F; p.ldo32 = s.ldIn; p.o32_c0 = 0; p.o32_w = s.nextra;
+      p.o32 = d_cin + s.F; p.ldo32 = s.ldIn; p.o32_c0 = 0; p.o32_w = s.nextra; p.o32_unscale = 1;
     }
   }
   a.P = P;
   e = ce::launch(a, st, PROF_CHAIN_TRAIN);
   if (e) return e;
-  wg::Builder w(N, dpacked);
-  const int mZL = w.add_x(b.ZL16, 128, s.d_out), mF = w.add_y(b.FB16, 256, s.F), mX = w.add_y(b.XB16, 64, s.nextra);
+  wg::Builder w(N, dpacked, b.sig);
+  const int mZL = w.add_x(b.ZL16, 128, s.d_out), mF = w.add_y(b.F16, 256, s.F), mX = w.add_y(b.X16, 64, s.nextra);
   int mH[VDN_MAX_LAYERS], mZ[VDN_MAX_LAYERS];
   for (int l = 0; l < L - 1; ++l) {
-    mH[l] = w.add_y(b.HB16[l], 256, ly.in_dim[l + 1]);
+    mH[l] = w.add_y(b.H16[l], 256, ly.in_dim[l + 1]);
     mZ[l] = w.add_x(b.ZB16[l], 256, ly.out_dim[l]);
   }
   {
     wg::Job* j = w.add_job(s.d_out, ly.in_dim[lo], ly.off_w[lo], ly.in_ld[lo], 1.0f, ly.off_b[lo], 1.0f);
-    wg::Builder::add_seg(j, mZL, 0, 1, mH[lo - 1], 0, 1);
+    wg::Builder::add_seg(j, mZL, 0, mH[lo - 1], 0);
   }
   for (int l = 1; l < L - 1; ++l) {
     wg::Job* j = w.add_job(ly.out_dim[l], ly.in_dim[l], ly.off_w[l], ly.in_ld[l], 1.0f, ly.off_b[l], 1.0f);
-    wg::Builder::add_seg(j, mZ[l], 0, 1, mH[l - 1], 0, 1);
+    wg::Builder::add_seg(j, mZ[l], 0, mH[l - 1], 0);
   }
   {
     wg::Job* j = w.add_job(ly.out_dim[0], s.F, ly.off_w[0], ly.in_ld[0], 1.0f, ly.off_b[0], 1.0f);
-    wg::Builder::add_seg(j, mZ[0], 0, 1, mF, 0, 1);
+    wg::Builder::add_seg(j, mZ[0], 0, mF, 0);
     wg::Job* j2 = w.add_job(ly.out_dim[0], s.nextra, ly.off_w[0] + s.F, ly.in_ld[0], 1.0f, -1, 1.0f);
-    wg::Builder::add_seg(j2, mZ[0], 0, 1, mX, 0, 1);
+    wg::Builder::add_seg(j2, mZ[0], 0, mX, 0);
   }
   return w.launch(st, PROF_WGRAD16);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // NeRF++ background field.  Packed layers: 0..D-1 pts_linears (layer skip+1 takes [hidden | embedding]),
-// D = [alpha ; feature] (fp16 / bf16 images rotated: features first), D+1 = views_linears.0 on [feature | view
+// D = [alpha ; feature] (weight images rotated: features first), D+1 = views_linears.0 on [feature | view
 // embedding], D+2 = [rgb ; dpt].
 // ------------------------------------------------------------------------------------------------------------
 struct NerfShape {
@@ -216,10 +219,9 @@ struct NerfShape {
   const MlpLayout* ly;
 };
 
-// EV16 / EVB16 [Npad, 128]: columns 0 .. d_e-1 the point embedding (zero to 95), 96 .. 96+d_ev-1 the view embedding
+// EV16 [Npad, 128]: columns 0 .. d_e-1 the point embedding (zero to 95), 96 .. 96+d_ev-1 the view embedding
 static __global__ void nerf_in16_kernel(const float* __restrict__ pts, const float* __restrict__ views, int d_in, int L,
-                                        int Lv, long long N, long long Npad, __half* __restrict__ ev16,
-                                        __nv_bfloat16* __restrict__ evb16) {
+                                        int Lv, long long N, long long Npad, __half* __restrict__ ev16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Npad * 16) return;
   long long m;
@@ -237,24 +239,24 @@ static __global__ void nerf_in16_kernel(const float* __restrict__ pts, const flo
     v[j] = r;
   }
   store8_h(ev16, i, v);
-  store8_b(evb16, i, v);
 }
 
 struct NerfChainBufs {
   long long Npad;
-  __half* EV16; __nv_bfloat16* EVB16;
-  __nv_bfloat16* HB16[VDN_MAX_LAYERS];
-  __nv_bfloat16* FTB16; __nv_bfloat16* HVB16;
+  __half* EV16;
+  __half* H16[VDN_MAX_LAYERS];
+  __half* FT16; __half* HV16;
   uint16_t* stash;
-  __nv_bfloat16* ZO16; __nv_bfloat16* SG16; __nv_bfloat16* ZV16; __nv_bfloat16* ZF16;
-  __nv_bfloat16* ZB16[VDN_MAX_LAYERS];
+  __half* ZO16; __half* SG16; __half* ZV16; __half* ZF16;
+  __half* ZB16[VDN_MAX_LAYERS];
   float* DVE; float* EE0; float* EE1;
+  float* sig;
 };
 static inline long long nerf_chain_blob_floats(int D, long long N) {
-  return pad128(N) * (64 + 64 + (long long)D * 128 + 128 + 64) + (long long)ce::stash_floats(N);
+  return pad128(N) * (64 + (long long)D * 128 + 128 + 64) + (long long)ce::stash_floats(N);
 }
 static inline long long nerf_chain_ws_floats(int D, long long N) {
-  return pad128(N) * (64 + 32 + 64 + 128 + (long long)D * 128 + 32 + 96 + 96);
+  return pad128(N) * (64 + 4 + 64 + 128 + (long long)D * 128 + 32 + 96 + 96) + 32;
 }
 static inline void nerf_chain_carve(int D, long long N, float* blob, float* ws, NerfChainBufs* b) {
   const long long Np = pad128(N);
@@ -262,22 +264,22 @@ static inline void nerf_chain_carve(int D, long long N, float* blob, float* ws, 
   if (blob) {
     float* p = blob;
     b->EV16 = reinterpret_cast<__half*>(p); p += Np * 64;
-    b->EVB16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 64;
-    for (int l = 0; l < D; ++l) { b->HB16[l] = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128; }
-    b->FTB16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128;
-    b->HVB16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 64;
+    for (int l = 0; l < D; ++l) { b->H16[l] = reinterpret_cast<__half*>(p); p += Np * 128; }
+    b->FT16 = reinterpret_cast<__half*>(p); p += Np * 128;
+    b->HV16 = reinterpret_cast<__half*>(p); p += Np * 64;
     b->stash = reinterpret_cast<uint16_t*>(p);
   }
   if (ws) {
     float* p = ws;
-    b->ZO16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 64;
-    b->SG16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 32;
-    b->ZV16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 64;
-    b->ZF16 = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128;
-    for (int l = 0; l < D; ++l) { b->ZB16[l] = reinterpret_cast<__nv_bfloat16*>(p); p += Np * 128; }
+    b->ZO16 = reinterpret_cast<__half*>(p); p += Np * 64;
+    b->SG16 = reinterpret_cast<__half*>(p); p += Np * 4;
+    b->ZV16 = reinterpret_cast<__half*>(p); p += Np * 64;
+    b->ZF16 = reinterpret_cast<__half*>(p); p += Np * 128;
+    for (int l = 0; l < D; ++l) { b->ZB16[l] = reinterpret_cast<__half*>(p); p += Np * 128; }
     b->DVE = p; p += Np * 32;
     b->EE0 = p; p += Np * 96;
-    b->EE1 = p;
+    b->EE1 = p; p += Np * 96;
+    b->sig = p;
   }
 }
 
@@ -286,8 +288,7 @@ static inline int nerf_chain_forward(const NerfShape& s, const float* packed, co
                                      cudaStream_t st) {
   const MlpLayout& ly = *s.ly;
   const int D = s.D;
-  int e = launch1d(nerf_in16_kernel, b.Npad * 16, st, pts, views, s.d_in, s.multires, s.multires_view, N, b.Npad, b.EV16,
-                   b.EVB16);
+  int e = launch1d(nerf_in16_kernel, b.Npad * 16, st, pts, views, s.d_in, s.multires, s.multires_view, N, b.Npad, b.EV16);
   if (e) return e;
   ce::Args a;
   ce::init_args(&a);
@@ -313,7 +314,7 @@ static inline int nerf_chain_forward(const NerfShape& s, const float* packed, co
     p.op = ce::OP_RELU; p.width = s.W; p.bias_off = ly.off_b[l];
     if (l == s.skip + 1 && s.skip >= 0) p.stash_r = 0;
     p.a_out = 1; p.a_wr = 256;
-    p.o16a = b.HB16[l]; p.ldo16a = 256; p.o16a_bf16 = 1;
+    p.o16a = b.H16[l]; p.ldo16a = 256;
   }
   {   // alpha head: image position W holds output 0 (orot = 1)
     ce::Phase& p = a.ph[P++];
@@ -328,7 +329,7 @@ static inline int nerf_chain_forward(const NerfShape& s, const float* packed, co
     ce::set_mma(&p, ly.off_ih[D], ly.out_ld[D], 0, 0, s.W, s.W);
     p.op = ce::OP_LINEAR; p.width = s.W; p.bias_off = ly.off_b[D] + 1;
     p.a_out = 1; p.a_wr = 256;
-    p.o16a = b.FTB16; p.ldo16a = 256; p.o16a_bf16 = 1;
+    p.o16a = b.FT16; p.ldo16a = 256;
   }
   {   // view layer
     ce::Phase& p = a.ph[P++];
@@ -336,7 +337,7 @@ static inline int nerf_chain_forward(const NerfShape& s, const float* packed, co
     ce::set_mma(&p, ly.off_ih[D + 1], ly.out_ld[D + 1], 0, 0, s.W / 2, s.W);
     p.op = ce::OP_RELU; p.width = s.W / 2; p.bias_off = ly.off_b[D + 1]; p.stash_r = 1;
     p.a_out = 1; p.a_wr = 128;
-    p.o16a = b.HVB16; p.ldo16a = 128; p.o16a_bf16 = 1;
+    p.o16a = b.HV16; p.ldo16a = 128;
   }
   {   // [rgb ; dpt]
     const int no = s.rgb_dims + s.dpt_dim;
@@ -357,112 +358,116 @@ static inline int nerf_chain_backward(const NerfShape& s, const float* packed, c
   const MlpLayout& ly = *s.ly;
   const int D = s.D;
   const int no = s.rgb_dims + s.dpt_dim;
-  int e = launch1d(gather2_bf16_kernel, b.Npad * 16, st, d_rgb, s.rgb_dims, s.rgb_dims, s.dpt_dim > 0 ? d_dpt : nullptr,
-                   s.dpt_dim, s.dpt_dim, N, b.Npad, b.ZO16, 128);
+  const float* dd = s.dpt_dim > 0 ? d_dpt : nullptr;
+  int e = launch_sigma(b.sig, st, d_rgb, d_rgb ? N : 0, s.rgb_dims, s.rgb_dims, 1.0f, dd, dd ? N : 0, s.dpt_dim > 0 ? s.dpt_dim : 1,
+                       s.dpt_dim > 0 ? s.dpt_dim : 1, 1.0f, d_sigma, d_sigma ? N : 0, 1, 1, 1.0f);
   if (e) return e;
-  e = launch1d(rows_to_16_kernel, b.Npad, st, d_sigma, 1, 1, 1.0f, N, b.Npad, (__half*)nullptr, b.SG16, 8);
+  e = launch1d(gather2_16_kernel, b.Npad * 16, st, d_rgb, s.rgb_dims, s.rgb_dims, dd, s.dpt_dim, s.dpt_dim, (const float*)b.sig, N,
+               b.Npad, b.ZO16, 128);
+  if (e) return e;
+  e = launch1d(rows_to_16_kernel, b.Npad, st, d_sigma, 1, 1, 1.0f, (const float*)b.sig, N, b.Npad, b.SG16, 8);
   if (e) return e;
   ce::Args a;
   ce::init_args(&a);
-  a.N = N; a.packed = packed;
+  a.N = N; a.packed = packed; a.sigma = b.sig;
   a.a0 = b.ZO16; a.a0_ld = 128; a.a0_w = 128;
   a.row_off[0] = ly.off_w[D]; a.row_len[0] = s.W;       // alpha row of the stacked head
   int P = 0;
   {   // [rgb ; dpt] -> view layer
     ce::Phase& p = a.ph[P++];
     p = ce::make_phase();
-    ce::set_mma_bf16(&p, ly.off_ibt[D + 2], ly.off_ibt2[D + 2], ly.in_ld[D + 2], 0, 0, s.W / 2, no);
+    ce::set_mma(&p, ly.off_iht[D + 2], ly.in_ld[D + 2], 0, 0, s.W / 2, no);
     p.op = ce::OP_MASK; p.width = s.W / 2;
-    p.aux0 = b.HVB16; p.ld0 = 128; p.aux0_bf16 = 1;
+    p.aux0 = b.HV16; p.ld0 = 128;
     p.a_out = 1; p.a_wr = 128;
-    p.o16a = b.ZV16; p.ldo16a = 128; p.o16a_bf16 = 1;
+    p.o16a = b.ZV16; p.ldo16a = 128;
   }
   if (d_views) {   // view-embedding tail of the view layer's input cotangent
     ce::Phase& p = a.ph[P++];
     p = ce::make_phase();
-    ce::set_mma_bf16(&p, ly.off_ibt[D + 1], ly.off_ibt2[D + 1], ly.in_ld[D + 1], s.W, 0, s.d_ev, s.W / 2);
+    ce::set_mma(&p, ly.off_iht[D + 1], ly.in_ld[D + 1], s.W, 0, s.d_ev, s.W / 2);
     p.op = ce::OP_OUT32; p.width = s.d_ev;
-    p.o32 = b.DVE; p.ldo32 = 32; p.o32_c0 = 0; p.o32_w = s.d_ev;
+    p.o32 = b.DVE; p.ldo32 = 32; p.o32_c0 = 0; p.o32_w = s.d_ev; p.o32_unscale = 1;
   }
   {   // view layer -> feature (linear head: no mask)
     ce::Phase& p = a.ph[P++];
     p = ce::make_phase();
-    ce::set_mma_bf16(&p, ly.off_ibt[D + 1], ly.off_ibt2[D + 1], ly.in_ld[D + 1], 0, 0, s.W, s.W / 2);
+    ce::set_mma(&p, ly.off_iht[D + 1], ly.in_ld[D + 1], 0, 0, s.W, s.W / 2);
     p.op = ce::OP_MASK; p.width = s.W;
     p.a_out = 1; p.a_wr = 256;
-    p.o16a = b.ZF16; p.ldo16a = 256; p.o16a_bf16 = 1;
+    p.o16a = b.ZF16; p.ldo16a = 256;
   }
   {   // stacked head -> h_{D-1}: features through the MMA, the alpha row as a rank-1 term
     ce::Phase& p = a.ph[P++];
     p = ce::make_phase();
-    ce::set_mma_bf16(&p, ly.off_ibt[D], ly.off_ibt2[D], ly.in_ld[D], 0, 0, s.W, s.W);
+    ce::set_mma(&p, ly.off_iht[D], ly.in_ld[D], 0, 0, s.W, s.W);
     p.op = ce::OP_MASK; p.width = s.W;
-    if (d_sigma) { p.r1 = d_sigma; p.r1_stride = 1; p.r1_mul = 1.0f; p.r1_row = 0; }
-    p.aux0 = b.HB16[D - 1]; p.ld0 = 256; p.aux0_bf16 = 1;
+    if (d_sigma) { p.r1 = d_sigma; p.r1_stride = 1; p.r1_mul = 1.0f; p.r1_row = 0; p.r1_scaled = 1; }
+    p.aux0 = b.H16[D - 1]; p.ld0 = 256;
     p.a_out = 1; p.a_wr = 256;
-    p.o16a = b.ZB16[D - 1]; p.ldo16a = 256; p.o16a_bf16 = 1;
+    p.o16a = b.ZB16[D - 1]; p.ldo16a = 256;
   }
   for (int l = D - 1; l >= 1; --l) {
     if (d_pts && s.skip >= 0 && l == s.skip + 1) {   // embedding tail of the skip concat
       ce::Phase& p = a.ph[P++];
       p = ce::make_phase();
-      ce::set_mma_bf16(&p, ly.off_ibt[l], ly.off_ibt2[l], ly.in_ld[l], s.W, 0, s.d_e, s.W);
+      ce::set_mma(&p, ly.off_iht[l], ly.in_ld[l], s.W, 0, s.d_e, s.W);
       p.op = ce::OP_OUT32; p.width = s.d_e;
-      p.o32 = b.EE1; p.ldo32 = 96; p.o32_c0 = 0; p.o32_w = s.d_e;
+      p.o32 = b.EE1; p.ldo32 = 96; p.o32_c0 = 0; p.o32_w = s.d_e; p.o32_unscale = 1;
     }
     ce::Phase& p = a.ph[P++];
     p = ce::make_phase();
-    ce::set_mma_bf16(&p, ly.off_ibt[l], ly.off_ibt2[l], ly.in_ld[l], 0, 0, s.W, s.W);
+    ce::set_mma(&p, ly.off_iht[l], ly.in_ld[l], 0, 0, s.W, s.W);
     p.op = ce::OP_MASK; p.width = s.W;
-    p.aux0 = b.HB16[l - 1]; p.ld0 = 256; p.aux0_bf16 = 1;
+    p.aux0 = b.H16[l - 1]; p.ld0 = 256;
     p.a_out = (l > 1 || d_pts) ? 1 : 0; p.a_wr = 256;
-    p.o16a = b.ZB16[l - 1]; p.ldo16a = 256; p.o16a_bf16 = 1;
+    p.o16a = b.ZB16[l - 1]; p.ldo16a = 256;
   }
   if (d_pts) {
     ce::Phase& p = a.ph[P++];
     p = ce::make_phase();
-    ce::set_mma_bf16(&p, ly.off_ibt[0], ly.off_ibt2[0], ly.in_ld[0], 0, 0, s.d_e, s.W);
+    ce::set_mma(&p, ly.off_iht[0], ly.in_ld[0], 0, 0, s.d_e, s.W);
     p.op = ce::OP_OUT32; p.width = s.d_e;
-    p.o32 = b.EE0; p.ldo32 = 96; p.o32_c0 = 0; p.o32_w = s.d_e;
+    p.o32 = b.EE0; p.ldo32 = 96; p.o32_c0 = 0; p.o32_w = s.d_e; p.o32_unscale = 1;
   }
   a.P = P;
   e = ce::launch(a, st, PROF_CHAIN_TRAIN);
   if (e) return e;
   // ---- weight / bias gradients ----
-  wg::Builder w(N, dpacked);
+  wg::Builder w(N, dpacked, b.sig);
   const int mZO = w.add_x(b.ZO16, 128, no), mSG = w.add_x(b.SG16, 8, 1), mZV = w.add_x(b.ZV16, 128, s.W / 2);
-  const int mZF = w.add_x(b.ZF16, 256, s.W), mFT = w.add_y(b.FTB16, 256, s.W), mHV = w.add_y(b.HVB16, 128, s.W / 2);
-  const int mEVe = w.add_y(b.EVB16, 128, s.d_e), mEVv = w.add_y(b.EVB16, 128, s.d_ev);   // point / view embedding parts
+  const int mZF = w.add_x(b.ZF16, 256, s.W), mFT = w.add_y(b.FT16, 256, s.W), mHV = w.add_y(b.HV16, 128, s.W / 2);
+  const int mEVe = w.add_y(b.EV16, 128, s.d_e), mEVv = w.add_y(b.EV16, 128, s.d_ev);   // point / view embedding parts
   int mH[VDN_MAX_LAYERS], mZ[VDN_MAX_LAYERS];
-  for (int l = 0; l < D; ++l) { mH[l] = w.add_y(b.HB16[l], 256, s.W); mZ[l] = w.add_x(b.ZB16[l], 256, s.W); }
+  for (int l = 0; l < D; ++l) { mH[l] = w.add_y(b.H16[l], 256, s.W); mZ[l] = w.add_x(b.ZB16[l], 256, s.W); }
   {   // [rgb ; dpt]
     wg::Job* j = w.add_job(no, s.W / 2, ly.off_w[D + 2], ly.in_ld[D + 2], 1.0f, ly.off_b[D + 2], 1.0f);
-    wg::Builder::add_seg(j, mZO, 0, 1, mHV, 0, 1);
+    wg::Builder::add_seg(j, mZO, 0, mHV, 0);
   }
   {   // view layer: feature columns, view-embedding columns
     wg::Job* j = w.add_job(s.W / 2, s.W, ly.off_w[D + 1], ly.in_ld[D + 1], 1.0f, ly.off_b[D + 1], 1.0f);
-    wg::Builder::add_seg(j, mZV, 0, 1, mFT, 0, 1);
+    wg::Builder::add_seg(j, mZV, 0, mFT, 0);
     wg::Job* j2 = w.add_job(s.W / 2, s.d_ev, ly.off_w[D + 1] + s.W, ly.in_ld[D + 1], 1.0f, -1, 1.0f);
-    wg::Builder::add_seg(j2, mZV, 0, 1, mEVv, 96, 1);
+    wg::Builder::add_seg(j2, mZV, 0, mEVv, 96);
   }
   {   // stacked head: feature rows 1 .. W, alpha row 0
     wg::Job* j = w.add_job(s.W, s.W, ly.off_w[D] + ly.in_ld[D], ly.in_ld[D], 1.0f, ly.off_b[D] + 1, 1.0f);
-    wg::Builder::add_seg(j, mZF, 0, 1, mH[D - 1], 0, 1);
+    wg::Builder::add_seg(j, mZF, 0, mH[D - 1], 0);
     if (d_sigma) {
       wg::Job* j2 = w.add_job(1, s.W, ly.off_w[D], ly.in_ld[D], 1.0f, ly.off_b[D], 1.0f);
-      wg::Builder::add_seg(j2, mSG, 0, 1, mH[D - 1], 0, 1);
+      wg::Builder::add_seg(j2, mSG, 0, mH[D - 1], 0);
     }
   }
   for (int l = D - 1; l >= 0; --l) {
     if (l == 0) {
       wg::Job* j = w.add_job(s.W, s.d_e, ly.off_w[0], ly.in_ld[0], 1.0f, ly.off_b[0], 1.0f);
-      wg::Builder::add_seg(j, mZ[0], 0, 1, mEVe, 0, 1);
+      wg::Builder::add_seg(j, mZ[0], 0, mEVe, 0);
     } else {
       wg::Job* j = w.add_job(s.W, s.W, ly.off_w[l], ly.in_ld[l], 1.0f, ly.off_b[l], 1.0f);
-      wg::Builder::add_seg(j, mZ[l], 0, 1, mH[l - 1], 0, 1);
+      wg::Builder::add_seg(j, mZ[l], 0, mH[l - 1], 0);
       if (s.skip >= 0 && l == s.skip + 1) {
         wg::Job* j2 = w.add_job(s.W, s.d_e, ly.off_w[l] + s.W, ly.in_ld[l], 1.0f, -1, 1.0f);
-        wg::Builder::add_seg(j2, mZ[l], 0, 1, mEVe, 0, 1);
+        wg::Builder::add_seg(j2, mZ[l], 0, mEVe, 0);
       }
     }
   }
@@ -478,7 +483,7 @@ static inline int nerf_chain_backward(const NerfShape& s, const float* packed, c
     VDN_LAUNCH(embed_vjp_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, views, 3, N, 3, s.multires_view, 1.0f, b.DVE, 32,
                nullptr, 0, 0.0f, 1.0f, d_views, 3, 0);
   }
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 }  // namespace vdn

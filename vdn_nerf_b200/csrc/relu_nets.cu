@@ -92,7 +92,7 @@ extern "C" int vdn_rendernet_forward(const int* cfg, const float* packed, const 
   VDN_LAUNCH(rendernet_input_kernel, (unsigned)((threads + 255) / 256), 256, 0, st, points, normals, view_dirs, feats, ldf,
                                                                            c.d_feature, c.multires_view, c.mode, N,
                                                                            CIN, c.ldIn);
-  int e = (int)cudaGetLastError();
+  int e = (int)(cudaError_t)::vdn::take_launch_error();
   if (e) return e;
   for (int l = 0; l < c.L; ++l) {
     Operand A = (l == 0) ? make_operand(CIN, c.ldIn, c.ldIn, c.in0)
@@ -148,7 +148,7 @@ extern "C" int vdn_rendernet_backward(const int* cfg, const float* packed, long 
     long long tot = N * ly.out_ld[L - 1];
     VDN_LAUNCH(act_backward_pad_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, d_out, out, c.d_out, N, ZL,
                                                                           ly.out_ld[L - 1], c.squeeze_out ? 0 : 1);
-    int e = (int)cudaGetLastError();
+    int e = (int)(cudaError_t)::vdn::take_launch_error();
     if (e) return e;
   }
   for (int l = L - 1; l >= 0; --l) {
@@ -404,7 +404,7 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
       const long long tot = N * (1 + ldh - (1 + c.W));
       VDN_LAUNCH(head_edges_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, d_sigma, N, ZHEAD, ldh, 1 + c.W);
     }
-    e = (int)cudaGetLastError();
+    e = (int)(cudaError_t)::vdn::take_launch_error();
     if (e) return e;
     Epilogue E = make_epilogue(EPI_STORE, nullptr, ZHEAD, ldh);
     E.coff = 1;
@@ -465,5 +465,5 @@ extern "C" int vdn_nerf_backward(const int* cfg, const float* packed, const floa
                                                                    c.multires_view, 1.0f, DVIN, c.ldV, nullptr, 0,
                                                                    0.0f, 1.0f, d_views, c.d_in_view, 0);
   }
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }

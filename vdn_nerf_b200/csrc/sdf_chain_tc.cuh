@@ -447,7 +447,7 @@ static inline int launch_sdf_chain(const MlpLayout& ly, int d_in, int multires, 
     VDN_LAUNCH(sdf_chain_tc_kernel<false>, grid, CH_THREADS, CH_SMEM, st, a, g_tc_fault, g_tc_dbg);
   }
   prof_end(PROF_CHAIN, st);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 }  // namespace vdn

@@ -255,7 +255,7 @@ extern "C" int vdn_grid_sdf(const int* cfg, float scale, const float* packed, co
     if (r >= 0) return r;
   }
   VDN_LAUNCH(grid_points_kernel, (unsigned)((count + 255) / 256), 256, 0, st, xs, ys, zs, i0, ny, nz, count, pts);
-  int e = (int)cudaGetLastError();
+  int e = (int)(cudaError_t)::vdn::take_launch_error();
   if (e) return e;
   return sdf_forward_impl(c, packed, pts, count, u_slab, 1, nullptr, 0, blob, 0, out_mul, st);
 }
@@ -294,7 +294,7 @@ extern "C" int vdn_sdf_normals(const int* cfg, float scale, const float* packed,
   long long tot = N * c.d_in;
   VDN_LAUNCH(embed_vjp_kernel, (unsigned)((tot + 255) / 256), 256, 0, st, x, c.d_in, N, c.d_in, c.multires, c.scale, g.DE,
                                                                  c.ldE, nullptr, 0, 0.0f, 1.0f, normals, c.d_in, 0);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" long long vdn_sdf_bwd_ws_floats(const int* cfg, long long N) {
@@ -356,7 +356,7 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
                                                                  d_normals, c.d_in, DEB, c.ldE,
                                                                  c.skip >= 0 ? QS : nullptr, c.ldH, qcol, kInvSqrt2,
                                                                  c.ldH);
-    e = (int)cudaGetLastError();
+    e = (int)(cudaError_t)::vdn::take_launch_error();
     if (e) return e;
     for (int l = 0; l <= L - 2; ++l) {
       Operand qbar = (l == 0) ? make_operand(DEB, c.ldE, c.ldE, c.d_e)
@@ -429,7 +429,7 @@ extern "C" int vdn_sdf_backward(const int* cfg, float scale, const float* packed
                                                                         d_normals, c.d_in, g.DE, c.ldE, nullptr, 0,
                                                                         c.scale, d_x, c.d_in);
     }
-    e = (int)cudaGetLastError();
+    e = (int)(cudaError_t)::vdn::take_launch_error();
     if (e) return e;
   }
   return 0;

@@ -141,7 +141,7 @@ extern "C" int vdn_adam_step(int n_tensors, float* const* params, const float* c
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
   VDN_LAUNCH(adam_step_kernel, dim3(bx, n_tensors), 256, 0, (cudaStream_t)stream, a, hyper_dev);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_color_loss(const float* color, const float* true_rgb, const float* mask, long long B, float* sums,
@@ -151,14 +151,14 @@ extern "C" int vdn_color_loss(const float* color, const float* true_rgb, const f
   cudaError_t e = cudaMemsetAsync(sums, 0, 3 * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   VDN_LAUNCH(color_loss_kernel, (unsigned)((B + 255) / 256), 256, 0, st, color, true_rgb, mask, B, sums, d_color);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_raygen_fwd(const float* px, const float* py, long long B, const float* kinv, const float* pose,
                               float* rays_o, float* rays_d, void* stream) {
   if (B <= 0) return 0;
   VDN_LAUNCH(raygen_fwd_kernel, (unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream, px, py, B, kinv, pose, rays_o, rays_d);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_raygen_bwd(const float* px, const float* py, long long B, const float* kinv, const float* d_rays_o,
@@ -168,5 +168,5 @@ extern "C" int vdn_raygen_bwd(const float* px, const float* py, long long B, con
   cudaError_t e = cudaMemsetAsync(d_pose, 0, 12 * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   VDN_LAUNCH(raygen_bwd_kernel, (unsigned)((B + 255) / 256), 256, 0, st, px, py, B, kinv, d_rays_o, d_rays_d, d_pose);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }

@@ -193,7 +193,7 @@ extern "C" int vdn_mlp_pack(int L, const int* in_dims, const int* out_dims, cons
   const int threads = 256;
   const int blocks = (start * 32 + threads - 1) / threads;
   VDN_LAUNCH(pack_weights_kernel, blocks, threads, 0, st, a, packed);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }
 
 extern "C" int vdn_mlp_unpack_grads(int L, const int* in_dims, const int* out_dims, const float* const* v,
@@ -221,5 +221,5 @@ extern "C" int vdn_mlp_unpack_grads(int L, const int* in_dims, const int* out_di
   const int threads = 256;
   const int blocks = (start * 32 + threads - 1) / threads;
   VDN_LAUNCH(unpack_grads_kernel, blocks, threads, 0, (cudaStream_t)stream, a, dpacked);
-  return (int)cudaGetLastError();
+  return (int)(cudaError_t)::vdn::take_launch_error();
 }

@@ -3,8 +3,9 @@
 //
 //     dW_l[out, in] += scale * sum_p  X_l[p, out] * Y_l[p, in]         (W-bar += z-bar^T u, delta^T q-bar)
 //
-// from the 16-bit operand tensors the chain kernels (chain_engine.cuh) left in HBM: X = a cotangent (bf16) or the
-// normals-pass delta, Y = the layer input or a phase-1 cotangent, all bf16 (kind::f16 cannot mix formats), tile-blocked.
+// from the fp16 operand tensors the chain kernels (chain_engine.cuh) left in HBM: X = a cotangent or the normals-pass
+// delta, Y = the layer input or a phase-1 cotangent, tile-blocked.  Exactly one operand of every segment is a cotangent
+// and carries the call's loss scale sigma (chain_engine.cuh), so the flush multiplies by 1 / sigma (Args::sigma[1]).
 // A "job" is one (layer, output-row block) with up to two (X, Y) segments that share an accumulator
 // (W-bar_l = [z-bar ; delta]^T [u ; q-bar]); the batch is split over the CTAs so that (jobs x splits) fills one wave of
 // the 148 SMs, every CTA streaming its points exactly once:
@@ -40,7 +41,6 @@ struct Job {
   int nseg;                     // 1 or 2 segments accumulated into the same tile
   int xmap[2], ymap[2];         // tensor-map indices
   int xcol[2], ycol[2];         // first column (element) inside the tensor
-  int xbf16[2], ybf16[2];
   int m_tiles;                  // 128-row halves of the output block (1 or 2)
   int n_mma;                    // MMA N (multiple of 16, <= 256)
   int rows, cols;               // valid extent of the output block
@@ -57,11 +57,12 @@ struct alignas(64) Args {
   Job jobs[MAX_JOBS];
   Unit units[MAX_UNITS];
   float* dpacked;
+  const float* sigma;           // device {sigma, 1 / sigma} of the backward call (null: 1)
 };
 
-__device__ __forceinline__ uint32_t idesc_mn(uint32_t M, uint32_t N, int a_bf16, int b_bf16) {
-  return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) |
-         ((M >> 4) << 24);
+// fp16 x fp16 -> fp32, both operands MN-major
+__device__ __forceinline__ uint32_t idesc_mn(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // MN-major operand without swizzle: core matrices of 8 K-rows x 16 bytes (128 contiguous bytes); the next 8 K-rows are
 // lbo bytes further, the next 8 M/N elements sbo bytes further
@@ -132,11 +133,10 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
     // ================= MMA issuer =================
     for (int it = 0; it < nit && ok; ++it) {
       const int s = it % STAGES, ph = (it / STAGES) & 1;
-      const int seg = it % jb.nseg;
       ok = mbar_wait(smem_u32(&full[s]), ph);
       tc_fence_after();
       const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES;
-      const uint32_t idesc = idesc_mn(128, (uint32_t)jb.n_mma, jb.xbf16[seg], jb.ybf16[seg]);
+      const uint32_t idesc = idesc_mn(128, (uint32_t)jb.n_mma);
       for (int mh = 0; mh < jb.m_tiles; ++mh)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
@@ -159,18 +159,12 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
       if (ok && want_b && seg == 0 && 2 * t < jb.m_tiles * 128) {
         // X tile in shared memory: [column group][64 rows][16 bytes]; features 2t, 2t+1 = word (t & 3) of group t >> 2
         const uint32_t base = s0 + (uint32_t)s * STAGE_BYTES + (uint32_t)(t >> 2) * 1024u + (uint32_t)(t & 3) * 4u;
-        const bool bf = jb.xbf16[0] != 0;
 #pragma unroll 8
         for (uint32_t k = 0; k < 64; ++k) {
           uint32_t w;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + k * 16u));
-          if (bf) {
-            bs0 += __uint_as_float(w << 16);
-            bs1 += __uint_as_float(w & 0xffff0000u);
-          } else {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
-            bs0 += f.x; bs1 += f.y;
-          }
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+          bs0 += f.x; bs1 += f.y;
         }
       }
       __syncwarp();
@@ -179,10 +173,12 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
     if (ok) ok = mbar_wait(smem_u32(&acc_full), 0);
     tc_fence_after();
     if (ok && nit > 0) {
+      const float isig = a.sigma ? __ldg(a.sigma + 1) : 1.0f;
+      const float scale = jb.scale * isig;
       if (want_b) {
         float* db = a.dpacked + jb.db_off;
-        if (2 * t < jb.rows) atomicAdd(db + 2 * t, bs0 * jb.db_scale);
-        if (2 * t + 1 < jb.rows) atomicAdd(db + 2 * t + 1, bs1 * jb.db_scale);
+        if (2 * t < jb.rows) atomicAdd(db + 2 * t, bs0 * jb.db_scale * isig);
+        if (2 * t + 1 < jb.rows) atomicAdd(db + 2 * t + 1, bs1 * jb.db_scale * isig);
       }
       const int q = warp & 3;                      // TMEM lane quarter this warp may read
       for (int mh = 0; mh < jb.m_tiles; ++mh) {
@@ -199,13 +195,13 @@ static __global__ void __launch_bounds__(THREADS, 1) wgrad16_kernel(const __grid
             for (int j = 0; j < 32; j += 4) {
               const int c = cc + j;
               if (c + 3 < jb.cols) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c), "f"(v[j] * jb.scale),
-                             "f"(v[j + 1] * jb.scale), "f"(v[j + 2] * jb.scale), "f"(v[j + 3] * jb.scale)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c), "f"(v[j] * scale),
+                             "f"(v[j + 1] * scale), "f"(v[j + 2] * scale), "f"(v[j + 3] * scale)
                              : "memory");
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                  if (c + e < jb.cols) atomicAdd(drow + c + e, v[j + e] * jb.scale);
+                  if (c + e < jb.cols) atomicAdd(drow + c + e, v[j + e] * scale);
               }
             }
           }
@@ -243,14 +239,19 @@ struct Builder {
   double cost[MAX_JOBS];
   bool bad = false;
 
-  explicit Builder(long long n, float* dpacked) : N(n) {
+  Builder(long long n, float* dpacked, const float* sigma) : N(n) {
     memset(&a, 0, sizeof(a));
     a.dpacked = dpacked;
+    a.sigma = sigma;
   }
   // tile-blocked 16-bit tensor of width W (chain_engine.cuh), read with boxes of `box_cg` column groups x 64 rows
   int add_map(const void* ptr, int W, int box_cg) {
     EncodeTiledFn fn = encode_fn();
-    if (!fn || nmaps >= MAX_MAPS || ((uintptr_t)ptr & 127) || (W & 7) || box_cg < 1 || box_cg > 32) { bad = true; return 0; }
+    if (!fn || nmaps >= MAX_MAPS || ((uintptr_t)ptr & 127) || (W & 7) || box_cg < 1 || box_cg > 32) {
+      ce::bad_value("wgrad tensor map arguments", nmaps);
+      bad = true;
+      return 0;
+    }
     const cuuint64_t tiles = (cuuint64_t)((N + 127) / 128);
     const cuuint64_t dims[3] = {512, (cuuint64_t)(W / 8), tiles};
     const cuuint64_t strides[2] = {2048, (cuuint64_t)W * 256};
@@ -259,34 +260,38 @@ struct Builder {
     CUresult r = fn(&a.maps[nmaps], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { bad = true; return 0; }
+    if (r != CUDA_SUCCESS) { ce::bad_value("cuTensorMapEncodeTiled", (int)r); bad = true; return 0; }
     return nmaps++;
   }
   // X operand of a job with `rows` output rows / Y operand with `cols` output columns
   int add_x(const void* ptr, int W, int rows) { return add_map(ptr, W, ((rows + 127) / 128) * 16); }
   int add_y(const void* ptr, int W, int cols) { return add_map(ptr, W, (((cols + 15) & ~15) + 7) / 8); }
   Job* add_job(int rows, int cols, long long dw_off, int dw_ld, float scale, long long db_off, float db_scale) {
-    if (njobs >= MAX_JOBS || rows < 1 || rows > 256 || cols < 1 || cols > 256) { bad = true; return &a.jobs[0]; }
+    if (njobs >= MAX_JOBS || rows < 1 || rows > 256 || cols < 1 || cols > 256) {
+      ce::bad_value("wgrad job shape", njobs);
+      bad = true;
+      return &a.jobs[0];
+    }
     Job* j = &a.jobs[njobs++];
     memset(j, 0, sizeof(*j));
     j->rows = rows; j->cols = cols; j->m_tiles = (rows + 127) / 128; j->n_mma = (cols + 15) & ~15;
     j->dw_off = dw_off; j->dw_ld = dw_ld; j->scale = scale; j->db_off = db_off; j->db_scale = db_scale;
     return j;
   }
-  static void add_seg(Job* j, int xmap, int xcol, int xbf16, int ymap, int ycol, int ybf16) {
+  static void add_seg(Job* j, int xmap, int xcol, int ymap, int ycol) {
     const int s = j->nseg++;
     if (s >= 2) return;
-    j->xmap[s] = xmap; j->xcol[s] = xcol; j->xbf16[s] = xbf16; j->ymap[s] = ymap; j->ycol[s] = ycol; j->ybf16[s] = ybf16;
+    j->xmap[s] = xmap; j->xcol[s] = xcol; j->ymap[s] = ymap; j->ycol[s] = ycol;
   }
   int launch(cudaStream_t st, int family) {
-    if (bad) return (int)cudaErrorInvalidValue;
+    if (bad) return ce::bad_value("wgrad builder", nmaps);
     if (njobs == 0 || N <= 0) return 0;
     const int chunks = (int)((N + 63) / 64);
     const int sms = ce::num_sms();
     double total = 0.0;
     for (int j = 0; j < njobs; ++j) {
       const Job& jb = a.jobs[j];
-      if (jb.nseg < 1 || jb.nseg > 2) return (int)cudaErrorInvalidValue;
+      if (jb.nseg < 1 || jb.nseg > 2) return ce::bad_value("wgrad job segments", j);
       cost[j] = (double)jb.nseg * (jb.m_tiles * 16 + (jb.n_mma + 7) / 8);
       total += cost[j];
     }
@@ -298,7 +303,7 @@ struct Builder {
       splits[j] = s;
       sum += s;
     }
-    if (sum > MAX_UNITS || sum > sms) return (int)cudaErrorInvalidValue;
+    if (sum > MAX_UNITS || sum > sms) return ce::bad_value("wgrad units", sum);
     int nu = 0;
     double flops = 0.0, bytes = 0.0;
     for (int j = 0; j < njobs; ++j) {
@@ -318,9 +323,6 @@ struct Builder {
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
-    if (ce::debug_nomix())
-      for (int j = 0; j < njobs; ++j)
-        for (int sgm = 0; sgm < 2; ++sgm) a.jobs[j].xbf16[sgm] = a.jobs[j].ybf16[sgm] = 0;
     prof_begin(family, st, flops, bytes);
     VDN_LAUNCH(wgrad16_kernel, nu, THREADS, SMEM, st, a, g_tc_fault);
     prof_end(family, st);
