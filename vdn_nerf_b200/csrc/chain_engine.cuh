@@ -35,7 +35,11 @@ namespace ce {
 
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;   // + warp 16: TMEM alloc + MMA issue; warp 17: weight stream
-constexpr int WSTAGES = 6;
+// Four 32 KB weight stages hold exactly the K blocks of one phase (K <= 256): slot X streams them, slot Y reuses all of
+// them, and the next phase's blocks arrive while the epilogues run.  Six stages prefetched further ahead but left only
+// ~28 KB of L1 for the epilogue's operand lines; with four, L1 is ~92 KB and the step is 4% faster (measured; three and
+// two stages are no better).
+constexpr int WSTAGES = 4;
 constexpr int KEEP = 4;                          // weight blocks of a phase kept in the ring for the second slot
 constexpr uint32_t W_STAGE = 32768;
 constexpr int MAX_PHASES = 16;
@@ -102,6 +106,7 @@ struct Args {
   const void* a0; int a0_ld, a0_w;          // A operand of phase 0
   long long row_off[2]; int row_len[2];     // rank-1 row vectors (float offsets into packed, -1: none)
   uint16_t* stash;                          // fp16 scratch [grid][2][MAX_STASH][8][512][8] (stays in L2)
+  int pf_mode;                              // software L2 prefetch one phase ahead: 0 none (default), 1 per line, 2 bulk (TMA)
   const float* sigma;                       // backward passes: device {sigma, 1 / sigma}, the power-of-two loss scale the
                                             // fp16 cotangents of this launch carry (null: 1)
   Phase ph[MAX_PHASES];
@@ -661,6 +666,18 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
     };
     // the lines of the tensors a phase reads (this warp's rows and columns) -> L2, one phase ahead
     auto prefetch = [&](const Phase& ph, long long m) {
+      if (a.pf_mode == 2) {       // a tile of a blocked tensor is contiguous: one bulk prefetch per tensor and tile
+        if (warp == 0 && lane == 0) {
+          const long long tile = m >> 7;
+          if (ph.aux0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint16_t*>(ph.aux0) + tile * ph.ld0 * 128),
+                         "r"((ph.width < ph.ld0 ? ph.width : ph.ld0) * 256));
+          if (ph.aux1)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const uint16_t*>(ph.aux1) + tile * ph.ld1 * 128),
+                         "r"((ph.width < ph.ld1 ? ph.width : ph.ld1) * 256));
+        }
+        return;
+      }
       if (ph.aux0) prefetch16(ph.aux0, m, ph.ld0, c0, ph.width, lane);
       if (ph.aux1) prefetch16(ph.aux1, m, ph.ld1, c0, ph.width, lane);
     };
@@ -676,14 +693,20 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
           if (s && !hasY) break;
           const long long tile = tX + s * G;
           const long long m = tile * 128 + row;
-          if (!last) {
-            prefetch(a.ph[p + 1], m);
-            if (ph.aload) prefetch16(ph.aload, m, ph.al_ld, c0, ph.al_w, lane);
-          } else {
-            const long long tn = tX + (2 + s) * G;
-            if (tn < ntiles) {
-              prefetch(a.ph[0], tn * 128 + row);
-              prefetch16(a.a0, tn * 128 + row, a.a0_ld, c0, a.a0_w, lane);
+          // No software L2 prefetch by default: prefetch.global.L2 and cp.async.bulk.prefetch.L2 of the next phase's
+          // operands both DOUBLED the DRAM reads of these kernels on B200 (ncu dram__bytes_read 939 MB vs 567 MB for the
+          // same launch) and slowed them down; the lines are fetched into L1 a few steps ahead instead (fast_phase).
+          // VDN_PF2=1 / 2 re-enable the two variants for measurement.
+          if (a.pf_mode) {
+            if (!last) {
+              prefetch(a.ph[p + 1], m);
+              if (ph.aload) prefetch16(ph.aload, m, ph.al_ld, c0, ph.al_w, lane);
+            } else {
+              const long long tn = tX + (2 + s) * G;
+              if (tn < ntiles) {
+                prefetch(a.ph[0], tn * 128 + row);
+                prefetch16(a.a0, tn * 128 + row, a.a0_ld, c0, a.a0_w, lane);
+              }
             }
           }
           const uint32_t tA = lane_base + 256u + (uint32_t)(s * 128 + hq * 32);
@@ -866,6 +889,11 @@ static inline int trace_err(int e, const char* where) {
 // Validates the table (the kernel trusts it) and launches.  Returns a cudaError_t value.
 static inline int launch(const Args& a_in, cudaStream_t st, int family) {
   Args a = a_in;
+  {
+    static int pf2 = -1;
+    if (pf2 < 0) { const char* e = getenv("VDN_PF2"); pf2 = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }
+    a.pf_mode = pf2;
+  }
   if (debug_nomix())
     for (int p = 0; p < a.P; ++p) a.ph[p].a_bf16 = a.ph[p].b_bf16 = 0;
   for (int p = 0; p < a.P; ++p) {

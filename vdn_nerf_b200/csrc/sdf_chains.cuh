@@ -45,8 +45,11 @@ __device__ __forceinline__ void store8_hs(__half* dst, long long i, const float 
 // ---- loss scale of one backward call -------------------------------------------------------------------------
 // sig[0] = sigma = 2^-e with the largest |cotangent * mul| over up to three fp32 sources in [2^(e-1), 2^e), sig[1] = 1 / sigma
 // (sigma = 1 when every cotangent is zero or not finite).  sig[2] (max, as ordered bits) and sig[3] (block counter) must
-// be zero on entry (a memset node precedes the launch).
-struct AmaxSrc { const float* p; long long rows; int w, ld; float mul; };
+// be zero on entry (a memset node precedes the launch).  A source of more than 2^21 elements is SAMPLED (every rstride-th
+// row, its maximum taken times four): the scale only has to place the cotangents inside fp16's 40 binades - there are 16
+// binades of headroom above the maximum and conversions saturate - and reading all of a [65536, 256] cotangent twice
+// would cost more than the conversion it prepares.
+struct AmaxSrc { const float* p; long long rows; int w, ld; float mul; int rstride; };
 struct AmaxArgs { AmaxSrc s[3]; };
 static __global__ void amax_sigma_kernel(const __grid_constant__ AmaxArgs a, float* __restrict__ sig) {
   float mx = 0.0f;
@@ -56,6 +59,12 @@ static __global__ void amax_sigma_kernel(const __grid_constant__ AmaxArgs a, flo
     const AmaxSrc& s = a.s[k];
     if (!s.p) continue;
     float m = 0.0f;
+    if (s.rstride > 1) {
+      const long long nr = s.rows / s.rstride;
+      for (long long i = t0; i < nr * s.w; i += nt) m = fmaxf(m, fabsf(__ldg(s.p + (i / s.w) * s.rstride * s.ld + (i % s.w))));
+      mx = fmaxf(mx, 4.0f * m * s.mul);
+      continue;
+    }
     const long long tot = s.rows * s.w;
     if (s.ld == s.w && (((uintptr_t)s.p) & 15) == 0) {
       const float4* p4 = reinterpret_cast<const float4*>(s.p);
@@ -96,8 +105,13 @@ static inline int launch_sigma(float* sig, cudaStream_t st, const float* p0, lon
   cudaError_t e = cudaMemsetAsync(sig, 0, 4 * sizeof(float), st);
   if (e != cudaSuccess) return ce::trace_err((int)e, "loss-scale memset");
   AmaxArgs a;
-  a.s[0] = {p0, r0, w0, ld0, m0}; a.s[1] = {p1, r1, w1, ld1, m1}; a.s[2] = {p2, r2, w2, ld2, m2};
-  const long long tot = r0 * w0 + r1 * w1 + r2 * w2;
+  a.s[0] = {p0, r0, w0, ld0, m0, 1}; a.s[1] = {p1, r1, w1, ld1, m1, 1}; a.s[2] = {p2, r2, w2, ld2, m2, 1};
+  long long tot = 0;
+  for (int k = 0; k < 3; ++k) {
+    const long long n = a.s[k].rows * a.s[k].w;
+    if (n > (1LL << 21)) a.s[k].rstride = (int)(n >> 20);
+    tot += n / a.s[k].rstride;
+  }
   int blocks = (int)((tot / 4 + 255) / 256);
   blocks = blocks < 1 ? 1 : (blocks > 4 * ce::num_sms() ? 4 * ce::num_sms() : blocks);
   VDN_LAUNCH(amax_sigma_kernel, blocks, 256, 0, st, a, sig);
