@@ -11,10 +11,7 @@
 //                                          SWIZZLE_128B image with 64-element K blocks, for the kind::f16 chain kernels
 //   IHT_l  [ceil(out_dim/64)][in_ld][64 halfs]  W_l^T rounded to fp16, same image (rows = input index, K = output index):
 //                                          the B operand of the fused normals / backward chains
-//   IB_l / IB2_l, IBT_l / IBT2_l   the same two images as bf16 "hi" and "lo" parts (w = hi + lo up to 2^-17 relative): the
-//                                          backward chains multiply bf16 cotangents with hi and lo in two accumulating
-//                                          MMAs (kind::f16 cannot mix fp16 and bf16 operands in one instruction)
-// The fp16 / bf16 images may rotate the OUTPUT index (orot): image position j holds output (j + orot) mod out_dim, so a
+// The fp16 images may rotate the OUTPUT index (orot): image position j holds output (j + orot) mod out_dim, so a
 // 257-wide stacked head [scalar ; 256 features] presents the features as positions 0..255 (one N = 256 MMA, K blocks
 // 0..3 of the transposed image) and the scalar as position 256.
 // with in_ld = round_up(in_dim, 16), out_ld = round_up(out_dim, 16).  The gradient buffer of a network uses
@@ -34,7 +31,6 @@ struct MlpLayout {
   int in_ld[VDN_MAX_LAYERS], out_ld[VDN_MAX_LAYERS];
   long long off_w[VDN_MAX_LAYERS], off_wt[VDN_MAX_LAYERS], off_b[VDN_MAX_LAYERS];
   long long off_iw[VDN_MAX_LAYERS], off_iwt[VDN_MAX_LAYERS], off_ih[VDN_MAX_LAYERS], off_iht[VDN_MAX_LAYERS];
-  long long off_ib[VDN_MAX_LAYERS], off_ib2[VDN_MAX_LAYERS], off_ibt[VDN_MAX_LAYERS], off_ibt2[VDN_MAX_LAYERS];
   long long total;  // floats
 };
 
@@ -68,18 +64,6 @@ inline int make_layout(int L, const int* in_dims, const int* out_dims, MlpLayout
     off += (long long)((in_dims[l] + 63) / 64) * ly->out_ld[l] * 32;   // 64 halfs = 32 floats per row and K block
     off = (off + 255) / 256 * 256;
     ly->off_iht[l] = off;
-    off += (long long)((out_dims[l] + 63) / 64) * ly->in_ld[l] * 32;
-    off = (off + 255) / 256 * 256;
-    ly->off_ib[l] = off;
-    off += (long long)((in_dims[l] + 63) / 64) * ly->out_ld[l] * 32;
-    off = (off + 255) / 256 * 256;
-    ly->off_ib2[l] = off;
-    off += (long long)((in_dims[l] + 63) / 64) * ly->out_ld[l] * 32;
-    off = (off + 255) / 256 * 256;
-    ly->off_ibt[l] = off;
-    off += (long long)((out_dims[l] + 63) / 64) * ly->in_ld[l] * 32;
-    off = (off + 255) / 256 * 256;
-    ly->off_ibt2[l] = off;
     off += (long long)((out_dims[l] + 63) / 64) * ly->in_ld[l] * 32;
   }
   ly->total = off;

@@ -1,12 +1,12 @@
 // Weight materialisation: one launch per network and optimiser step turns the raw parameters
 // (weight_v / weight_g / bias of old-style nn.utils.weight_norm, reference fields.py:65-66, 141-142; plain
 // weight / bias for the NeRF background field) into the packed layout of mlp_layout.cuh - fp32 W and W^T for the
-// FFMA kernels plus tf32-rounded SWIZZLE_128B tile images of both for the tcgen05 kernels - and one launch turns
+// FFMA kernels plus SWIZZLE_128B tile images of both (tf32-rounded for the layer-wise tcgen05 kernels, fp16 for the
+// chain engine) - and one launch turns
 // a packed gradient back into per-parameter gradients (weight-norm backward).
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
-#include <cuda_bf16.h>
 #include "../../include/vdn_b200.h"
 
 namespace vdn {
@@ -17,7 +17,7 @@ struct PackLayer {
   const float* b[2];
   int rows[2];
   int in_dim, in_ld, out_dim, out_ld, rot, orot;
-  long long off_w, off_wt, off_b, off_iw, off_iwt, off_ih, off_iht, off_ib, off_ib2, off_ibt, off_ibt2;
+  long long off_w, off_wt, off_b, off_iw, off_iwt, off_ih, off_iht;
 };
 struct PackArgs {
   int L;
@@ -63,10 +63,6 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
   float* IWT = packed + P.off_iwt;
   __half* IH = reinterpret_cast<__half*>(packed + P.off_ih);
   __half* IHT = reinterpret_cast<__half*>(packed + P.off_iht);
-  __nv_bfloat16* IB = reinterpret_cast<__nv_bfloat16*>(packed + P.off_ib);
-  __nv_bfloat16* IB2 = reinterpret_cast<__nv_bfloat16*>(packed + P.off_ib2);
-  __nv_bfloat16* IBT = reinterpret_cast<__nv_bfloat16*>(packed + P.off_ibt);
-  __nv_bfloat16* IBT2 = reinterpret_cast<__nv_bfloat16*>(packed + P.off_ibt2);
   int rj = r - P.orot;                      // position of output r in the (rotated) fp16 images
   if (rj < 0) rj += P.out_dim;
   for (int k = lane; k < P.in_ld; k += 32) {
@@ -87,10 +83,6 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
       const long long i_t = (long long)(rj >> 6) * P.in_ld * 64 + (tc::sw128_offset_h((uint32_t)k, (uint32_t)(rj & 63)) >> 1);
       IH[i_w] = hw;
       IHT[i_t] = hw;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-      const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-      IB[i_w] = hi; IB2[i_w] = lo;
-      IBT[i_t] = hi; IBT2[i_t] = lo;
     }
   }
   if (lane == 0) B[r] = P.b[src] ? P.b[src][rr] : 0.0f;
@@ -184,7 +176,6 @@ extern "C" int vdn_mlp_pack(int L, const int* in_dims, const int* out_dims, cons
     if (P.orot < 0 || P.orot >= P.out_dim) return (int)cudaErrorInvalidValue;
     P.off_w = ly.off_w[l]; P.off_wt = ly.off_wt[l]; P.off_b = ly.off_b[l];
     P.off_iw = ly.off_iw[l]; P.off_iwt = ly.off_iwt[l]; P.off_ih = ly.off_ih[l]; P.off_iht = ly.off_iht[l];
-    P.off_ib = ly.off_ib[l]; P.off_ib2 = ly.off_ib2[l]; P.off_ibt = ly.off_ibt[l]; P.off_ibt2 = ly.off_ibt2[l];
   }
   a.row_start[L] = start;
   cudaStream_t st = (cudaStream_t)stream;

@@ -139,12 +139,18 @@ def bump_param_epoch() -> None:
     _PARAM_EPOCH += 1
 
 
+_REPACK_SERIAL = 0      # one value per force_repack(True) window (= per graph capture)
+
+
 def force_repack(on: bool) -> None:
-    """While on, PackedMLP.packed() re-materialises the weights on every call instead of trusting its version-keyed
-    cache: used while a training step is captured into a CUDA graph, so that the pack launch is part of the graph and
-    every replay sees the parameters the optimiser has written since."""
-    global _FORCE_REPACK
+    """While on, PackedMLP.packed() does not trust the cache it built before: the first call of every network inside the
+    window re-materialises the weights, later calls with unchanged parameters reuse that buffer.  Used while a training
+    step is captured into a CUDA graph, so that ONE pack launch per network is part of the graph and every replay sees
+    the parameters the optimiser has written since."""
+    global _FORCE_REPACK, _REPACK_SERIAL
     _FORCE_REPACK = bool(on)
+    if on:
+        _REPACK_SERIAL += 1
 
 
 class PackedMLP:
@@ -192,6 +198,7 @@ class PackedMLP:
         if self.total <= 0:
             raise _lib.VdnLibraryError("invalid MLP layout")
         self._key = None
+        self._window_key = None
         self._packed = None
 
     def _src_ptrs(self, pick):
@@ -204,6 +211,8 @@ class PackedMLP:
 
     def packed(self) -> torch.Tensor:
         key = (_PARAM_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self.params)
+        if _FORCE_REPACK and self._packed is not None and self._window_key == (_REPACK_SERIAL, key):
+            return self._packed           # packed earlier in this capture window, parameters untouched since
         if key != self._key or self._packed is None or _FORCE_REPACK:
             dev = self.params[0].device
             for p in self.params:
@@ -216,6 +225,7 @@ class PackedMLP:
                                    self._src_ptrs(lambda s: s[1]), self._src_ptrs(lambda s: s[2]), self._rows,
                                    self._rot, self._orot, _p(buf), _stream()), "vdn_mlp_pack")
             self._packed = buf
+            self._window_key = (_REPACK_SERIAL, key) if _FORCE_REPACK else None
             # a pack recorded during graph capture has not run: never let an eager call trust that buffer
             self._key = None if (_FORCE_REPACK or torch.cuda.is_current_stream_capturing()) else key
         return self._packed
@@ -224,6 +234,7 @@ class PackedMLP:
         """Forget the cached packed weights (parameters changed in a way the version counters do not see, e.g. through
         `.data` or by a captured optimiser step)."""
         self._key = None
+        self._window_key = None
 
     def unpack_grads(self, dpacked: torch.Tensor, needs: Sequence[bool]) -> List[Optional[torch.Tensor]]:
         """Packed gradient -> gradients of self.params (same order); weight-norm backward included."""
