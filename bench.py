@@ -457,7 +457,7 @@ def run_ours(args):
                  "chain": "sdf_chain_tc_kernel (fused SDF value chain of the hierarchical sampler, kind::f16)",
                  "chain_train": "chain_kernel (fused training chains: SDF forward / normals / backward phases 1+2, colour and "
                                 "NeRF forward / backward; tcgen05 kind::f16, A operand in TMEM, 16-bit saved tensors)",
-                 "wgrad16": "wgrad16_kernel (grouped weight gradient, TMA tensor maps, MN-major bf16 operands)"}
+                 "wgrad16": "wgrad16_kernel (grouped weight gradient, TMA tensor maps, MN-major fp16 operands)"}
         if args.precision == "tf32":
             dom = max(fam, key=lambda k: fam[k][0])
             d_ms, d_n, d_fl, d_by = fam[dom]
@@ -491,8 +491,8 @@ def run_ours(args):
                                                                 " incl. ray gradients (learnable poses)" if pose else "",
                                                                 " + NCCL grad all-reduce" if world > 1 else ""),
                                 "fused_chains": bool(ops.get_chain()) and args.precision == "tf32",
-                                "operand_formats": "fp16 forward / normals chains, bf16 backward chains and weight "
-                                                   "gradient, fp32 accumulate" if args.precision == "tf32" else "fp32",
+                                "operand_formats": "fp16 operands everywhere (cotangents carry a per-call power-of-two "
+                                                   "loss scale), fp32 accumulate" if args.precision == "tf32" else "fp32",
                                 "rays_per_step_per_gpu": B, "global_batch": B * world, "n_samples": 64,
                                 "n_importance": 64, "n_outside": 32, "mode": args.precision, "cuda_graph": bool(gstep),
                                 "l2": "256 MiB flush between timed iterations"},
@@ -528,7 +528,7 @@ def run_ours(args):
                 line["reference_cuda_eager"] = reference_cuda_eager(B, depth)
         line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
                      "scaling": "strong" if (cpu_kind == "grid" or args.global_batch > 0) else "weak", "vs_baseline": None,
-                     "dtype": line.get("dtype", "bf16" if args.precision == "tf32" else "f32"),
+                     "dtype": line.get("dtype", "f16" if args.precision == "tf32" else "f32"),
                      "data": "synthetic", "gpu_launches": int(launches), "clocks": clocks})
         order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline",

@@ -24,16 +24,27 @@ def driver_loss(render_out, true_rgb, mask=None, igr_weight=0.1, mask_weight=0.0
     """
     color = render_out["color_fine"]
     mask_given = mask is not None
-    if mask is None:
-        mask = torch.ones_like(render_out["weight_sum"])
-    if data_parallel and global_batch is not None and not mask_given:
-        mask_sum = float(global_batch) + 1e-5      # use_mask=False: mask == 1 (dpt_runner.py:209); host scalar
-    elif data_parallel:
-        mask_sum = vdist.global_sum(mask.sum()) + 1e-5     # use_mask=True: the normaliser is the global mask count
+    fused = color.is_cuda and not data_parallel
+    need_mask = (not fused) or mask_weight != 0.0 or (gt_feats is not None and render_out.get("render_feats") is not None)
+    mask_sum = None
+    if need_mask:
+        if mask is None:
+            mask = torch.ones_like(render_out["weight_sum"])
+        if data_parallel and global_batch is not None and not mask_given:
+            mask_sum = float(global_batch) + 1e-5      # use_mask=False: mask == 1 (dpt_runner.py:209); host scalar
+        elif data_parallel:
+            mask_sum = vdist.global_sum(mask.sum()) + 1e-5     # use_mask=True: the normaliser is the global mask count
+        elif mask_given:
+            mask_sum = mask.sum() + 1e-5
+        else:
+            mask_sum = float(mask.numel()) + 1e-5      # mask == 1: its sum is the ray count
+    if fused:
+        # one kernel for the masked L1 sum, the mask count and the gradient sign (driver.color_loss, vdn_color_loss)
+        from .driver import color_loss
+        loss, _ = color_loss(color, true_rgb, mask if mask_given else None)
     else:
-        mask_sum = mask.sum() + 1e-5
-    color_error = (color - true_rgb) * mask
-    loss = F.l1_loss(color_error, torch.zeros_like(color_error), reduction="sum") / mask_sum
+        color_error = (color - true_rgb) * mask
+        loss = F.l1_loss(color_error, torch.zeros_like(color_error), reduction="sum") / mask_sum
     if data_parallel:
         eik = vdist.global_eikonal(render_out["_eik_num"], render_out["_eik_den"])
     else:
