@@ -155,8 +155,14 @@ def timed_steps(fn, steps, warmup, world, dev, flush, lib):
     barrier(world)
     evs = []
     l0 = lib.vdn_launch_count()
+    align = torch.zeros(1, device=dev) if world > 1 else None
     for i in range(steps):
         flush.zero_()
+        if align is not None:
+            # untimed, like the flush: a one-element all-reduce lines the ranks up on the device, so that the skew the
+            # flushes and the host introduce between steps is not billed to the first collective of the timed step
+            import torch.distributed as dist
+            dist.all_reduce(align)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn(warmup + i)
@@ -495,7 +501,7 @@ def run_ours(args):
                                                    "loss scale), fp32 accumulate" if args.precision == "tf32" else "fp32",
                                 "rays_per_step_per_gpu": B, "global_batch": B * world, "n_samples": 64,
                                 "n_importance": 64, "n_outside": 32, "mode": args.precision, "cuda_graph": bool(gstep),
-                                "l2": "256 MiB flush between timed iterations"},
+                                "l2": "256 MiB flush between timed iterations" + (" (+ one-element all-reduce to align the ranks, untimed)" if world > 1 else "")},
                      "e2e": {"value": B * world / e2e_t, "unit": "rays/s",
                              "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)), "d2h_bytes_per_step": 4},
                      "roofline": roof})

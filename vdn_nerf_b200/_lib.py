@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvdn_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 

@@ -39,7 +39,7 @@ void prof_end(int family, cudaStream_t st) {
 }  // namespace vdn
 using namespace vdn;
 
-extern "C" int vdn_abi_version(void) { return 4; }
+extern "C" int vdn_abi_version(void) { return 5; }
 extern "C" long long vdn_launch_count(void) { return g_launches.load(); }
 extern "C" const char* vdn_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
