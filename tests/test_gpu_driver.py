@@ -233,3 +233,30 @@ def test_train_loop_with_fused_adam_decreases_the_loss(white):
         assert ops.tc_fault() == 0
     finally:
         ops.set_precision("fp32")
+
+
+def test_gradients_written_straight_into_the_all_reduce_buffer(white):
+    """dist.FlatGradAllReduce registers its flat buffer as the gradient arena: from the second step on the weight-norm
+    backward writes every network gradient into its slot (no pack / unpack copy), and the gradients equal those of a
+    step without the arena.  Single process: the collective itself is covered by the gloo tests."""
+    from vdn_nerf_b200 import dist as vdist
+    fx, _, conf = white
+    mods = configs.build_networks(conf, fields, seed=0, device=DEV)
+    rend = make_renderer(mods, conf)
+    params = [p for m in mods if m is not None for p in m.parameters()]
+    o, d, near, far = (util.t(fx[k], DEV) for k in ("rays_o", "rays_d", "near", "far"))
+    rgb = torch.full((o.shape[0], 3), 0.5, device=DEV)
+    kw = dict(background_rgb=torch.ones(1, 3, device=DEV), perturb_overwrite=0)
+    try:
+        train_step(rend, params, o, d, near, far, rgb, **kw)
+        want = [p.grad.clone() for p in params]
+        sync = vdist.FlatGradAllReduce(params)
+        for _ in range(2):          # the first call builds the buffer and registers the arena
+            train_step(rend, params, o, d, near, far, rgb, grad_sync=sync, global_batch=o.shape[0], **kw)
+        lo, hi = sync.flat.data_ptr(), sync.flat.data_ptr() + 4 * sync.flat.numel()
+        n_alias = sum(lo <= p.grad.data_ptr() < hi for p in params)
+        assert n_alias >= len(params) - 2, (n_alias, len(params))      # all but `variance` (its gradient is not unpacked)
+        for p, w in zip(params, want):
+            assert util.relerr(p.grad, w) < 1e-6
+    finally:
+        ops.set_grad_arena([], [])

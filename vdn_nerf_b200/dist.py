@@ -78,22 +78,37 @@ class FlatGradAllReduce:
                 n = p.numel()
                 self._views.append(self.flat[off: off + n].view(p.shape))
                 off += n
-        # pack: one multi-tensor copy instead of one launch per parameter (41 tensors for the womsk_white networks)
+            if dev.type == "cuda":
+                # let the weight-norm backward write straight into this buffer (ops.set_grad_arena): a gradient that
+                # already lives in its slot needs neither the pack nor the unpack copy
+                from . import ops
+                ops.set_grad_arena(self.params, self._views)
+        # pack: one multi-tensor copy (instead of one launch per parameter) for the gradients that are not in place
+        inplace = [p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(self.params, self._views)]
         missing = [v for p, v in zip(self.params, self._views) if p.grad is None]
         if missing:
             torch._foreach_zero_(missing)
-        have = [(v, p.grad) for p, v in zip(self.params, self._views) if p.grad is not None]
+        have = [(v, p.grad) for p, v, ip in zip(self.params, self._views, inplace) if p.grad is not None and not ip]
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if scale != 1.0:
             self.flat.mul_(scale)
-        # unpack: one multi-tensor copy back into the (existing or freshly created) .grad tensors
-        for p, v in zip(self.params, self._views):
+        # unpack: one multi-tensor copy back into the (existing or freshly created) .grad tensors that are not views
+        out_g, out_v = [], []
+        for p, v, ip in zip(self.params, self._views, inplace):
+            if ip:
+                continue
             if p.grad is None:
                 p.grad = torch.empty_like(v)
-        torch._foreach_copy_([p.grad for p in self.params], self._views)
+            out_g.append(p.grad)
+            out_v.append(v)
+        if out_g:
+            torch._foreach_copy_(out_g, out_v)
+        if dev.type == "cuda":
+            from . import ops
+            ops.reset_grad_arena_use()
 
 
 def gather_grid(u_local: torch.Tensor, resolution: int, group=None) -> Optional[torch.Tensor]:

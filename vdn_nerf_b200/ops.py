@@ -153,6 +153,33 @@ def force_repack(on: bool) -> None:
         _REPACK_SERIAL += 1
 
 
+# Gradient arena (data-parallel training, dist.FlatGradAllReduce): when a parameter has a slot in a flat all-reduce
+# buffer, the weight-norm backward writes its gradient THERE, autograd adopts that tensor as `.grad`, and the pack /
+# unpack copies around the collective disappear.  A slot is handed out once per step and only while `.grad` is None, so
+# a network evaluated twice in one graph, or gradients accumulated over several backward calls, stay correct.
+_GRAD_ARENA = {}
+_ARENA_USED = set()
+
+
+def set_grad_arena(params, views) -> None:
+    _GRAD_ARENA.clear()
+    _ARENA_USED.clear()
+    for p, v in zip(params, views):
+        _GRAD_ARENA[id(p)] = v
+
+
+def reset_grad_arena_use() -> None:
+    _ARENA_USED.clear()
+
+
+def _grad_buffer(p: torch.Tensor) -> torch.Tensor:
+    v = _GRAD_ARENA.get(id(p))
+    if v is None or id(p) in _ARENA_USED or p.grad is not None or v.device != p.device:
+        return torch.empty_like(p)
+    _ARENA_USED.add(id(p))
+    return v.view_as(v)         # a fresh alias: autograd may adopt it as .grad without cloning
+
+
 class PackedMLP:
     """Effective (weight-normed, padded, transposed) weights of one network in one device buffer.
 
@@ -247,15 +274,15 @@ class PackedMLP:
                     dv.append(0); dg.append(0); db.append(0)
                     continue
                 w, g, b = srcs[s]
-                gw = torch.empty_like(w) if needs[i] else None
+                gw = _grad_buffer(w) if needs[i] else None
                 grads.append(gw); i += 1
                 gg = None
                 if g is not None:
-                    gg = torch.empty_like(g) if needs[i] else None
+                    gg = _grad_buffer(g) if needs[i] else None
                     grads.append(gg); i += 1
                 gb = None
                 if b is not None:
-                    gb = torch.empty_like(b) if needs[i] else None
+                    gb = _grad_buffer(b) if needs[i] else None
                     grads.append(gb); i += 1
                 dv.append(gw.data_ptr() if gw is not None else 0)
                 dg.append(gg.data_ptr() if gg is not None else 0)
