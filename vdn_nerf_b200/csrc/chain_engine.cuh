@@ -30,7 +30,17 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+// Debug build (-DVDN_CHAIN_TL): CTA 0 records clock64() stamps of every (tile pair, phase, slot) into the buffer given to
+// vdn_debug_timeline(): [0..3] MMA issuer (start, accumulator drained, A ready, MMAs issued), [4 + 2 w], [5 + 2 w] epilogue
+// warp w (accumulator full, phase done); 40 values per (pair, phase, slot).  tools/diag_chain_tl.py prints it.
+#ifdef VDN_CHAIN_TL
+#define VDN_TL(ptr, i) do { if (ptr) (ptr)[i] = clock64(); } while (0)
+#else
+#define VDN_TL(ptr, i) do { } while (0)
+#endif
+
 namespace vdn {
+extern long long* g_tc_dbg;   // api.cu: optional device buffer for debug time stamps (vdn_debug_timeline)
 namespace ce {
 
 constexpr int EPI_WARPS = 16;
@@ -44,7 +54,8 @@ constexpr int KEEP = 4;                          // weight blocks of a phase kep
 constexpr uint32_t W_STAGE = 32768;
 constexpr int MAX_PHASES = 16;
 constexpr int MAX_STASH = 2;                     // stash slots per tile (fp16, 64 values per thread each)
-constexpr size_t SMEM = WSTAGES * W_STAGE + 1024 + MAX_PHASES * 256 * sizeof(float) + 2 * 256 * sizeof(float);
+constexpr uint32_t TAIL_BYTES = 128 * 128;        // skip-connection tail of a tile's 128 rows: up to 64 values of 16 bits each
+constexpr size_t SMEM = WSTAGES * W_STAGE + 1024 + MAX_PHASES * 256 * sizeof(float) + 2 * 256 * sizeof(float) + TAIL_BYTES;
 
 constexpr float kB2 = 144.26950408889634f;       // beta / ln 2 (Softplus(beta=100), fields.py:50)
 constexpr float kInvB2 = 1.0f / 144.26950408889634f;
@@ -90,7 +101,8 @@ struct Phase {
   float* o32; int ldo32; int o32_c0, o32_w; float o32_mul; int act;   // fp32 store of act(x) for columns [o32_c0, o32_c0 + o32_w)
   int o32_unscale;       // the fp32 output is a cotangent: multiply by 1 / sigma
   int o32_vec;           // set by launch(): full groups of that store may use 16-byte accesses
-  int fast;              // set by launch(): regular phase, run_op_fast applies
+  int fast;              // set by launch(): number of leading 64-column blocks whose warps take the fast path (0: none)
+  int edge;              // set by launch(): the block after them is the ragged edge of a skip layer (slow path)
   float* o32b; int ldo32b; int o32b_c0, o32b_w;                       // second fp32 store of x (no activation), other columns
   const void* tail; int ldt; int tail_w; float tail_mul;   // A columns [width, width + tail_w) from here
   const float* r1; int r1_stride; float r1_mul; int r1_row;   // rank-1 term, r1_row in {0, 1}
@@ -214,15 +226,46 @@ static __device__ __noinline__ void o32_scalar(float* dst, int ld, int c_first, 
     if (c >= 0 && c < w) op[c] = apply_act(x[j], act) * mul;
   }
 }
-// columns >= width of an A tile: skip-connection tail (from a 16-bit tensor) or zero padding; r is patched in place
-static __device__ __noinline__ void ragged_tail(const Phase& ph, long long m, int cg, float* r, float* r2) {
-#pragma unroll 1
+// columns >= width of an A tile: skip-connection tail or zero padding; r is patched in place.  The tail values of the
+// thread's row were copied into shared memory with cp.async at the start of the phase (phase_body), so the element-wise
+// loop never waits for them.  Inlined on purpose, with everything in registers.  Earlier versions made the ONE ragged
+// layer of the SDF net cost as much as five regular ones (per-CTA timeline, tools/diag_chain_tl.py): an out-of-line
+// function taking `const Phase&` turned every field access into a generic load from kernel-parameter space (~1 us each),
+// passing `r` by pointer put the caller's arrays into local memory, and loading the tail values where they are used cost
+// one DRAM round trip (1.6 us) per group of eight columns.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void ragged_tail(bool has_tail, uint32_t stail, int tail_w, float tail_mul, int width, int cg,
+                                            float (&r)[8], float (&r2)[8], bool has_r2) {
+  const int t0 = cg - width;                        // tail column of element 0 (negative: the group straddles the edge)
+  const int tw = has_tail ? tail_w : 0;
+  const int g0 = (t0 > 0 ? t0 : 0) >> 3;
+  uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = make_uint4(0u, 0u, 0u, 0u);
+  if (tw > 0) cp_async_wait_all();
+  if (g0 * 8 < tw) u0 = lds128(stail + (uint32_t)g0 * 16u);
+  if (g0 * 8 + 8 < tw) u1 = lds128(stail + (uint32_t)g0 * 16u + 16u);
+  const int sh = t0 - g0 * 8;                       // element j lives at position sh + j of the 16 loaded ones (-7 .. 7)
+#pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = cg + j;
-    if (c >= ph.width) {
-      const int tcol = c - ph.width;
-      r[j] = (ph.tail && tcol < ph.tail_w) ? ld16_one(ph.tail, m, ph.ldt, tcol, 0) * ph.tail_mul : 0.0f;
-      if (r2) r2[j] = 0.0f;
+    const int e = sh + j, t = t0 + j;
+    // 16-bit element e of {u0, u1}: word e >> 1, half e & 1 - selected with compile-time word indices
+    uint32_t word = 0;
+    word = (e >> 1) == 0 ? u0.x : word; word = (e >> 1) == 1 ? u0.y : word; word = (e >> 1) == 2 ? u0.z : word;
+    word = (e >> 1) == 3 ? u0.w : word; word = (e >> 1) == 4 ? u1.x : word; word = (e >> 1) == 5 ? u1.y : word;
+    word = (e >> 1) == 6 ? u1.z : word; word = (e >> 1) == 7 ? u1.w : word;
+    const uint16_t h = (e & 1) ? (uint16_t)(word >> 16) : (uint16_t)(word & 0xffffu);
+    const float v = (t >= 0 && t < tw) ? __half2float(__ushort_as_half(h)) * tail_mul : 0.0f;
+    if (t >= 0) {
+      r[j] = v;
+      if (has_r2) r2[j] = 0.0f;
     }
   }
 }
@@ -248,171 +291,149 @@ __device__ __forceinline__ long long blk_base(long long m, int W, int c0, int ha
   return (m >> 7) * ((long long)W * 128) + (long long)((c0 >> 3) + 4 * half) * 1024 + (m & 127) * 8;
 }
 
-// raw 16-byte loads of the auxiliary tensors for the four groups of a half (issued well before their use)
+// One group of eight columns (cg = c0 + 8 g .. + 7) of one phase for one thread (row m): the general element-wise path.
+// The caller loops over the groups WITHOUT unrolling, so that this body exists once per epilogue kind: the general path
+// runs rarely (first / last layers, the ragged skip layer), its instructions are never resident in the instruction cache,
+// and the fully unrolled version spent most of its time fetching them (per-CTA timeline, tools/diag_chain_tl.py: 2 us per
+// group against 0.3 us in the resident fast path).
 template <int OP>
-__device__ __forceinline__ void load_aux(const Phase& ph, long long m, int c0, int half, uint4 (&q0)[4], uint4 (&q1)[4]) {
-  if (OpTraits<OP>::aux0 && ph.aux0) {
-    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux0) + blk_base(m, ph.ld0, c0, half));
-#pragma unroll
-    for (int gi = 0; gi < 4; ++gi)
-      if (c0 + 32 * half + 8 * gi < ph.width) q0[gi] = __ldg(p + gi * 128);
-  }
-  if (OpTraits<OP>::aux1 && ph.aux1) {
-    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux1) + blk_base(m, ph.ld1, c0, half));
-#pragma unroll
-    for (int gi = 0; gi < 4; ++gi)
-      if (c0 + 32 * half + 8 * gi < ph.width) q1[gi] = __ldg(p + gi * 128);
-  }
-}
-
-// One phase's element-wise work for one thread: its row m, columns c0 + 32 half .. + 31 (four groups of eight; the
-// accumulator is drained and processed in two halves so that 32 + ~50 registers suffice: a thread of a 576-thread CTA
-// has 96).  q0 / q1 hold the auxiliary operands of this half.
-template <int OP>
-__device__ __forceinline__ void run_op(const Phase& ph, const float (&v)[4][8], int half, const uint4 (&q0)[4],
-                                       const uint4 (&q1)[4], const float* sb, const float* srow, long long m, long long N,
-                                       int c0, uint32_t tA, uint16_t* stash_base, float sig, float isig) {
+__device__ __forceinline__ void run_group(const Phase& ph, const float (&v)[8], int g, const uint4& q0, const uint4& q1,
+                                          const float* sb, const float* srow, long long m, long long N, int c0, uint32_t tA,
+                                          uint16_t* stash_base, float sig, float isig, uint32_t stail) {
   using T = OpTraits<OP>;
-  const int ncols = ph.a_out ? ph.a_wr : ph.width;      // columns this phase touches
   const int width = ph.width;
   const float dsc = ph.dsc;
   const bool rowok = m < N;
   const bool has_r1 = ph.r1 != nullptr;
   const float r1v = (has_r1 && rowok) ? ph.r1[m * ph.r1_stride] * ph.r1_mul * (ph.r1_scaled ? sig : 1.0f) : 0.0f;   // padded rows stay exactly zero
   const float* rr = srow + ph.r1_row * 256;
-  const int cb = c0 + 32 * half;
-  // destinations of this half (tile-blocked 16-bit copies; fp32 row-major side output)
-  uint4* pa = ph.o16a ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16a) + blk_base(m, ph.ldo16a, c0, half)) : nullptr;
+  const int cg = c0 + 8 * g;
+  // destinations of this group (tile-blocked 16-bit copies; fp32 row-major side output)
+  uint4* pa = ph.o16a ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16a) + blk_base(m, ph.ldo16a, c0, 0)) + g * 128 : nullptr;
   uint4* pb = (OP == OP_P1STEP && ph.o16b)
-                  ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16b) + blk_base(m, ph.ldo16b, c0, half)) : nullptr;
+                  ? reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ph.o16b) + blk_base(m, ph.ldo16b, c0, 0)) + g * 128 : nullptr;
   const bool o32_on = ph.o32 && rowok;
   const bool o32b_on = ph.o32b && rowok;
-  float4* pv = (o32_on && ph.o32_vec) ? reinterpret_cast<float4*>(ph.o32 + m * ph.ldo32 + (cb - ph.o32_c0)) : nullptr;
+  float4* pv = (o32_on && ph.o32_vec) ? reinterpret_cast<float4*>(ph.o32 + m * ph.ldo32 + (cg - ph.o32_c0)) : nullptr;
   const float om = ph.o16a_mul;
   const float o32_mul = ph.o32_unscale ? ph.o32_mul * isig : ph.o32_mul;
+  float x[8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + cg), b1 = *reinterpret_cast<const float4*>(sb + cg + 4);
+    x[0] = fmaf(v[0], dsc, b0.x); x[1] = fmaf(v[1], dsc, b0.y); x[2] = fmaf(v[2], dsc, b0.z);
+    x[3] = fmaf(v[3], dsc, b0.w); x[4] = fmaf(v[4], dsc, b1.x); x[5] = fmaf(v[5], dsc, b1.y);
+    x[6] = fmaf(v[6], dsc, b1.z); x[7] = fmaf(v[7], dsc, b1.w);
+  }
+  if (has_r1) {
+    const float4 w0 = *reinterpret_cast<const float4*>(rr + cg), w1 = *reinterpret_cast<const float4*>(rr + cg + 4);
+    x[0] = fmaf(r1v, w0.x, x[0]); x[1] = fmaf(r1v, w0.y, x[1]); x[2] = fmaf(r1v, w0.z, x[2]); x[3] = fmaf(r1v, w0.w, x[3]);
+    x[4] = fmaf(r1v, w1.x, x[4]); x[5] = fmaf(r1v, w1.y, x[5]); x[6] = fmaf(r1v, w1.z, x[6]); x[7] = fmaf(r1v, w1.w, x[7]);
+  }
+  if (OP != OP_STASH && ph.stash_r >= 0) {      // written earlier by this very thread: plain (coherent) load
+    const uint4 u = *reinterpret_cast<const uint4*>(stash_base + ((size_t)ph.stash_r * 8 + g) * (512 * 8));
+    float s8[8];
+    unpack_h8(u, s8);
 #pragma unroll
-  for (int gi = 0; gi < 4; ++gi) {
-    const int g = half * 4 + gi;
-    const int cg = cb + 8 * gi;
-    if (cg >= ncols) break;
-    float x[8];
-    {
-      const float4 b0 = *reinterpret_cast<const float4*>(sb + cg), b1 = *reinterpret_cast<const float4*>(sb + cg + 4);
-      x[0] = fmaf(v[gi][0], dsc, b0.x); x[1] = fmaf(v[gi][1], dsc, b0.y); x[2] = fmaf(v[gi][2], dsc, b0.z);
-      x[3] = fmaf(v[gi][3], dsc, b0.w); x[4] = fmaf(v[gi][4], dsc, b1.x); x[5] = fmaf(v[gi][5], dsc, b1.y);
-      x[6] = fmaf(v[gi][6], dsc, b1.z); x[7] = fmaf(v[gi][7], dsc, b1.w);
+    for (int j = 0; j < 8; ++j) x[j] += s8[j];
+  }
+  if (OP == OP_STASH) {
+    *reinterpret_cast<uint4*>(stash_base + ((size_t)ph.stash_w * 8 + g) * (512 * 8)) =
+        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]),
+                   pack_h2(v[6], v[7]));
+    return;
+  }
+  // fp32 side outputs of x (final outputs, skip-connection tails)
+  if (o32_on && cg + 8 > ph.o32_c0 && cg < ph.o32_c0 + ph.o32_w) {
+    if (pv && cg >= ph.o32_c0 && cg + 8 <= ph.o32_c0 + ph.o32_w) {      // o32_vec: no activation, unit scale handled below
+      const float mul = o32_mul;
+      pv[0] = make_float4(x[0] * mul, x[1] * mul, x[2] * mul, x[3] * mul);
+      pv[1] = make_float4(x[4] * mul, x[5] * mul, x[6] * mul, x[7] * mul);
+    } else {
+      o32_scalar(ph.o32, ph.ldo32, ph.o32_c0, ph.o32_w, ph.act, o32_mul, m, cg, x[0], x[1], x[2], x[3], x[4], x[5], x[6],
+                 x[7]);
     }
-    if (has_r1) {
-      const float4 w0 = *reinterpret_cast<const float4*>(rr + cg), w1 = *reinterpret_cast<const float4*>(rr + cg + 4);
-      x[0] = fmaf(r1v, w0.x, x[0]); x[1] = fmaf(r1v, w0.y, x[1]); x[2] = fmaf(r1v, w0.z, x[2]); x[3] = fmaf(r1v, w0.w, x[3]);
-      x[4] = fmaf(r1v, w1.x, x[4]); x[5] = fmaf(r1v, w1.y, x[5]); x[6] = fmaf(r1v, w1.z, x[6]); x[7] = fmaf(r1v, w1.w, x[7]);
-    }
-    if (OP != OP_STASH && ph.stash_r >= 0) {      // written earlier by this very thread: plain (coherent) load
-      const uint4 u = *reinterpret_cast<const uint4*>(stash_base + ((size_t)ph.stash_r * 8 + g) * (512 * 8));
-      float s8[8];
-      unpack_h8(u, s8);
+  }
+  if (o32b_on && cg + 8 > ph.o32b_c0 && cg < ph.o32b_c0 + ph.o32b_w)
+    o32_scalar(ph.o32b, ph.ldo32b, ph.o32b_c0, ph.o32b_w, 0, 1.0f, m, cg, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+  if (OP == OP_OUT32) return;
+  // ---- the A value (and the optional second output) ----
+  float r[8], r2[8];
+  const bool in = cg < width;
+  if (OP == OP_SOFTPLUS) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] += s8[j];
-    }
-    if (OP == OP_STASH) {
-      *reinterpret_cast<uint4*>(stash_base + ((size_t)ph.stash_w * 8 + g) * (512 * 8)) =
-          make_uint4(pack_h2(v[gi][0], v[gi][1]), pack_h2(v[gi][2], v[gi][3]), pack_h2(v[gi][4], v[gi][5]),
-                     pack_h2(v[gi][6], v[gi][7]));
-      continue;
-    }
-    // fp32 side outputs of x (final outputs, skip-connection tails)
-    if (o32_on && cg + 8 > ph.o32_c0 && cg < ph.o32_c0 + ph.o32_w) {
-      if (pv && cg >= ph.o32_c0 && cg + 8 <= ph.o32_c0 + ph.o32_w) {      // o32_vec: no activation, unit scale handled below
-        const float mul = o32_mul;
-        pv[2 * gi] = make_float4(x[0] * mul, x[1] * mul, x[2] * mul, x[3] * mul);
-        pv[2 * gi + 1] = make_float4(x[4] * mul, x[5] * mul, x[6] * mul, x[7] * mul);
-      } else {
-        o32_scalar(ph.o32, ph.ldo32, ph.o32_c0, ph.o32_w, ph.act, o32_mul, m, cg, x[0], x[1], x[2], x[3], x[4], x[5], x[6],
-                   x[7]);
-      }
-    }
-    if (o32b_on && cg + 8 > ph.o32b_c0 && cg < ph.o32b_c0 + ph.o32b_w)
-      o32_scalar(ph.o32b, ph.ldo32b, ph.o32b_c0, ph.o32b_w, 0, 1.0f, m, cg, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-    if (OP == OP_OUT32) continue;
-    // ---- the A value (and the optional second output) ----
-    float r[8], r2[8];
-    const bool in = cg < width;
-    if (OP == OP_SOFTPLUS) {
+    for (int j = 0; j < 8; ++j) r[j] = softplus2(x[j]);
+  } else if (OP == OP_RELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = softplus2(x[j]);
-    } else if (OP == OP_RELU) {
+    for (int j = 0; j < 8; ++j) r[j] = fmaxf(x[j], 0.0f);
+  } else if (OP == OP_LINEAR) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = fmaxf(x[j], 0.0f);
-    } else if (OP == OP_LINEAR) {
+    for (int j = 0; j < 8; ++j) r[j] = x[j];
+  } else if (OP == OP_MASK) {
+    if (ph.aux0 && in) {
+      float h8[8];
+      unpack_h8(q0, h8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
+    } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = x[j];
-    } else if (OP == OP_MASK) {
-      if (ph.aux0 && in) {
-        float h8[8];
-        unpack_h8(q0[gi], h8);
+    }
+  } else {   // OP_NSTEP / OP_P1STEP / OP_P2STEP: softplus'(z) = 1 - 2^-a' from the saved activation
+    float s_[8];
+    if (in) {
+      float a8[8];
+      unpack_h8(q0, a8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = h8[j] > 0.0f ? x[j] : 0.0f;
-      } else {
+      for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);
+    } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = x[j];
-      }
-    } else {   // OP_NSTEP / OP_P1STEP / OP_P2STEP: softplus'(z) = 1 - 2^-a' from the saved activation
-      float s_[8];
+      for (int j = 0; j < 8; ++j) s_[j] = 0.0f;
+    }
+    if (OP == OP_NSTEP) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
+    } else if (OP == OP_P1STEP) {
+      float d8[8];
       if (in) {
-        float a8[8];
-        unpack_h8(q0[gi], a8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s_[j] = 1.0f - ex2f(-a8[j]);
+        unpack_h8(q1, d8);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s_[j] = 0.0f;
+        for (int j = 0; j < 8; ++j) d8[j] = 0.0f;
       }
-      if (OP == OP_NSTEP) {
+      const float am = ph.a_mul;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = s_[j] * x[j];
-      } else if (OP == OP_P1STEP) {
-        float d8[8];
-        if (in) {
-          unpack_h8(q1[gi], d8);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) d8[j] = 0.0f;
-        }
-        const float am = ph.a_mul;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          r[j] = s_[j] * x[j] * am;
-          r2[j] = 100.0f * (1.0f - s_[j]) * d8[j] * x[j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        r[j] = s_[j] * x[j] * am;
+        r2[j] = 100.0f * (1.0f - s_[j]) * d8[j] * x[j];
+      }
+    } else {
+      float z8[8];
+      if (ph.aux1 && in) {
+        unpack_h8(q1, z8);
       } else {
-        float z8[8];
-        if (ph.aux1 && in) {
-          unpack_h8(q1[gi], z8);
-        } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z8[j] = 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = fmaf(s_[j], x[j], z8[j]);
+        for (int j = 0; j < 8; ++j) z8[j] = 0.0f;
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaf(s_[j], x[j], z8[j]);
     }
-    // ragged edge: columns >= width carry the skip tail or zero padding
-    if (cg + 8 > width) ragged_tail(ph, m, cg, r, OP == OP_P1STEP ? r2 : nullptr);
-    uint32_t p[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = pack2<OP>(r[2 * i], r[2 * i + 1]);
-    if (ph.a_out) tc::tmem_st4(tA + (uint32_t)(4 * g), p);
-    if (pa) {
-      if (OP == OP_P2STEP) {               // stored pre-scaled (z-bar * dsc / kB2: the weight gradient's operand)
-        pa[gi * 128] = make_uint4(pack2<OP>(r[0] * om, r[1] * om), pack2<OP>(r[2] * om, r[3] * om),
-                                  pack2<OP>(r[4] * om, r[5] * om), pack2<OP>(r[6] * om, r[7] * om));
-      } else {
-        pa[gi * 128] = make_uint4(p[0], p[1], p[2], p[3]);
-      }
-    }
-    if (OP == OP_P1STEP && pb)
-      pb[gi * 128] = make_uint4(pack2<OP>(r2[0], r2[1]), pack2<OP>(r2[2], r2[3]), pack2<OP>(r2[4], r2[5]), pack2<OP>(r2[6], r2[7]));
   }
+  // ragged edge: columns >= width carry the skip tail or zero padding
+  if (cg + 8 > width) ragged_tail(ph.tail != nullptr, stail, ph.tail_w, ph.tail_mul, width, cg, r, r2, OP == OP_P1STEP);
+  uint32_t p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = pack2<OP>(r[2 * i], r[2 * i + 1]);
+  if (ph.a_out) tc::tmem_st4(tA + (uint32_t)(4 * g), p);
+  if (pa) {
+    if (OP == OP_P2STEP) {               // stored pre-scaled (z-bar * dsc / kB2: the weight gradient's operand)
+      pa[0] = make_uint4(pack2<OP>(r[0] * om, r[1] * om), pack2<OP>(r[2] * om, r[3] * om),
+                                pack2<OP>(r[4] * om, r[5] * om), pack2<OP>(r[6] * om, r[7] * om));
+    } else {
+      pa[0] = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+  }
+  if (OP == OP_P1STEP && pb)
+    pb[0] = make_uint4(pack2<OP>(r2[0], r2[1]), pack2<OP>(r2[2], r2[3]), pack2<OP>(r2[4], r2[5]), pack2<OP>(r2[6], r2[7]));
 }
 
 // Fast path for REGULAR phases (Phase::fast, set by launch()): every column of an active warp is a valid output (width a
@@ -499,7 +520,7 @@ __device__ __forceinline__ void fast_group(const Phase& ph, const float (&v)[8],
 template <int OP>
 __device__ __forceinline__ void fast_phase(const Phase& ph, bool last, uint32_t tD, uint32_t tA, int c0, long long m,
                                            const float* sb, uint32_t bar_d_full, uint32_t par, uint32_t bar_d_drained,
-                                           uint32_t bar_a_ready, bool* ok) {
+                                           uint32_t bar_a_ready, bool* ok, long long* dw) {
   using namespace tc;
   using T = OpTraits<OP>;
   const bool has0 = T::aux0 && ph.aux0 != nullptr, has1 = T::aux1 && ph.aux1 != nullptr;
@@ -521,7 +542,8 @@ __device__ __forceinline__ void fast_phase(const Phase& ph, bool last, uint32_t 
     if (has0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + g * 128));
     if (has1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p1 + g * 128));
   }
-  *ok = mbar_wait(bar_d_full, par);
+  *ok = mbar_wait_relaxed(bar_d_full, par);
+  VDN_TL(dw, 0);
   tc_fence_after();
   // groups 0..3 stream through two 8-value buffers; when group 4 arrives the remaining three are fetched at once and the
   // accumulator is released at half time, so the other tile's MMAs overlap the second half of this epilogue
@@ -556,55 +578,90 @@ __device__ __forceinline__ void fast_phase(const Phase& ph, bool last, uint32_t 
   }
 }
 
-// One (phase, slot) of the epilogue role for one epilogue kind: auxiliary loads of the first half go out before the
-// wait for the accumulator, D is released as soon as its second half sits in registers.
+// One (phase, slot) of the epilogue role for one epilogue kind.
 template <int OP>
 __device__ __forceinline__ bool phase_body(const Phase& ph, bool last, int s, uint32_t tD, uint32_t tA, int c0, long long m,
                                            long long N, const float* sb, const float* srow, uint16_t* stb, uint32_t bar_d_full,
-                                           uint32_t par, uint32_t bar_d_drained, uint32_t bar_a_ready, float sig, float isig) {
+                                           uint32_t par, uint32_t bar_d_drained, uint32_t bar_a_ready, float sig, float isig, long long* dw, uint32_t stail) {
   using namespace tc;
   if (OP != OP_OUT32 && OP != OP_STASH && ph.fast) {
     bool ok = true;
-    if (c0 < ph.width) {
-      fast_phase<OP>(ph, last, tD, tA, c0, m, sb, bar_d_full, par, bar_d_drained, bar_a_ready, &ok);
-    } else {                     // this warp's columns are not outputs of the phase: keep the barrier protocol in step
-      ok = mbar_wait(bar_d_full, par);
+    if ((c0 >> 6) < ph.fast) {
+      fast_phase<OP>(ph, last, tD, tA, c0, m, sb, bar_d_full, par, bar_d_drained, bar_a_ready, &ok, dw);
+      return ok;
+    }
+    if (!ph.edge) {              // this warp's columns are not outputs of the phase: keep the barrier protocol in step
+      ok = mbar_wait_relaxed(bar_d_full, par);
+      VDN_TL(dw, 0);
       mbar_arrive(bar_d_drained);
       if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
+      return ok;
     }
-    return ok;
+    // ragged edge block of a skip layer: the general path below
   }
-  uint4 q0[4], q1[4];
-  load_aux<OP>(ph, m, c0, 0, q0, q1);
-  const bool ok = mbar_wait(bar_d_full, par);
+  if (ph.tail && c0 + 64 > ph.width) {      // this warp's columns include tail columns: fetch the row's tail values now
+    for (int k = 0; k * 8 < ph.tail_w && k < 8; ++k)
+      cp_async16(stail + (uint32_t)k * 16u, reinterpret_cast<const uint16_t*>(ph.tail) + blk_index(m, ph.ldt, 8 * k));
+    cp_async_commit();
+  }
+  // general path: one group of eight columns at a time (run_group), the next group's auxiliary operands in flight
+  const int ncols = ph.a_out ? ph.a_wr : ph.width;      // columns this phase touches
+  const bool has0 = OpTraits<OP>::aux0 && ph.aux0 != nullptr, has1 = OpTraits<OP>::aux1 && ph.aux1 != nullptr;
+  const uint4* p0 = has0 ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux0) + blk_base(m, ph.ld0, c0, 0)) : nullptr;
+  const uint4* p1 = has1 ? reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux1) + blk_base(m, ph.ld1, c0, 0)) : nullptr;
+  uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0, q0n = q0, q1n = q0;
+  if (has0 && c0 < ph.width) q0n = __ldg(p0);
+  if (has1 && c0 < ph.width) q1n = __ldg(p1);
+  const bool ok = mbar_wait_relaxed(bar_d_full, par);
+  VDN_TL(dw, 0);
   tc_fence_after();
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    float v[4][8];
+  int ng = (ncols - c0 + 7) >> 3;                        // groups of this warp that the phase touches (0 .. 8)
+  ng = ng < 0 ? 0 : (ng > 8 ? 8 : ng);
+  bool released = false;
+  // the accumulator values of group g + 1 are requested before group g is processed (a tensor-memory load issued right
+  // after the group's tensor-memory store would wait for it)
+  float v[8], vn[8];
 #pragma unroll
-    for (int gi = 0; gi < 4; ++gi) {
-      if (c0 + 32 * half + 8 * gi < ph.n_mma) {
-        tmem_ld8(tD + (uint32_t)(32 * half + 8 * gi), v[gi]);
+  for (int j = 0; j < 8; ++j) vn[j] = 0.0f;
+  if (ng > 0 && c0 < ph.n_mma) tmem_ld8(tD, vn);
+#pragma unroll 1
+  for (int g = 0; g < ng; ++g) {
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = vn[j];
+    if (g + 1 < ng) {
+      if (c0 + 8 * (g + 1) < ph.n_mma) {
+        tmem_ld8(tD + (uint32_t)(8 * (g + 1)), vn);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[gi][j] = 0.0f;
+        for (int j = 0; j < 8; ++j) vn[j] = 0.0f;
       }
-    }
-    tmem_ld_wait();
-    if (half == 1) {
+    } else {                    // the accumulator has left tensor memory
       tc_fence_before();
       mbar_arrive(bar_d_drained);
       // the slot's next A operand is what it holds already: release the MMA issuer right away
       if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
+      released = true;
     }
-    run_op<OP>(ph, v, half, q0, q1, sb, srow, m, N, c0, tA, stb, sig, isig);
-    if (half == 0) load_aux<OP>(ph, m, c0, 1, q0, q1);     // second half's operands: in flight during its TMEM load
+    q0 = q0n; q1 = q1n;
+    if (g + 1 < ng && c0 + 8 * (g + 1) < ph.width) {
+      if (has0) q0n = __ldg(p0 + (g + 1) * 128);
+      if (has1) q1n = __ldg(p1 + (g + 1) * 128);
+    }
+    run_group<OP>(ph, v, g, q0, q1, sb, srow, m, N, c0, tA, stb, sig, isig, stail);
+#ifdef VDN_CHAIN_TL
+    if (dw && (threadIdx.x >> 5) == 12) (dw - 28)[40 + g] = clock64();      // warp 12: group g done
+#endif
+  }
+  if (!released) {              // none of this warp's columns belongs to the phase
+    mbar_arrive(bar_d_drained);
+    if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
   }
   return ok;
 }
 
 static __global__ void __launch_bounds__(THREADS, 1)
-chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
+chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault, long long* __restrict__ dbg) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full[WSTAGES], w_empty[WSTAGES], a_ready[2], d_full, d_drained;
@@ -613,6 +670,7 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
   const uint32_t sW = (smem_u32(smem_raw) + 1023u) & ~1023u;
   float* sB = reinterpret_cast<float*>(smem_raw + (sW - smem_u32(smem_raw)) + WSTAGES * W_STAGE);
   float* sRow = sB + MAX_PHASES * 256;
+  const uint32_t sTail = smem_u32(sRow + 512);      // [128 rows][128 bytes]
   const long long ntiles = (a.N + 127) / 128;
   const long long G = gridDim.x;
 
@@ -648,6 +706,7 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t tD = lane_base + (uint32_t)c0;
     uint32_t dcnt = 0;
+    const uint32_t stail = sTail + (uint32_t)row * 128u;
     const float sig = a.sigma ? __ldg(a.sigma) : 1.0f, isig = a.sigma ? __ldg(a.sigma + 1) : 1.0f;
     // [128 x w] 16-bit values, row-major in HBM -> slot s (packed columns 0 ..), then signal the slot
     auto aload = [&](int s, long long tile, const void* src, int ld, int w) {
@@ -713,17 +772,24 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
           uint16_t* stb = a.stash ? a.stash + (((size_t)blockIdx.x * 2 + s) * MAX_STASH * 8) * (512 * 8) + (size_t)tid * 8 : nullptr;
           const uint32_t bf = smem_u32(&d_full), bd = smem_u32(&d_drained), ba = smem_u32(&a_ready[s]), par = dcnt & 1;
           ++dcnt;
+          long long* dw = nullptr;
+          (void)dw;
+#ifdef VDN_CHAIN_TL
+          if (dbg && blockIdx.x == 0 && lane == 0)
+            dw = dbg + ((((tX - blockIdx.x) / (2 * G)) * MAX_PHASES + p) * 2 + s) * 48 + 4 + 2 * warp;
+#endif
           switch (ph.op) {
-            case OP_OUT32: ok = phase_body<OP_OUT32>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
-            case OP_SOFTPLUS: ok = phase_body<OP_SOFTPLUS>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
-            case OP_NSTEP: ok = phase_body<OP_NSTEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
-            case OP_P1STEP: ok = phase_body<OP_P1STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
-            case OP_P2STEP: ok = phase_body<OP_P2STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
-            case OP_RELU: ok = phase_body<OP_RELU>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
-            case OP_LINEAR: ok = phase_body<OP_LINEAR>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
-            case OP_STASH: ok = phase_body<OP_STASH>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
-            default: ok = phase_body<OP_MASK>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig); break;
+            case OP_OUT32: ok = phase_body<OP_OUT32>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
+            case OP_SOFTPLUS: ok = phase_body<OP_SOFTPLUS>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
+            case OP_NSTEP: ok = phase_body<OP_NSTEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
+            case OP_P1STEP: ok = phase_body<OP_P1STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
+            case OP_P2STEP: ok = phase_body<OP_P2STEP>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
+            case OP_RELU: ok = phase_body<OP_RELU>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
+            case OP_LINEAR: ok = phase_body<OP_LINEAR>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
+            case OP_STASH: ok = phase_body<OP_STASH>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
+            default: ok = phase_body<OP_MASK>(ph, last, s, tD, tA, c0, m, a.N, sb, sRow, stb, bf, par, bd, ba, sig, isig, dw, stail); break;
           }
+          VDN_TL(dw, 1);
           if (!last) {
             if (ph.a_out) {
               tmem_st_wait();
@@ -754,11 +820,19 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
         const int keep = nkb < KEEP ? nkb : KEEP;
         for (int s = 0; s < 2 && ok; ++s) {
           if (s && !hasY) break;
+          long long* di = nullptr;
+          (void)di;
+#ifdef VDN_CHAIN_TL
+          if (dbg && blockIdx.x == 0) di = dbg + ((((tX - blockIdx.x) / (2 * G)) * MAX_PHASES + p) * 2 + s) * 48;
+#endif
+          VDN_TL(di, 0);
           // the accumulator of the previous phase must have been drained (first phase ever: passes immediately)
           ok = mbar_wait(smem_u32(&d_drained), (drained & 1) ^ 1);
           ++drained;
+          VDN_TL(di, 1);
           ok = ok && mbar_wait(smem_u32(&a_ready[s]), acnt[s] & 1);
           ++acnt[s];
+          VDN_TL(di, 2);
           tc_fence_after();
           // Slot X streams all blocks of the phase in order and leaves the LAST `keep` in the ring; slot Y uses those
           // first (no wait), releases them, then takes the others, which were fetched again behind them.  (Holding the
@@ -781,6 +855,7 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault) {
             if (s == 1 || !hasY || kb < nkb - keep) umma_commit(smem_u32(&w_empty[ws]));
           }
           umma_commit(smem_u32(&d_full));
+          VDN_TL(di, 3);
         }
         wt += (uint32_t)(hasY ? 2 * nkb - keep : nkb);
       }
@@ -898,10 +973,17 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
     for (int p = 0; p < a.P; ++p) a.ph[p].a_bf16 = a.ph[p].b_bf16 = 0;
   for (int p = 0; p < a.P; ++p) {
     Phase& ph = a.ph[p];
-    ph.fast = ((ph.width & 63) == 0 && (!ph.a_out || ph.a_wr == ph.width) && !ph.o32 && !ph.o32b && !ph.r1 && ph.stash_r < 0 &&
-               !ph.tail && ph.op != OP_OUT32 && ph.op != OP_STASH &&
-               (!(ph.op == OP_NSTEP || ph.op == OP_P1STEP || ph.op == OP_P2STEP) || ph.aux0) && (ph.op != OP_P1STEP || ph.aux1))
-                  ? 1 : 0;
+    const bool common = !ph.o32b && !ph.r1 && ph.stash_r < 0 && ph.op != OP_OUT32 && ph.op != OP_STASH &&
+                        (!(ph.op == OP_NSTEP || ph.op == OP_P1STEP || ph.op == OP_P2STEP) || ph.aux0) &&
+                        (ph.op != OP_P1STEP || ph.aux1);
+    // regular phase: every column of an active warp is an output, nothing else happens
+    const bool whole = common && (ph.width & 63) == 0 && (!ph.a_out || ph.a_wr == ph.width) && !ph.o32 && !ph.tail;
+    // skip layer: the outputs end inside the last 64-column block, which also carries the tail / zero padding up to a_wr and
+    // possibly an fp32 side output of exactly those columns - that block takes the general path, the others the fast one
+    const bool edge = common && !whole && ph.a_out && (ph.a_wr & 63) == 0 && ph.a_wr > ph.width && ph.a_wr - ph.width < 64 &&
+                      (!ph.o32 || ph.o32_c0 >= ph.a_wr - 64);
+    ph.fast = (whole || edge) ? ph.width / 64 : 0;
+    ph.edge = edge ? 1 : 0;
     ph.o32_vec = (ph.o32 && ph.act == 0 && ((uintptr_t)ph.o32 & 15) == 0 && (ph.ldo32 & 3) == 0 && (ph.o32_c0 & 7) == 0) ? 1 : 0;
   }
   if (a.N <= 0) return 0;
@@ -915,6 +997,7 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
         (ph.img2_off >= 0 && (ph.img2_off & 255)) || (ph.a_bf16 != ph.b_bf16))
       return bad_value("chain phase shape", p);
     if ((ph.op == OP_STASH || ph.stash_r >= 0) && !a.stash) return bad_value("chain phase stash", p);
+    if (ph.tail && (ph.tail_w < 1 || ph.tail_w > 64 || (ph.ldt & 7))) return bad_value("chain phase tail", p);
     // every operand is fp16 (OpTraits); cotangent scaling needs the launch's sigma
     if (ph.a_bf16 || ph.b_bf16 || (ph.o16b && ph.op != OP_P1STEP) || (ph.o16a_mul != 1.0f && ph.op != OP_P2STEP) ||
         ((ph.r1_scaled || ph.o32_unscale) && !a.sigma))
@@ -937,7 +1020,16 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
     attr_set = true;
   }
   prof_begin(family, st, flops, bytes);
-  VDN_LAUNCH(chain_kernel, grid_for(a.N), THREADS, SMEM, st, a, g_tc_fault);
+  long long* dbg = nullptr;
+#ifdef VDN_CHAIN_TL
+  {   // record the VDN_TL_LAUNCH-th chain launch of this translation unit
+    static int tl_n = 0;
+    const char* e = getenv("VDN_TL_LAUNCH");
+    if (e && atoi(e) == tl_n) dbg = g_tc_dbg;
+    ++tl_n;
+  }
+#endif
+  VDN_LAUNCH(chain_kernel, grid_for(a.N), THREADS, SMEM, st, a, g_tc_fault, dbg);
   prof_end(family, st);
   return debug_sync(st, "chain_kernel", a.ph[0].op);
 }

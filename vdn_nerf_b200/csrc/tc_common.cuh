@@ -55,6 +55,17 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_
   }
   return false;
 }
+// For the epilogue warps of the chain engine: a few tight polls (the barrier usually flips within them), then back off, so
+// that warps waiting for an accumulator do not take issue slots from the warps that are still producing it - a spinning
+// warp is always "ready" to the scheduler, and twelve of them made the four warps of a ragged skip layer four times slower.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t max_spins = 1u << 22) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < max_spins; ++i) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if (i >= 8) __nanosleep(40);
+  }
+  return false;
+}
 // Same, for long waits of single-thread roles (MMA issuer, weight stream): back off between polls so the spinning
 // thread does not take issue slots from the warps doing the element-wise work on its scheduler.
 __device__ __forceinline__ bool mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns = 64, uint32_t max_spins = 1u << 22) {
