@@ -586,18 +586,59 @@ __device__ __forceinline__ bool phase_body(const Phase& ph, bool last, int s, ui
   using namespace tc;
   if (OP != OP_OUT32 && OP != OP_STASH && ph.fast) {
     bool ok = true;
-    if ((c0 >> 6) < ph.fast) {
-      fast_phase<OP>(ph, last, tD, tA, c0, m, sb, bar_d_full, par, bar_d_drained, bar_a_ready, &ok, dw);
-      return ok;
-    }
-    if (!ph.edge) {              // this warp's columns are not outputs of the phase: keep the barrier protocol in step
+    if (ph.edge) {
+      // Skip layer: three regular 64-column blocks and the ragged one.  The ragged block's eight groups go through the
+      // general element-wise code, which is a long dependent chain per group - left to the block's own four warps (one
+      // per scheduler, nothing to interleave with) it took 4x a regular block.  So it is SHARED: every warp of a row
+      // quarter may touch all of the quarter's tensor-memory lanes, and each of the four takes two groups, before its
+      // own regular block.
+      const int hq = c0 >> 6, ce = ph.fast * 64;
+      const uint32_t tDe = tD - (uint32_t)c0 + (uint32_t)ce, tAe = tA - (uint32_t)(hq * 32) + (uint32_t)(ph.fast * 32);
+      const int g0 = 2 * ((hq + 1) & 3);
+      const bool has0 = OpTraits<OP>::aux0 && ph.aux0 != nullptr, has1 = OpTraits<OP>::aux1 && ph.aux1 != nullptr;
+      uint4 q0[2], q1[2];
+      q0[0] = q0[1] = q1[0] = q1[1] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (ce + 8 * (g0 + k) < ph.width) {
+          if (has0) q0[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux0) + blk_base(m, ph.ld0, ce, 0)) + (g0 + k) * 128);
+          if (has1) q1[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ph.aux1) + blk_base(m, ph.ld1, ce, 0)) + (g0 + k) * 128);
+        }
+      }
+      if (ph.tail) {
+        for (int k = 0; k * 8 < ph.tail_w && k < 8; ++k)
+          cp_async16(stail + (uint32_t)k * 16u, reinterpret_cast<const uint16_t*>(ph.tail) + blk_index(m, ph.ldt, 8 * k));
+        cp_async_commit();
+      }
       ok = mbar_wait_relaxed(bar_d_full, par);
-      VDN_TL(dw, 0);
-      mbar_arrive(bar_d_drained);
-      if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
-      return ok;
+      tc_fence_after();
+      float v[2][8];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (ce + 8 * (g0 + k) < ph.n_mma) {
+          tmem_ld8(tDe + (uint32_t)(8 * (g0 + k)), v[k]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[k][j] = 0.0f;
+        }
+      }
+      tmem_ld_wait();
+#pragma unroll 1
+      for (int k = 0; k < 2; ++k)
+        run_group<OP>(ph, k ? v[1] : v[0], g0 + k, k ? q0[1] : q0[0], k ? q1[1] : q1[0], sb, srow, m, N, ce, tAe, stb, sig, isig, stail);
     }
-    // ragged edge block of a skip layer: the general path below
+    if ((c0 >> 6) < ph.fast) {
+      bool ok2 = true;
+      fast_phase<OP>(ph, last, tD, tA, c0, m, sb, bar_d_full, par, bar_d_drained, bar_a_ready, &ok2, dw);
+      return ok && ok2;
+    }
+    // this warp's own columns are not regular outputs of the phase: keep the barrier protocol in step
+    if (!ph.edge) ok = mbar_wait_relaxed(bar_d_full, par);
+    VDN_TL(dw, 0);
+    tc_fence_before();
+    mbar_arrive(bar_d_drained);
+    if (!last && !ph.a_out && !ph.aload) mbar_arrive(bar_a_ready);
+    return ok;
   }
   if (ph.tail && c0 + 64 > ph.width) {      // this warp's columns include tail columns: fetch the row's tail values now
     for (int k = 0; k * 8 < ph.tail_w && k < 8; ++k)
@@ -980,8 +1021,8 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
     const bool whole = common && (ph.width & 63) == 0 && (!ph.a_out || ph.a_wr == ph.width) && !ph.o32 && !ph.tail;
     // skip layer: the outputs end inside the last 64-column block, which also carries the tail / zero padding up to a_wr and
     // possibly an fp32 side output of exactly those columns - that block takes the general path, the others the fast one
-    const bool edge = common && !whole && ph.a_out && (ph.a_wr & 63) == 0 && ph.a_wr > ph.width && ph.a_wr - ph.width < 64 &&
-                      (!ph.o32 || ph.o32_c0 >= ph.a_wr - 64);
+    const bool edge = common && !whole && ph.a_out && ph.a_wr == 256 && ph.width > 192 && ph.width < 256 &&
+                      (!ph.o32 || ph.o32_c0 >= 192);
     ph.fast = (whole || edge) ? ph.width / 64 : 0;
     ph.edge = edge ? 1 : 0;
     ph.o32_vec = (ph.o32 && ph.act == 0 && ((uintptr_t)ph.o32 & 15) == 0 && (ph.ldo32 & 3) == 0 && (ph.o32_c0 & 7) == 0) ? 1 : 0;
