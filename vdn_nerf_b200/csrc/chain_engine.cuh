@@ -11,16 +11,21 @@
 //
 // Execution model (the one of sdf_chain_tc.cuh, generalised): per CTA two tiles ("slots" X and Y) are in flight and
 // alternate phases.  The A operand of a slot lives in TENSOR MEMORY as packed 16-bit pairs (columns 256 + 128 s ..,
-// lane = point) and is the A operand of tcgen05.mma kind::f16 (fp16 or bf16 A, fp16 weights, fp32 accumulate); one
-// 256-column fp32 accumulator D is shared by both slots: sixteen epilogue warps drain it into registers as soon as
-// a phase completes, release it for the other slot's MMAs, and run the element-wise work from registers while the
-// tensor pipe is busy with the other slot.  Weight K blocks ([n x 64] fp16 SWIZZLE_128B images, mlp_layout.cuh)
-// stream through a 6-stage cp.async.bulk / mbarrier ring; the first blocks of a phase serve both slots.
+// lane = point) and is the A operand of tcgen05.mma kind::f16 (fp16 A, fp16 weights, fp32 accumulate); one
+// 256-column fp32 accumulator D is shared by both slots: sixteen epilogue warps stream it through registers group by
+// group, release it at half time for the other slot's MMAs, and finish the element-wise work while the tensor pipe is
+// busy with the other slot.  Weight K blocks ([n x 64] fp16 SWIZZLE_128B images, mlp_layout.cuh) stream through a
+// 4-stage cp.async.bulk / mbarrier ring that holds exactly one phase; both slots use the same blocks.
 //
-// What reaches HBM is 16-bit: every phase may store the A operand it produces (row-major [Npad, ld] fp16 / bf16) -
-// that tensor is at the same time the saved activation of the backward passes and an operand of the grouped
-// weight-gradient kernel (wgrad16.cuh), which reads it through TMA tensor maps.  Saved activations are read back
-// by the later passes as per-thread 128-byte rows (thread = point, 64 consecutive features).
+// What reaches HBM is fp16 and tile-blocked ([tile][8-column group][128 rows][8], see blk_index): every phase may store
+// the A operand it produces - that tensor is at the same time the saved activation of the backward passes and an
+// operand of the grouped weight-gradient kernel (wgrad16.cuh), which reads it through TMA tensor maps.  Cotangents
+// carry the launch's power-of-two loss scale (Args::sigma).
+//
+// Two element-wise code paths: the FAST path (fast_phase / fast_group: fully unrolled, resident in the instruction
+// cache, no spills) for regular 64-column blocks, and the GENERAL path (run_group, looped) for everything else - fp32
+// side outputs, rank-1 terms, scratch, the ragged block of a skip layer.  tools/diag_chain_tl.py (build with
+// -DVDN_CHAIN_TL) prints the per-CTA timeline that guided their design.
 //
 // Thread mapping of the epilogue warps: warp w -> TMEM lane quarter q = w & 3 (rows 32 q .. 32 q + 31) and column
 // block hq = w >> 2 (columns 64 hq .. 64 hq + 63), eight groups of eight columns.
@@ -32,7 +37,8 @@
 
 // Debug build (-DVDN_CHAIN_TL): CTA 0 records clock64() stamps of every (tile pair, phase, slot) into the buffer given to
 // vdn_debug_timeline(): [0..3] MMA issuer (start, accumulator drained, A ready, MMAs issued), [4 + 2 w], [5 + 2 w] epilogue
-// warp w (accumulator full, phase done); 40 values per (pair, phase, slot).  tools/diag_chain_tl.py prints it.
+// warp w (accumulator full, phase done), [40 + g] warp 12's general-path group g done; 48 values per (pair, phase, slot).
+// tools/diag_chain_tl.py prints it.
 #ifdef VDN_CHAIN_TL
 #define VDN_TL(ptr, i) do { if (ptr) (ptr)[i] = clock64(); } while (0)
 #else
