@@ -124,6 +124,7 @@ struct Args {
   const void* a0; int a0_ld, a0_w;          // A operand of phase 0
   long long row_off[2]; int row_len[2];     // rank-1 row vectors (float offsets into packed, -1: none)
   uint16_t* stash;                          // fp16 scratch [grid][2][MAX_STASH][8][512][8] (stays in L2)
+  int pf1_next;                             // L1 prefetch of the next tile's first loads during the last phase
   int pf_mode;                              // software L2 prefetch one phase ahead: 0 none (default), 1 per line, 2 bulk (TMA)
   const float* sigma;                       // backward passes: device {sigma, 1 / sigma}, the power-of-two loss scale the
                                             // fp16 cotangents of this launch carry (null: 1)
@@ -815,6 +816,29 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault, long long*
               }
             }
           }
+          if (last && a.pf1_next) {
+            // tile boundary: the slot's next tile starts with loads nothing has announced yet (its A operand, the
+            // auxiliary operands of phase 0) - bring this thread's lines into L1 while the last phase runs
+            const long long tn = tX + (2 + s) * G;
+            if (tn < ntiles) {
+              const long long mn = tn * 128 + row;
+              if (c0 < a.a0_w) {
+                const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.a0) + blk_base(mn, a.a0_ld, c0, 0));
+                for (int g = 0; g < 8 && c0 + 8 * g < a.a0_w; ++g) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + g * 128));
+              }
+              const Phase& p0 = a.ph[0];
+              if (c0 < p0.width) {
+                if (p0.aux0) {
+                  const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p0.aux0) + blk_base(mn, p0.ld0, c0, 0));
+                  for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + g * 128));
+                }
+                if (p0.aux1) {
+                  const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p0.aux1) + blk_base(mn, p0.ld1, c0, 0));
+                  for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + g * 128));
+                }
+              }
+            }
+          }
           const uint32_t tA = lane_base + 256u + (uint32_t)(s * 128 + hq * 32);
           uint16_t* stb = a.stash ? a.stash + (((size_t)blockIdx.x * 2 + s) * MAX_STASH * 8) * (512 * 8) + (size_t)tid * 8 : nullptr;
           const uint32_t bf = smem_u32(&d_full), bd = smem_u32(&d_drained), ba = smem_u32(&a_ready[s]), par = dcnt & 1;
@@ -1015,6 +1039,9 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
     static int pf2 = -1;
     if (pf2 < 0) { const char* e = getenv("VDN_PF2"); pf2 = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0; }
     a.pf_mode = pf2;
+    static int pf1n = -1;
+    if (pf1n < 0) { const char* e = getenv("VDN_PF1NEXT"); pf1n = (e && e[0] == '0') ? 0 : 1; }      // on by default (-1 % step time, measured)
+    a.pf1_next = pf1n;
   }
   if (debug_nomix())
     for (int p = 0; p < a.P; ++p) a.ph[p].a_bf16 = a.ph[p].b_bf16 = 0;
