@@ -174,7 +174,7 @@ def reset_grad_arena_use() -> None:
 
 def _grad_buffer(p: torch.Tensor) -> torch.Tensor:
     v = _GRAD_ARENA.get(id(p))
-    if v is None or id(p) in _ARENA_USED or p.grad is not None or v.device != p.device:
+    if v is None or id(p) in _ARENA_USED or p.grad is not None or v.device != p.device or v.shape != p.shape:
         return torch.empty_like(p)
     _ARENA_USED.add(id(p))
     return v.view_as(v)         # a fresh alias: autograd may adopt it as .grad without cloning
