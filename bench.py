@@ -423,6 +423,12 @@ def run_ours(args):
         barrier(world)
         t0 = time.perf_counter()
         n_e2e = max(2, args.steps // 2)
+        # Every step copies its rays from pinned host memory and copies its loss back to pinned host memory; the host
+        # READS the loss of step i after it has queued step i + 1 (one event per step), the way a training loop that logs
+        # its loss without stalling the GPU does - all n_e2e values are read before the clock stops.
+        loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
+        losses = []
         for i in range(n_e2e):
             for h, g_ in zip(host, dbuf):
                 g_.copy_(h, non_blocking=True)
@@ -432,7 +438,14 @@ def run_ours(args):
             else:
                 loss, _ = train_step(rend, params, dbuf[0], dbuf[1], dbuf[2], dbuf[3], dbuf[4], gt_feats=gt,
                                      background_rgb=bg, cos_anneal_ratio=1.0, grad_sync=sync, global_batch=B * world)
-            float(loss)                                   # device -> host read of the step's result
+            loss_host[i & 1].copy_(loss.reshape(1), non_blocking=True)      # device -> host copy of the step's result
+            loss_ev[i & 1].record()
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                losses.append(float(loss_host[(i - 1) & 1]))
+        loss_ev[(n_e2e - 1) & 1].synchronize()
+        losses.append(float(loss_host[(n_e2e - 1) & 1]))
+        assert len(losses) == n_e2e and all(v == v for v in losses)
         barrier(world)
         e2e_t = max_over_ranks((time.perf_counter() - t0) / n_e2e, world, dev)
         # per-family device time of one extra step (CUDA events on the launching stream)
