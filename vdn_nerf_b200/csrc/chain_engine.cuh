@@ -70,27 +70,24 @@ enum Op : int {
   OP_OUT32 = 0,   // fp32 output only: o32[m, c] = act(x) * o32_mul (act 0 none, 1 sigmoid, 2 relu)
   OP_SOFTPLUS,    // A = fp16 log2(1 + 2^x)                                     (SDF forward, base-2 softplus units)
   OP_NSTEP,       // A = fp16 S * x,  S = 1 - 2^-aux0                            (SDF normals pass: delta_{l-1})
-  OP_P1STEP,      // A = bf16 S * x * a_mul ; o16b = bf16 100 (1 - S) aux1 x     (backward of the normals pass)
-  OP_P2STEP,      // A = bf16 S * x + aux1                                       (ordinary backward with injection)
+  OP_P1STEP,      // A = S * x * a_mul ; o16b = 100 (1 - S) aux1 x               (backward of the normals pass)
+  OP_P2STEP,      // A = S * x + aux1                                            (ordinary backward with injection)
   OP_RELU,        // A = fp16 max(x, 0)
   OP_LINEAR,      // A = fp16 x
   OP_STASH,       // scratch <- raw accumulator
-  OP_MASK,        // A = bf16 (aux0 > 0 ? x : 0)   (aux0 null: x)
+  OP_MASK,        // A = (aux0 > 0 ? x : 0)   (aux0 null: x)
 };
 // x = acc * dsc + bias (+ stash) (+ r1[m] * row[c])
 
 struct Phase {
   // ---- tensor-core side ----
   long long img_off;     // float offset (into `packed`) of K block 0 of the 16-bit image of B
-  long long img2_off;    // second image accumulated with the same A (the "lo" part of a bf16 hi/lo weight), -1: none
   int img_rows;          // rows per K block of that image
   int row0;              // first image row (multiple of 8)
   int kb0;               // first K block
   int n_mma;             // N of the MMA (multiple of 16, <= 256)
   int nks;               // K steps of 16 (1..16)
   int a_col;             // packed-column offset of the A operand inside the slot
-  int a_bf16;            // A operand format (0 fp16, 1 bf16)
-  int b_bf16;            // B (weight image) format
   // ---- epilogue ----
   int op;
   int width;             // valid output columns of this phase (<= n_mma)
@@ -142,11 +139,6 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ uint32_t pack_b2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
 __device__ __forceinline__ void unpack_h8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -155,21 +147,10 @@ __device__ __forceinline__ void unpack_h8(const uint4& u, float (&f)[8]) {
     f[2 * i] = t.x; f[2 * i + 1] = t.y;
   }
 }
-__device__ __forceinline__ void unpack_b8(const uint4& u, float (&f)[8]) {
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __uint_as_float(w[i] << 16);
-    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
-}
 __device__ __forceinline__ float ex2f(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
-}
-__device__ __forceinline__ void unpack8(const uint4& u, int bf16, float (&f)[8]) {
-  if (bf16) unpack_b8(u, f); else unpack_h8(u, f);
 }
 // a' = log2(1 + 2^t), same evaluation as sdf_chain_tc.cuh
 __device__ __forceinline__ float softplus2(float t) {
@@ -201,10 +182,6 @@ __device__ __forceinline__ uint4 ld16(const void* base, long long m, int W, int 
 }
 __device__ __forceinline__ void st16(void* base, long long m, int W, int c, const uint32_t (&p)[4]) {
   *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + blk_index(m, W, c)) = make_uint4(p[0], p[1], p[2], p[3]);
-}
-__device__ __forceinline__ float ld16_one(const void* base, long long m, int W, int c, int bf16) {
-  const uint16_t h = __ldg(reinterpret_cast<const uint16_t*>(base) + blk_index(m, W, c));
-  return bf16 ? __uint_as_float((uint32_t)h << 16) : __half2float(__ushort_as_half(h));
 }
 // the 128-byte lines of columns [c0, c0 + 64) of rows m .. m + 31 (a warp's rows) -> L2; issued by lanes 0, 8, 16, 24
 __device__ __forceinline__ void prefetch16(const void* base, long long m, int W, int c0, int wmax, int lane) {
@@ -885,15 +862,13 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault, long long*
       const bool hasY = tX + G < ntiles;
       for (int p = 0; p < a.P && ok; ++p) {
         const Phase& ph = a.ph[p];
-        const uint32_t idesc = umma_idesc_f16(128, (uint32_t)ph.n_mma) | (ph.a_bf16 ? (1u << 7) : 0u) | (ph.b_bf16 ? (1u << 10) : 0u);
-        const int nkb1 = (ph.nks + 3) >> 2;                      // K blocks of one image
-        const int nkb = ph.img2_off >= 0 ? 2 * nkb1 : nkb1;      // blocks streamed per phase (hi image, then lo image)
+        const uint32_t idesc = umma_idesc_f16(128, (uint32_t)ph.n_mma);
+        const int nkb = (ph.nks + 3) >> 2;                       // K blocks streamed per phase
         const int keep = nkb < KEEP ? nkb : KEEP;
         for (int s = 0; s < 2 && ok; ++s) {
           if (s && !hasY) break;
-          long long* di = nullptr;
-          (void)di;
 #ifdef VDN_CHAIN_TL
+          long long* di = nullptr;
           if (dbg && blockIdx.x == 0) di = dbg + ((((tX - blockIdx.x) / (2 * G)) * MAX_PHASES + p) * 2 + s) * 48;
 #endif
           VDN_TL(di, 0);
@@ -918,10 +893,9 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault, long long*
               tc_fence_after();
             }
             const uint32_t b0 = sW + ws * W_STAGE;
-            const int ka = kb >= nkb1 ? kb - nkb1 : kb;          // K block of A (the lo image reuses the same A columns)
-            const int nk = ph.nks - 4 * ka < 4 ? ph.nks - 4 * ka : 4;
+            const int nk = ph.nks - 4 * kb < 4 ? ph.nks - 4 * kb : 4;
             for (int ks = 0; ks < nk; ++ks)
-              umma_f16_ts(tmem_base, tAcol + (uint32_t)(s * 128 + ph.a_col + ka * 32 + ks * 8), umma_desc_sw128(b0 + ks * 32),
+              umma_f16_ts(tmem_base, tAcol + (uint32_t)(s * 128 + ph.a_col + kb * 32 + ks * 8), umma_desc_sw128(b0 + ks * 32),
                           idesc, (j | ks) ? 1u : 0u);
             if (s == 1 || !hasY || kb < nkb - keep) umma_commit(smem_u32(&w_empty[ws]));
           }
@@ -939,18 +913,15 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault, long long*
       for (int p = 0; p < a.P && ok; ++p) {
         const Phase& ph = a.ph[p];
         const uint32_t bytes = (uint32_t)ph.n_mma * 128u;
-        const int nkb1 = (ph.nks + 3) >> 2;
-        const int nkb = ph.img2_off >= 0 ? 2 * nkb1 : nkb1;
+        const int nkb = (ph.nks + 3) >> 2;
         const int keep = nkb < KEEP ? nkb : KEEP;
         const int nfetch = hasY ? 2 * nkb - keep : nkb;
         for (int f = 0; f < nfetch && ok; ++f, ++wt) {
           const int kb = f < nkb ? f : f - nkb;                  // slot X: all blocks; slot Y: the first nkb - keep again
-          const int ka = kb >= nkb1 ? kb - nkb1 : kb;
-          const long long img = kb >= nkb1 ? ph.img2_off : ph.img_off;
           const uint32_t ws = wt % WSTAGES, wph = (wt / WSTAGES) & 1;
           ok = mbar_wait_backoff(smem_u32(&w_empty[ws]), wph ^ 1, 256);
           mbar_arrive_expect_tx(smem_u32(&w_full[ws]), bytes);
-          bulk_g2s(sW + ws * W_STAGE, a.packed + img + ((size_t)(ph.kb0 + ka) * ph.img_rows + ph.row0) * 32, bytes,
+          bulk_g2s(sW + ws * W_STAGE, a.packed + ph.img_off + ((size_t)(ph.kb0 + kb) * ph.img_rows + ph.row0) * 32, bytes,
                    smem_u32(&w_full[ws]));
         }
       }
@@ -967,7 +938,7 @@ inline Phase make_phase() {
   Phase p;
   memset(&p, 0, sizeof(p));
   p.dsc = 1.0f; p.bias_off = -1; p.bias_mul = 1.0f; p.a_mul = 1.0f; p.o16a_mul = 1.0f; p.o32_mul = 1.0f; p.tail_mul = 1.0f;
-  p.r1_mul = 1.0f; p.stash_w = -1; p.stash_r = -1; p.img2_off = -1;
+  p.r1_mul = 1.0f; p.stash_w = -1; p.stash_r = -1;
   return p;
 }
 inline void init_args(Args* a) {
@@ -976,16 +947,9 @@ inline void init_args(Args* a) {
 }
 // B = rows [row0, row0 + n) of the fp16 image at img_off ([kblocks][img_rows][64]), K blocks kb0 ..
 inline void set_mma(Phase* p, long long img_off, int img_rows, int row0, int kb0, int n, int k, int a_col = 0) {
-  p->img_off = img_off; p->img2_off = -1; p->img_rows = img_rows; p->row0 = row0; p->kb0 = kb0;
-  p->n_mma = (n + 15) & ~15; p->nks = (k + 15) / 16; p->a_bf16 = 0; p->b_bf16 = 0; p->a_col = a_col;
+  p->img_off = img_off; p->img_rows = img_rows; p->row0 = row0; p->kb0 = kb0;
+  p->n_mma = (n + 15) & ~15; p->nks = (k + 15) / 16; p->a_col = a_col;
 }
-// bf16 A operand times a bf16 hi/lo weight pair (two accumulating passes over the same A columns)
-inline void set_mma_bf16(Phase* p, long long hi_off, long long lo_off, int img_rows, int row0, int kb0, int n, int k,
-                         int a_col = 0) {
-  set_mma(p, hi_off, img_rows, row0, kb0, n, k, a_col);
-  p->img2_off = lo_off; p->a_bf16 = 1; p->b_bf16 = 1;
-}
-
 inline int num_sms() {
   static int n = 0;
   if (!n) {
@@ -1014,14 +978,6 @@ static inline int debug_sync(cudaStream_t st, const char* what, int tag) {
   return (int)e;
 }
 
-// Debug aid (VDN_NOMIX=1): declare every operand fp16 to the tensor core (numerically wrong for bf16 data; isolates
-// instruction-descriptor problems).
-static inline bool debug_nomix() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("VDN_NOMIX"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on == 1;
-}
-
 // invalid table / descriptor (a bug in the caller, fatal for the call): say where
 static inline int bad_value(const char* where, int detail) {
   fprintf(stderr, "[vdn] invalid value: %s (%d)\n", where, detail);
@@ -1043,8 +999,6 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
     if (pf1n < 0) { const char* e = getenv("VDN_PF1NEXT"); pf1n = (e && e[0] == '0') ? 0 : 1; }      // on by default (-1 % step time, measured)
     a.pf1_next = pf1n;
   }
-  if (debug_nomix())
-    for (int p = 0; p < a.P; ++p) a.ph[p].a_bf16 = a.ph[p].b_bf16 = 0;
   for (int p = 0; p < a.P; ++p) {
     Phase& ph = a.ph[p];
     const bool common = !ph.o32b && !ph.r1 && ph.stash_r < 0 && ph.op != OP_OUT32 && ph.op != OP_STASH &&
@@ -1067,16 +1021,15 @@ static inline int launch(const Args& a_in, cudaStream_t st, int family) {
     const Phase& ph = a.ph[p];
     if (ph.n_mma < 16 || ph.n_mma > 256 || (ph.n_mma & 15) || ph.nks < 1 || ph.nks > 16 || (ph.row0 & 7) ||
         ph.width > ph.n_mma || (ph.a_out && (p == a.P - 1 || (ph.a_wr & 7) || ph.a_wr > 256)) ||
-        (ph.aload && (ph.a_out || p == a.P - 1 || (ph.al_w & 7))) || (ph.img_off & 255) ||
-        (ph.img2_off >= 0 && (ph.img2_off & 255)) || (ph.a_bf16 != ph.b_bf16))
+        (ph.aload && (ph.a_out || p == a.P - 1 || (ph.al_w & 7))) || (ph.img_off & 255))
       return bad_value("chain phase shape", p);
     if ((ph.op == OP_STASH || ph.stash_r >= 0) && !a.stash) return bad_value("chain phase stash", p);
     if (ph.tail && (ph.tail_w < 1 || ph.tail_w > 64 || (ph.ldt & 7))) return bad_value("chain phase tail", p);
     // every operand is fp16 (OpTraits); cotangent scaling needs the launch's sigma
-    if (ph.a_bf16 || ph.b_bf16 || (ph.o16b && ph.op != OP_P1STEP) || (ph.o16a_mul != 1.0f && ph.op != OP_P2STEP) ||
+    if ((ph.o16b && ph.op != OP_P1STEP) || (ph.o16a_mul != 1.0f && ph.op != OP_P2STEP) ||
         ((ph.r1_scaled || ph.o32_unscale) && !a.sigma))
       return bad_value("chain phase format", p);
-    flops += 2.0 * (double)a.N * ph.n_mma * ph.nks * 16 * (ph.img2_off >= 0 ? 2 : 1);
+    flops += 2.0 * (double)a.N * ph.n_mma * ph.nks * 16;
     const double row16 = 2.0 * (double)a.N;
     if (ph.aux0) bytes += row16 * ph.width;
     if (ph.aux1) bytes += row16 * ph.width;
