@@ -130,12 +130,12 @@ def max_over_ranks(x, world, dev):
     return float(t[0])
 
 
-def ncu_traffic(name):
+def ncu_traffic(name, rnd="r02"):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches) from the
-    committed `ncu --set full` summary profiles/r02_ncu_full_<name>.txt; None when the file is missing."""
+    committed `ncu --set full` summary profiles/<rnd>_ncu_full_<name>.txt; None when the file is missing."""
     units = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_full_%s.txt" % name)
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "%s_ncu_full_%s.txt" % (rnd, name))
         tot, n = 0.0, 0
         for ln in open(path):
             f = ln.split()
@@ -364,7 +364,7 @@ def run_ours(args):
                      "roofline": {"bound": "tensor", "kernel": kname,
                                   "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                                   "frac": ach / pk["bf16_sustained"],
-                                  "traffic": ncu_traffic("chain") if args.precision == "tf32" else None,
+                                  "traffic": ncu_traffic("chain", "r01") if args.precision == "tf32" else None,
                                   "traffic_note": "DRAM bytes per launch of a 2 M-point slab (ncu --set full, "
                                                   "profiles/r01_ncu_full_chain.txt); algorithmic: 8 MB written",
                                   "peak_source": pk["source"] + " bf16 sustained (kind::f16 runs at the bf16 rate)",
@@ -492,9 +492,11 @@ def run_ours(args):
                         "peak_source": pk["source"] + " bf16 sustained"}
             roof.update({"kernel": "%s, %d launches per step" % (names[dom], d_n),
                          "hbm_frac": f_h, "tensor_frac": f_t,
-                         "traffic": ncu_traffic(dom),
-                         "traffic_note": "DRAM bytes per launch from ncu --set full (profiles/r02_ncu_full_%s.txt) when "
-                                         "committed; compare algorithmic_bytes_per_launch" % dom,
+                         # the committed capture is of the default workload (womsk_white, 512 rays): no figure for others
+                         "traffic": ncu_traffic(dom) if (B == 512 and not depth and not pose) else None,
+                         "traffic_note": "DRAM bytes per launch, mean of the launches of one step, from ncu --set full of "
+                                         "this workload at 512 rays (profiles/r02_ncu_full_%s.txt); compare "
+                                         "algorithmic_bytes_per_launch" % dom,
                          "algorithmic_bytes_per_launch": d_by / max(1, d_n), "algorithmic_bytes_per_step": d_by,
                          "executed_flops_per_launch": d_fl / max(1, d_n), "kernel_ms": d_ms,
                          "launch_ms": d_ms / max(1, d_n), "tensor_view": tensor_view})
