@@ -894,9 +894,14 @@ chain_kernel(const __grid_constant__ Args a, int* __restrict__ fault, long long*
             }
             const uint32_t b0 = sW + ws * W_STAGE;
             const int nk = ph.nks - 4 * kb < 4 ? ph.nks - 4 * kb : 4;
-            for (int ks = 0; ks < nk; ++ks)
-              umma_f16_ts(tmem_base, tAcol + (uint32_t)(s * 128 + ph.a_col + kb * 32 + ks * 8), umma_desc_sw128(b0 + ks * 32),
-                          idesc, (j | ks) ? 1u : 0u);
+            // unrolled: the four descriptors are independent, so the issue rate is set by the MMA instructions themselves
+            // and not by a serial address computation per instruction (the issuer shares its scheduler with four
+            // epilogue warps)
+            const uint32_t a0c = tAcol + (uint32_t)(s * 128 + ph.a_col + kb * 32);
+            const uint64_t d0 = umma_desc_sw128(b0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              if (ks < nk) umma_f16_ts(tmem_base, a0c + (uint32_t)(ks * 8), d0 + (uint64_t)(ks * 2), idesc, (j | ks) ? 1u : 0u);
             if (s == 1 || !hasY || kb < nkb - keep) umma_commit(smem_u32(&w_empty[ws]));
           }
           umma_commit(smem_u32(&d_full));
