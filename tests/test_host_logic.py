@@ -125,3 +125,22 @@ def test_host_helpers_of_the_graph_capturable_step():
     assert ops._FORCE_REPACK is False
     with pytest.raises(_lib.VdnLibraryError):
         mods[1].forward_split(torch.zeros(4, 3))
+
+
+def test_committed_ncu_summaries_feed_the_bench_line():
+    """bench.py's `roofline.traffic` comes from the committed `ncu --set full` summary of the dominant kernel: the file must
+    parse, cover the eight chain launches of a step, and its DRAM bytes must be close to the algorithmic bytes the chains
+    are built to move (no re-reads) - the check that caught the software L2 prefetch doubling the reads."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    per_launch = bench.ncu_traffic("chain_train")
+    assert per_launch is not None
+    text = open(os.path.join(root, "profiles", "r02_ncu_full_chain_train.txt")).read()
+    assert text.count("== launch") == 8
+    assert "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum" in text      # tcgen05 MMAs were counted
+    algorithmic = 561610752.0            # bench.py: algorithmic_bytes_per_launch of the 512-ray womsk_white step
+    assert 0.9 < per_launch / algorithmic < 1.1, per_launch
+    assert bench.ncu_traffic("wgrad16") > 5e8 and bench.ncu_traffic("no_such_kernel") is None
