@@ -144,3 +144,30 @@ def test_committed_ncu_summaries_feed_the_bench_line():
     algorithmic = 561610752.0            # bench.py: algorithmic_bytes_per_launch of the 512-ray womsk_white step
     assert 0.9 < per_launch / algorithmic < 1.1, per_launch
     assert bench.ncu_traffic("wgrad16") > 5e8 and bench.ncu_traffic("no_such_kernel") is None
+
+
+def test_gradient_arena_hands_out_each_slot_once_per_step():
+    """ops.set_grad_arena / _grad_buffer (used by the weight-norm backward when dist.FlatGradAllReduce is active): a slot of
+    the flat all-reduce buffer is handed out as a fresh alias once per step and only while `.grad` is None; everything
+    else gets a private tensor, so repeated use of a network in one graph and gradient accumulation stay correct."""
+    a = torch.nn.Parameter(torch.zeros(4, 3))
+    b = torch.nn.Parameter(torch.zeros(5))
+    flat = torch.zeros(17)
+    views = [flat[:12].view(4, 3), flat[12:].view(5)]
+    try:
+        ops.set_grad_arena([a, b], views)
+        g1 = ops._grad_buffer(a)
+        assert g1.data_ptr() == views[0].data_ptr() and g1 is not views[0]        # an alias autograd may adopt
+        assert ops._grad_buffer(a).data_ptr() != views[0].data_ptr()               # second use in the same step: private
+        b.grad = torch.ones(5)
+        assert ops._grad_buffer(b).data_ptr() != views[1].data_ptr()               # accumulation: never the slot
+        b.grad = None
+        ops.reset_grad_arena_use()
+        assert ops._grad_buffer(a).data_ptr() == views[0].data_ptr()               # next step: handed out again
+        assert ops._grad_buffer(b).data_ptr() == views[1].data_ptr()
+        c = torch.nn.Parameter(torch.zeros(2, 2))
+        assert ops._grad_buffer(c).shape == (2, 2)                                 # not registered: private
+        ops.set_grad_arena([c], [flat[:6].view(2, 3)])
+        assert ops._grad_buffer(c).shape == (2, 2)                                 # stale entry of another shape: ignored
+    finally:
+        ops.set_grad_arena([], [])
