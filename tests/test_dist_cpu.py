@@ -89,3 +89,21 @@ def test_flat_grad_allreduce_single_process_paths():
     sync()
     assert sync.flat is flat and torch.equal(ps[1].grad, torch.ones(5))
     assert torch.equal(sync.flat, torch.cat([p.grad.reshape(-1) for p in ps]))
+
+
+def test_flat_grad_allreduce_leaves_in_place_gradients_alone():
+    """A gradient that already lives in its slot of the flat buffer (the weight-norm backward wrote it there, ops.set_grad_arena)
+    is neither packed nor unpacked: the collective runs on the buffer, `.grad` keeps aliasing it, the scale still applies."""
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
+    ps[0].grad = torch.full((3, 4), 2.0)
+    ps[1].grad = torch.ones(5)
+    sync = vdist.FlatGradAllReduce(ps)
+    sync()
+    v0 = sync._views[0]
+    v0.fill_(3.0)                       # what the backward would do: write the new gradient into the slot ...
+    ps[0].grad = v0.view_as(v0)         # ... and autograd adopts the alias
+    ps[1].grad = torch.full((5,), 7.0)  # a gradient produced elsewhere still goes through the copies
+    sync(scale=0.5)
+    assert ps[0].grad.data_ptr() == v0.data_ptr()
+    assert torch.equal(ps[0].grad, torch.full((3, 4), 1.5)) and torch.equal(ps[1].grad, torch.full((5,), 3.5))
+    assert torch.equal(sync.flat, torch.cat([p.grad.reshape(-1) for p in ps]))
