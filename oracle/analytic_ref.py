@@ -406,3 +406,97 @@ def sdf_normals_chain_emulated(p, x, spec: vo.SDFSpec) -> torch.Tensor:
     de = a + (de_skip if de_skip is not None else 0.0)
     J = embed_jac(y, spec.multires)
     return torch.einsum("nc,ncj->nj", de, J)
+
+
+def loss_scale(*cots) -> float:
+    """sigma = 2^-e with the largest |cotangent| in [2^(e-1), 2^e) (csrc/sdf_chains.cuh: amax_sigma_kernel); 1 for all-zero."""
+    am = max(float(c.abs().max()) for c in cots if c is not None)
+    if not (am > 0.0) or math.isinf(am):
+        return 1.0
+    _, e = math.frexp(am)
+    return 2.0 ** -max(-100, min(100, e))
+
+
+def sdf_backward_emulated(p, x, spec: vo.SDFSpec, d_sdf, d_feat, d_n, sigma=None):
+    """The two-phase SDF backward of `sdf_passes` with the STORAGE ROUNDING of the fused chains (csrc/sdf_chains.cuh): fp16
+    weights; every tensor the chains keep in 16 bits rounded to fp16 where the kernel stores it - the saved activations
+    a' (from which softplus' and softplus'' are recomputed), the normals-pass deltas, and the cotangent tensors q-bar,
+    z-bar^g, z-bar, which hold `sigma` times the true value (saturating at the fp16 range).  Products and sums are exact
+    (fp64): this isolates what the 16-bit formats and the loss scale cost.  sigma None: the kernel's choice; 1.0: what
+    an unscaled fp16 backward would do.  Returns (dW list, db list)."""
+    dt = torch.float64
+    h16 = lambda a: a.to(torch.float16).to(dt)                                   # round to nearest, fp16 range
+
+    def c16(a, s):                                                               # cotangent storage: fp16(sigma * a) / sigma
+        return (a * s).clamp(-65504.0, 65504.0).to(torch.float16).to(dt) / s
+    L = spec.n_lin
+    skip = spec.skip_in[0] if len(spec.skip_in) else -1
+    W = [h16(vo.effective_weight(p, f"lin{l}").to(dt)) for l in range(L)]
+    b = [p[f"lin{l}.bias"].to(dt) for l in range(L)]
+    y = x.to(dt) * spec.scale
+    e = vo.embed(y, spec.multires)
+    er = h16(e * B2) / B2                                                        # E16 holds kB2 * e
+    d_e = e.shape[1]
+    if sigma is None:
+        # |J_e n-bar| <= 2^multires |n-bar| (sdf_chain_backward's bound)
+        sigma = loss_scale(d_feat, None if d_sdf is None else d_sdf / spec.scale,
+                           None if d_n is None else d_n * float(2 ** spec.multires))
+    # forward with rounded saved activations; S1 = softplus' recomputed from the saved a' = kB2 * softplus(z)
+    H, U, S1 = [], [], []
+    h = er
+    for l in range(L):
+        u = torch.cat([h, er], 1) * INV_SQRT2 if l == skip else h
+        U.append(u)
+        z = u @ W[l].T + b[l]
+        if l < L - 1:
+            a = h16(sp(z) * B2)                                                  # A16_l
+            h = a / B2
+            H.append(h)
+            S1.append(1.0 - torch.exp2(-a))
+    # normals pass with rounded deltas (D16_l)
+    G = [None] * (L + 1)
+    row = W[L - 1][0:1, :]
+    D = [None] * (L - 1)
+
+    def gin(l):
+        if l == L - 2:
+            return row.expand(x.shape[0], -1)
+        g = G[l + 1]
+        return g[:, : W[l].shape[0]] * INV_SQRT2 if l + 1 == skip else g
+    for l in range(L - 2, -1, -1):
+        D[l] = h16(S1[l] * gin(l))
+        G[l] = D[l] @ W[l]
+    J = embed_jac(y, spec.multires)
+    dW = [torch.zeros_like(w) for w in W]
+    db = [torch.zeros_like(v) for v in b]
+    ZG = [None] * (L - 1)
+    # phase 1: q-bar_l and z-bar^g_l are stored (Q16, ZG16)
+    if d_n is not None:
+        deb = c16(torch.einsum("ncj,nj->nc", J, d_n.to(dt)), sigma)
+        qbar = deb
+        for l in range(L - 1):
+            dbar = qbar @ W[l].T
+            dW[l] += D[l].T @ qbar
+            ZG[l] = c16(100.0 * (1.0 - S1[l]) * D[l] * dbar, sigma)             # softplus''(z) * gin = 100 (1 - S) delta
+            nxt = S1[l] * dbar
+            qbar = c16(torch.cat([nxt * INV_SQRT2, deb * INV_SQRT2], 1) if l + 1 == skip else nxt, sigma)
+        dW[L - 1][0] += qbar.sum(0)
+    # phase 2: z-bar_l is stored (FB16 / SB, ZB16)
+    zl = torch.zeros(x.shape[0], W[-1].shape[0], dtype=dt)
+    if d_sdf is not None:
+        zl[:, 0] = d_sdf.reshape(-1).to(dt) / spec.scale
+    if d_feat is not None:
+        zl[:, 1:] = d_feat.to(dt)
+    zbar = c16(zl, sigma)
+    for l in range(L - 1, -1, -1):
+        dW[l] += zbar.T @ U[l]
+        db[l] += zbar.sum(0)
+        if l == 0:
+            break
+        ubar = zbar @ W[l]
+        hbar = ubar[:, : H[l - 1].shape[1]] * INV_SQRT2 if l == skip else ubar
+        zb = S1[l - 1] * hbar
+        if ZG[l - 1] is not None:
+            zb = zb + ZG[l - 1]
+        zbar = c16(zb, sigma)
+    return dW, db

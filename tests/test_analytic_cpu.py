@@ -182,3 +182,33 @@ def test_fused_chain_normals_arithmetic_with_bf16_saved_activations():
     errn = float((gotn - wantn).abs().max() / wantn.abs().max())
     print(f"fused-chain normals (CPU emulation, bf16 saved activations) rel err {errn:.2e}")
     assert errn < 2e-3
+
+
+@pytest.mark.parametrize("cot_scale", [1.0, 1e-6])
+def test_loss_scaled_fp16_backward_error_budget(cot_scale):
+    """The fused backward chains store every cotangent tensor in fp16 times a per-call power-of-two loss scale
+    (csrc/sdf_chains.cuh).  Emulated on the CPU at the reference's initialisation (storage rounding only, exact sums):
+    parameter gradients stay within the chain tolerance of the fp64 analytic backward whatever the magnitude of the
+    incoming cotangents - while an UNSCALED fp16 backward of cotangents of the size a 512-ray step really produces
+    (1e-6 and below) loses them to underflow."""
+    from tests import util
+    mods, conf = util.build("womsk_white")
+    nets = util.oracle_nets(mods, conf, dtype=torch.float64)
+    p, spec = nets.sdf, nets.sdf_spec
+    g = torch.Generator().manual_seed(5)
+    n = 600
+    x = (torch.rand(n, 3, generator=g) * 2.0 - 1.0).double()
+    d_sdf = torch.randn(n, 1, generator=g).double() * cot_scale
+    d_feat = torch.randn(n, 256, generator=g).double() * 0.1 * cot_scale
+    d_n = torch.randn(n, 3, generator=g).double() * cot_scale
+    with torch.no_grad():
+        _, _, dW, db, _ = ar.sdf_passes(p, x, spec, d_sdf, d_feat, d_n, want_dx=False)
+        dWs, dbs = ar.sdf_backward_emulated(p, x, spec, d_sdf, d_feat, d_n)
+        dW1, db1 = ar.sdf_backward_emulated(p, x, spec, d_sdf, d_feat, d_n, sigma=1.0)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    worst = max(max(rel(a, b) for a, b in zip(dWs, dW)), max(rel(a, b) for a, b in zip(dbs, db)))
+    worst1 = max(max(rel(a, b) for a, b in zip(dW1, dW)), max(rel(a, b) for a, b in zip(db1, db)))
+    print(f"cotangents x {cot_scale:g}: loss-scaled fp16 backward rel err {worst:.2e}, unscaled {worst1:.2e}")
+    assert worst < 1e-2
+    if cot_scale < 1e-3:
+        assert worst1 > 10 * worst           # without the scale the small cotangents are flushed / badly quantised
